@@ -1,0 +1,555 @@
+/*
+ * SPEC ORACLE — test infrastructure, NOT product code, NOT the reference matcher.
+ * PARITY UNPINNED: /root/reference holds only README.md:1 ("# GTSAM-NDT"); there is no
+ * reference arithmetic to follow. Each function below cites the SPEC.md section it
+ * restates. Scalar loops, f32 per point, f64 sums; see ndt2d_oracle.h for who may call it.
+ *
+ * Build: see oracle/Makefile (-O2 -ffp-contract=off -mfma: fmaf() is one rounding,
+ * nothing else is contracted).
+ */
+#include "ndt2d_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+    float res, st, inv_st, ox, oy;
+    int ov, nhx, nhy, njx, njy;
+    uint32_t *n;  /* per cell */
+    int64_t *s;   /* 5 per cell: sx sy sxx sxy syy */
+    float *cells; /* 8 per cell */
+} level_t;
+
+struct oracle_matcher {
+    oracle_params prm;
+    int nlevels;
+    float res[ORACLE_MAX_LEVELS];
+    int explicit_grid;
+    float gox, goy, gex, gey;
+    int has_target;
+    level_t lv[ORACLE_MAX_LEVELS];
+};
+
+/* ---------------------------------------------------------------- helpers */
+
+static uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+static void level_free(level_t *L)
+{
+    free(L->n); free(L->s); free(L->cells);
+    L->n = NULL; L->s = NULL; L->cells = NULL;
+}
+
+void oracle_default_params(oracle_params *p)
+{
+    /* SPEC 1 defaults */
+    p->eig_ratio = 0.001; p->eps_trans = 1e-4; p->eps_rot = 1e-5;
+    p->max_step_trans = 0.5; p->max_step_rot = 0.2;
+    p->lambda_init = 1e-3; p->lambda_min = 1e-9; p->lambda_max = 1e7;
+    p->min_points = 3; p->max_iterations = 30; p->overlap = 0; p->reserved = 0;
+}
+
+oracle_matcher *oracle_create(void)
+{
+    oracle_matcher *m = (oracle_matcher *)calloc(1, sizeof(*m));
+    if (!m) return NULL;
+    oracle_default_params(&m->prm);
+    m->nlevels = 1; m->res[0] = 1.0f;
+    return m;
+}
+
+static void drop_target(oracle_matcher *m)
+{
+    for (int l = 0; l < ORACLE_MAX_LEVELS; ++l) level_free(&m->lv[l]);
+    m->has_target = 0;
+}
+
+void oracle_destroy(oracle_matcher *m)
+{
+    if (!m) return;
+    drop_target(m);
+    free(m);
+}
+
+int oracle_set_params(oracle_matcher *m, const oracle_params *p)
+{
+    if (p->min_points < 2 || p->max_iterations < 1 || (p->overlap != 0 && p->overlap != 1)) return 1;
+    if (m->has_target && p->overlap != m->prm.overlap) drop_target(m);
+    m->prm = *p;
+    return 0;
+}
+
+int oracle_set_resolutions(oracle_matcher *m, const float *res, int nlevels)
+{
+    if (nlevels < 1 || nlevels > ORACLE_MAX_LEVELS) return 1;
+    for (int l = 0; l < nlevels; ++l) if (!(res[l] > 0.0f) || res[l] > 8.0f) return 1;
+    drop_target(m);
+    m->nlevels = nlevels;
+    for (int l = 0; l < nlevels; ++l) m->res[l] = res[l];
+    return 0;
+}
+
+int oracle_set_grid(oracle_matcher *m, float ox, float oy, float ex, float ey)
+{
+    drop_target(m);
+    m->explicit_grid = (ex > 0.0f && ey > 0.0f);
+    m->gox = ox; m->goy = oy; m->gex = ex; m->gey = ey;
+    return 0;
+}
+
+/* SPEC 2: geometry of one level, explicit or auto-fit */
+static int level_setup(oracle_matcher *m, int l, const float *xy, int n)
+{
+    level_t *L = &m->lv[l];
+    level_free(L);
+    L->res = m->res[l];
+    L->ov = m->prm.overlap;
+    L->st = L->ov ? L->res * 0.5f : L->res;
+    L->inv_st = 1.0f / L->st;
+    if (m->explicit_grid) {
+        L->ox = m->gox; L->oy = m->goy;
+        L->nhx = (int)ceilf(m->gex / L->st);
+        L->nhy = (int)ceilf(m->gey / L->st);
+    } else {
+        float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+        for (int i = 0; i < n; ++i) {
+            float x = xy[2 * i], y = xy[2 * i + 1];
+            if (!isfinite(x) || !isfinite(y)) continue;
+            if (x < xmin) xmin = x;
+            if (x > xmax) xmax = x;
+            if (y < ymin) ymin = y;
+            if (y > ymax) ymax = y;
+        }
+        if (!(xmin <= xmax)) { xmin = xmax = ymin = ymax = 0.0f; }
+        L->ox = floorf(xmin / L->res) * L->res - L->res;
+        L->oy = floorf(ymin / L->res) * L->res - L->res;
+        L->nhx = (int)ceilf((xmax - L->ox) / L->st) + 2;
+        L->nhy = (int)ceilf((ymax - L->oy) / L->st) + 2;
+    }
+    if (L->nhx < 1 || L->nhy < 1) return 1;
+    L->njx = L->nhx + L->ov;
+    L->njy = L->nhy + L->ov;
+    size_t nc = (size_t)L->njx * (size_t)L->njy;
+    L->n = (uint32_t *)calloc(nc, sizeof(uint32_t));
+    L->s = (int64_t *)calloc(nc * 5, sizeof(int64_t));
+    L->cells = (float *)calloc(nc * 8, sizeof(float));
+    return (L->n && L->s && L->cells) ? 0 : 2;
+}
+
+/* SPEC 2: lattice index; returns 0 when outside */
+static int lattice(const level_t *L, float X, float Y, int *hx, int *hy)
+{
+    float fx = (X - L->ox) * L->inv_st;
+    float fy = (Y - L->oy) * L->inv_st;
+    if (!((fx >= 0.0f) && (fx < (float)L->nhx) && (fy >= 0.0f) && (fy < (float)L->nhy))) return 0;
+    *hx = (int)fx; *hy = (int)fy;
+    return 1;
+}
+
+/* SPEC 3: integer accumulation of one point into its K cells */
+static void accumulate(level_t *L, const float *xy, int n)
+{
+    const int K = L->ov ? 2 : 1;
+    for (int i = 0; i < n; ++i) {
+        float X = xy[2 * i], Y = xy[2 * i + 1];
+        int hx, hy;
+        if (!lattice(L, X, Y, &hx, &hy)) continue;
+        for (int b = 0; b < K; ++b) for (int a = 0; a < K; ++a) {
+            int jx = hx + a, jy = hy + b;
+            double cx = (double)L->ox + ((double)(jx - L->ov)) * (double)L->st + 0.5 * (double)L->res;
+            double cy = (double)L->oy + ((double)(jy - L->ov)) * (double)L->st + 0.5 * (double)L->res;
+            double dx = (double)X - cx, dy = (double)Y - cy;
+            int64_t qx = llrint(dx * 1048576.0), qy = llrint(dy * 1048576.0);
+            size_t c = (size_t)jy * (size_t)L->njx + (size_t)jx;
+            L->n[c] += 1;
+            int64_t *s = L->s + 5 * c;
+            s[0] += qx; s[1] += qy; s[2] += qx * qx; s[3] += qx * qy; s[4] += qy * qy;
+        }
+    }
+}
+
+/* SPEC 3: finalisation of every cell */
+static void finalize(level_t *L, const oracle_params *P)
+{
+    const double U = 1.0 / 1048576.0;
+    for (int jy = 0; jy < L->njy; ++jy) for (int jx = 0; jx < L->njx; ++jx) {
+        size_t c = (size_t)jy * (size_t)L->njx + (size_t)jx;
+        float *rec = L->cells + 8 * c;
+        memset(rec, 0, 8 * sizeof(float));
+        uint32_t n = L->n[c];
+        if (n < (uint32_t)P->min_points) continue;
+        const int64_t *s = L->s + 5 * c;
+        double N = (double)n;
+        double mx = (double)s[0] / N, my = (double)s[1] / N;
+        double cxx = ((double)s[2] - (double)s[0] * mx) / (N - 1.0);
+        double cxy = ((double)s[3] - (double)s[0] * my) / (N - 1.0);
+        double cyy = ((double)s[4] - (double)s[1] * my) / (N - 1.0);
+        mx *= U; my *= U; cxx *= U * U; cxy *= U * U; cyy *= U * U;
+        double tr = cxx + cyy, hd = 0.5 * (cxx - cyy), rad = sqrt(hd * hd + cxy * cxy);
+        double l1 = 0.5 * tr + rad, l2 = 0.5 * tr - rad;
+        if (!(l1 > 1e-10)) continue;
+        if (l2 < P->eig_ratio * l1) {
+            double l2n = P->eig_ratio * l1, vx, vy;
+            if (hd >= 0.0) { vx = hd + rad; vy = cxy; } else { vx = cxy; vy = rad - hd; }
+            double nn = vx * vx + vy * vy, dl = l1 - l2n;
+            cxx = l2n + dl * (vx * vx) / nn;
+            cxy = dl * (vx * vy) / nn;
+            cyy = l2n + dl * (vy * vy) / nn;
+        }
+        double det = cxx * cyy - cxy * cxy;
+        double cx = (double)L->ox + ((double)(jx - L->ov)) * (double)L->st + 0.5 * (double)L->res;
+        double cy = (double)L->oy + ((double)(jy - L->ov)) * (double)L->st + 0.5 * (double)L->res;
+        rec[0] = (float)(cx + mx); rec[1] = (float)(cy + my);
+        rec[2] = (float)(cyy / det); rec[3] = (float)(-(cxy / det)); rec[4] = (float)(cxx / det);
+        rec[5] = (float)det; rec[6] = (float)n; rec[7] = 1.0f;
+    }
+}
+
+int oracle_set_target(oracle_matcher *m, const float *xy, int n)
+{
+    drop_target(m);
+    for (int l = 0; l < m->nlevels; ++l) {
+        int rc = level_setup(m, l, xy, n);
+        if (rc) { drop_target(m); return rc; }
+        accumulate(&m->lv[l], xy, n);
+        finalize(&m->lv[l], &m->prm);
+    }
+    m->has_target = 1;
+    return 0;
+}
+
+/* SPEC 7 */
+int oracle_add_target(oracle_matcher *m, const float *xy, int n)
+{
+    if (!m->has_target) return oracle_set_target(m, xy, n);
+    for (int l = 0; l < m->nlevels; ++l) {
+        accumulate(&m->lv[l], xy, n);
+        finalize(&m->lv[l], &m->prm);
+    }
+    return 0;
+}
+
+static const level_t *get_level(const oracle_matcher *m, int level)
+{
+    if (!m->has_target || level < 0 || level >= m->nlevels) return NULL;
+    return &m->lv[level];
+}
+
+int oracle_level_geometry(const oracle_matcher *m, int level, float out[5], int32_t dims[4])
+{
+    const level_t *L = get_level(m, level);
+    if (!L) return 1;
+    out[0] = L->res; out[1] = L->st; out[2] = L->inv_st; out[3] = L->ox; out[4] = L->oy;
+    dims[0] = L->nhx; dims[1] = L->nhy; dims[2] = L->njx; dims[3] = L->njy;
+    return 0;
+}
+
+int oracle_get_cells(const oracle_matcher *m, int level, float *cells)
+{
+    const level_t *L = get_level(m, level);
+    if (!L) return 1;
+    memcpy(cells, L->cells, (size_t)L->njx * L->njy * 8 * sizeof(float));
+    return 0;
+}
+
+int oracle_get_sums(const oracle_matcher *m, int level, uint32_t *n, int64_t *sums)
+{
+    const level_t *L = get_level(m, level);
+    if (!L) return 1;
+    size_t nc = (size_t)L->njx * L->njy;
+    memcpy(n, L->n, nc * sizeof(uint32_t));
+    memcpy(sums, L->s, nc * 5 * sizeof(int64_t));
+    return 0;
+}
+
+/* SPEC 4: pose to f32 */
+typedef struct { float c, s, tx, ty; } pose32;
+static pose32 pose_to_f32(const double p[3])
+{
+    pose32 q;
+    q.c = (float)cos(p[2]); q.s = (float)sin(p[2]);
+    q.tx = (float)p[0]; q.ty = (float)p[1];
+    return q;
+}
+
+int oracle_cell_index(const oracle_matcher *m, int level, const float *xy, int n,
+                      const double *pose, int32_t *idx)
+{
+    const level_t *L = get_level(m, level);
+    if (!L) return 1;
+    pose32 q = {1.0f, 0.0f, 0.0f, 0.0f};
+    if (pose) q = pose_to_f32(pose);
+    for (int i = 0; i < n; ++i) {
+        float x = xy[2 * i], y = xy[2 * i + 1], X = x, Y = y;
+        if (pose) {
+            float rx = fmaf(q.c, x, -(q.s * y)), ry = fmaf(q.s, x, q.c * y);
+            X = rx + q.tx; Y = ry + q.ty;
+        }
+        int hx, hy;
+        idx[i] = lattice(L, X, Y, &hx, &hy) ? hy * L->nhx + hx : -1;
+    }
+    return 0;
+}
+
+/* SPEC 4.1 */
+float oracle_expneg(float h)
+{
+    float z = h * 1.44269502f;
+    float t = z + 12582912.0f;
+    float nf = t - 12582912.0f;
+    int32_t ni = (int32_t)(f2u(t) - 0x4B400000u);
+    float r = fmaf(nf, -0.693145752f, h);
+    r = fmaf(nf, -1.42860677e-6f, r);
+    float y = -r;
+    float p = 1.38888889e-3f;
+    p = fmaf(p, y, 8.33333333e-3f);
+    p = fmaf(p, y, 4.16666667e-2f);
+    p = fmaf(p, y, 1.66666667e-1f);
+    p = fmaf(p, y, 0.5f);
+    p = fmaf(p, y, 1.0f);
+    p = fmaf(p, y, 1.0f);
+    return p * u2f((uint32_t)(0x3F800000 - ni * 0x800000));
+}
+
+/* SPEC 4: the ten f32 terms of one (point, cell) pair; returns 0 when skipped */
+static int pair_terms(const float *rec, float rx, float ry, float X, float Y, float T[10])
+{
+    if (rec[7] == 0.0f) return 0;
+    float mux = rec[0], muy = rec[1], B00 = rec[2], B01 = rec[3], B11 = rec[4];
+    float qx = X - mux, qy = Y - muy;
+    float ux = fmaf(B00, qx, B01 * qy), uy = fmaf(B01, qx, B11 * qy);
+    float mm = fmaf(qx, ux, qy * uy), h = 0.5f * mm;
+    if (!(h < 30.0f)) return 0;
+    float e = oracle_expneg(h);
+    float a2 = fmaf(uy, rx, -(ux * ry));
+    float vx = fmaf(B01, rx, -(B00 * ry)), vy = fmaf(B11, rx, -(B01 * ry));
+    float w = fmaf(ux, rx, uy * ry);
+    float k = fmaf(rx, vy, -(ry * vx));
+    k = k - w;
+    k = fmaf(-a2, a2, k);
+    T[0] = e;
+    T[1] = e * ux; T[2] = e * uy; T[3] = e * a2;
+    T[4] = e * fmaf(-ux, ux, B00); T[5] = e * fmaf(-ux, uy, B01); T[6] = e * fmaf(-ux, a2, vx);
+    T[7] = e * fmaf(-uy, uy, B11); T[8] = e * fmaf(-uy, a2, vy); T[9] = e * k;
+    return 1;
+}
+
+/* SPEC 4: evaluate; terms_out (optional) gets n*K*10 f32 */
+static void evaluate_level(const level_t *L, const float *xy, int n, const double pose[3],
+                           double out[10], int32_t *count, float *terms_out)
+{
+    pose32 q = pose_to_f32(pose);
+    const int K = L->ov ? 2 : 1;
+    double acc[10] = {0};
+    int32_t cnt = 0;
+    if (terms_out) memset(terms_out, 0, (size_t)n * K * K * 10 * sizeof(float));
+    for (int i = 0; i < n; ++i) {
+        float x = xy[2 * i], y = xy[2 * i + 1];
+        float rx = fmaf(q.c, x, -(q.s * y)), ry = fmaf(q.s, x, q.c * y);
+        float X = rx + q.tx, Y = ry + q.ty;
+        int hx, hy;
+        if (!lattice(L, X, Y, &hx, &hy)) continue;
+        for (int b = 0; b < K; ++b) for (int a = 0; a < K; ++a) {
+            const float *rec = L->cells + 8 * ((size_t)(hy + b) * L->njx + (size_t)(hx + a));
+            float T[10];
+            if (!pair_terms(rec, rx, ry, X, Y, T)) continue;
+            for (int t = 0; t < 10; ++t) acc[t] += (double)T[t];
+            if (terms_out) memcpy(terms_out + ((size_t)i * K * K + (size_t)(b * K + a)) * 10, T, sizeof(T));
+            cnt += 1;
+        }
+    }
+    memcpy(out, acc, sizeof(acc));
+    *count = cnt;
+}
+
+int oracle_evaluate(const oracle_matcher *m, int level, const float *xy, int n,
+                    const double pose[3], double out10[10], int32_t *count)
+{
+    const level_t *L = get_level(m, level);
+    if (!L) return 1;
+    evaluate_level(L, xy, n, pose, out10, count, NULL);
+    return 0;
+}
+
+int oracle_point_terms(const oracle_matcher *m, int level, const float *xy, int n,
+                       const double pose[3], float *terms)
+{
+    const level_t *L = get_level(m, level);
+    if (!L) return 1;
+    double out[10]; int32_t cnt;
+    evaluate_level(L, xy, n, pose, out, &cnt, terms);
+    return 0;
+}
+
+/* SPEC 5: damped 3x3 Cholesky solve. H6 = {H00,H01,H02,H11,H12,H22}. Returns 1 when solved. */
+int oracle_solve(const double g[3], const double H6[6], double lambda, double d[3])
+{
+    double A00 = H6[0] + lambda * fmax(fabs(H6[0]), 1e-9);
+    double A11 = H6[3] + lambda * fmax(fabs(H6[3]), 1e-9);
+    double A22 = H6[5] + lambda * fmax(fabs(H6[5]), 1e-9);
+    double A01 = H6[1], A02 = H6[2], A12 = H6[4];
+    double p0 = A00;
+    if (!(p0 > 0.0)) return 0;
+    double L00 = sqrt(p0);
+    double L10 = A01 / L00, L20 = A02 / L00;
+    double p1 = A11 - L10 * L10;
+    if (!(p1 > 0.0)) return 0;
+    double L11 = sqrt(p1);
+    double L21 = (A12 - L20 * L10) / L11;
+    double p2 = (A22 - L20 * L20) - L21 * L21;
+    if (!(p2 > 0.0)) return 0;
+    double L22 = sqrt(p2);
+    double y0 = -g[0] / L00;
+    double y1 = (-g[1] - L10 * y0) / L11;
+    double y2 = ((-g[2] - L20 * y0) - L21 * y1) / L22;
+    d[2] = y2 / L22;
+    d[1] = (y1 - L21 * d[2]) / L11;
+    d[0] = ((y0 - L10 * d[1]) - L20 * d[2]) / L00;
+    return 1;
+}
+
+typedef struct { double v[10]; int32_t count; } eval_t;
+
+/* SPEC 5: one pyramid level of Levenberg-Marquardt; updates p, E, returns status */
+static int align_level(const level_t *L, const oracle_params *P, const float *xy, int n,
+                       double p[3], eval_t *E, int *evals_total)
+{
+    double lambda = P->lambda_init;
+    evaluate_level(L, xy, n, p, E->v, &E->count, NULL);
+    int evals = 1, status = 1;
+    if (n == 0 || E->count == 0) { *evals_total += evals; return 3; }
+    for (;;) {
+        if (evals >= P->max_iterations) break;
+        double d[3];
+        int stalled = 0;
+        while (!oracle_solve(&E->v[1], &E->v[4], lambda, d)) {
+            lambda = lambda * 10.0;
+            if (lambda > P->lambda_max) { stalled = 1; break; }
+        }
+        if (stalled) { status = 2; break; }
+        double nt = sqrt(d[0] * d[0] + d[1] * d[1]);
+        if (nt > P->max_step_trans) {
+            double sc = P->max_step_trans / nt;
+            d[0] *= sc; d[1] *= sc; d[2] *= sc; nt = P->max_step_trans;
+        }
+        if (fabs(d[2]) > P->max_step_rot) {
+            double sc = P->max_step_rot / fabs(d[2]);
+            d[0] *= sc; d[1] *= sc; d[2] *= sc; nt *= sc;
+        }
+        int small = (nt < P->eps_trans) && (fabs(d[2]) < P->eps_rot);
+        double pn[3] = {p[0] + d[0], p[1] + d[1], p[2] + d[2]};
+        eval_t En;
+        evaluate_level(L, xy, n, pn, En.v, &En.count, NULL);
+        evals += 1;
+        if (En.v[0] > E->v[0]) {
+            p[0] = pn[0]; p[1] = pn[1]; p[2] = pn[2];
+            *E = En;
+            lambda = fmax(lambda / 10.0, P->lambda_min);
+            if (small) { status = 0; break; }
+        } else {
+            if (small) { status = 0; break; }
+            lambda = lambda * 10.0;
+            if (lambda > P->lambda_max) { status = 2; break; }
+        }
+    }
+    *evals_total += evals;
+    return status;
+}
+
+int oracle_align(const oracle_matcher *m, const float *xy, int n, const double init[3],
+                 oracle_result *res)
+{
+    if (!m->has_target) return 1;
+    double p[3] = {init[0], init[1], init[2]};
+    eval_t E; memset(&E, 0, sizeof(E));
+    int evals = 0, status = 3;
+    for (int l = 0; l < m->nlevels; ++l)
+        status = align_level(&m->lv[l], &m->prm, xy, n, p, &E, &evals);
+    const double TWO_PI = 6.283185307179586476925286766559;
+    res->pose[0] = p[0]; res->pose[1] = p[1];
+    res->pose[2] = p[2] - TWO_PI * rint(p[2] / TWO_PI);
+    res->score = E.v[0];
+    res->grad[0] = E.v[1]; res->grad[1] = E.v[2]; res->grad[2] = E.v[3];
+    res->hessian[0] = E.v[4]; res->hessian[1] = E.v[5]; res->hessian[2] = E.v[6];
+    res->hessian[3] = E.v[5]; res->hessian[4] = E.v[7]; res->hessian[5] = E.v[8];
+    res->hessian[6] = E.v[6]; res->hessian[7] = E.v[8]; res->hessian[8] = E.v[9];
+    res->iterations = evals; res->status = status; res->count = E.count; res->reserved = 0;
+    return 0;
+}
+
+int oracle_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+int oracle_align_batch(const oracle_matcher *m, const float *xy, const int64_t *offsets, int nscans,
+                       const double *init, oracle_result *res, int nthreads)
+{
+    if (!m->has_target) return 1;
+    if (nthreads <= 0) nthreads = oracle_num_threads();
+    #pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+    for (int b = 0; b < nscans; ++b)
+        oracle_align(m, xy + 2 * offsets[b], (int)(offsets[b + 1] - offsets[b]), init + 3 * b, res + b);
+    return 0;
+}
+
+/* SPEC 6 */
+int oracle_sweep(const oracle_matcher *m, int level, const float *xy, int n, const float *hyp,
+                 int64_t nhyp, double *scores, int64_t *best_idx, double *best_score, int nthreads)
+{
+    const level_t *L = get_level(m, level);
+    if (!L) return 1;
+    if (nthreads <= 0) nthreads = oracle_num_threads();
+    int64_t bi = -1; double bs = -1.0;
+    #pragma omp parallel num_threads(nthreads)
+    {
+        int64_t lbi = -1; double lbs = -1.0;
+        #pragma omp for schedule(static)
+        for (int64_t j = 0; j < nhyp; ++j) {
+            double pose[3] = {(double)hyp[3 * j], (double)hyp[3 * j + 1], (double)hyp[3 * j + 2]};
+            double out[10]; int32_t cnt;
+            evaluate_level(L, xy, n, pose, out, &cnt, NULL);
+            if (scores) scores[j] = out[0];
+            if (out[0] > lbs) { lbs = out[0]; lbi = j; } /* static schedule: j ascending per thread */
+        }
+        #pragma omp critical
+        {
+            if (lbi >= 0 && (lbs > bs || (lbs == bs && lbi < bi))) { bs = lbs; bi = lbi; }
+        }
+    }
+    if (best_idx) *best_idx = bi;
+    if (best_score) *best_score = bs;
+    return 0;
+}
+
+/* SPEC 8 */
+int oracle_polar_to_points(const float *ranges_f32, const uint16_t *ranges_u16, int nbeams,
+                           double angle_min, double angle_inc, float range_scale,
+                           float range_min, float range_max, float *xy_out)
+{
+    int k = 0;
+    for (int i = 0; i < nbeams; ++i) {
+        float rho;
+        if (ranges_u16) {
+            if (ranges_u16[i] == 0) continue;
+            rho = (float)ranges_u16[i] * range_scale;
+        } else {
+            rho = ranges_f32[i];
+        }
+        if (!((rho >= range_min) && (rho <= range_max))) continue;
+        double phi = angle_min + (double)i * angle_inc;
+        float cb = (float)cos(phi), sb = (float)sin(phi);
+        xy_out[2 * k] = rho * cb; xy_out[2 * k + 1] = rho * sb;
+        ++k;
+    }
+    return k;
+}
