@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — NDT scan-matches/sec on the workload BASELINE.json's metric is quoted on.
+
+Workload (N = 1 and per rank for N > 1): BASELINE.json configs[1], "scan-to-map NDT align, 1080-beam scans vs
+200 x 200 m map at 0.25 m cells". One step = one batched align pass over `--scans` synthetic 1080-beam scans
+(SURVEY.md 8(d) generator) against the same map; every scan runs the full Levenberg-Marquardt loop of SPEC.md 5.
+
+  value   whole-job matches/s with scans, offsets and initial poses already resident in HBM
+  e2e     the same through the host-buffer C-ABI call (ndt2d_align_batch / _ranges): pinned host -> device copy
+          of the step's scans, kernel, device -> host copy of the results, all inside the timed region
+  roofline  Newton-step evaluations x algorithmic bytes (N*(8+32K)+92) / kernel time,
+          against the measured HBM copy bandwidth (MEASURED_PEAKS.json). It is a gather-traffic convention:
+          the cell table is L2-resident, so the fraction is not DRAM utilisation.
+  cpu_baseline  the CPU spec oracle (a port of SPEC.md; the reference mount holds no source) on the host cores
+
+--impl reference times that same CPU oracle as the reference arm (the reference's own matcher does not exist
+in /root/reference). Multi-GPU: independent scans are sharded per rank, no data-path collective.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "NDT scan-matches/sec (1080-pt 2D scans)"
+UNIT = "matches/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--scans", type=int, default=16384, help="scans per step per GPU (16384 x 1080 x 8 B = 141 MB > L2)")
+    ap.add_argument("--map-scans", type=int, default=2048, help="scans fused into the target map")
+    ap.add_argument("--res", type=float, nargs="+", default=[0.25])
+    ap.add_argument("--overlap", type=int, default=0)
+    ap.add_argument("--perturb", type=float, nargs=2, default=[0.03, 0.3], help="initial guess error: metres, degrees")
+    ap.add_argument("--input", default="xy", choices=["xy", "ranges_f32", "ranges_u16"], help="e2e input format")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="scans in the cpu_baseline sample (0: auto, about 10-20 s)")
+    ap.add_argument("--ref-scans", type=int, default=0, help="scans per step of the reference arm (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(args, rank, with_map=True, count=None):
+    """Synthetic scans for this rank (distinct trajectory slots per rank), the shared map, and initial guesses.
+    `count` < args.scans takes the first scans of the same workload (bounded CPU samples)."""
+    from gtsam_ndt_b200 import synth
+    world = max(1, args.gpus)
+    traj = args.scans * world
+    sc = synth.SCAN_1080
+    count = count or args.scans
+    ranges, poses = synth.scans(count, traj_len=traj, first=rank, step=world, **sc)
+    pert = synth.uniform3(count, first=rank * args.scans) * np.array([args.perturb[0], args.perturb[0], math.radians(args.perturb[1])])
+    init = poses + pert
+    map_xy = synth.make_map(args.map_scans, traj_len=args.map_scans, **sc) if with_map else None
+    return ranges, poses, init, map_xy
+
+
+def to_points(ranges):
+    """SPEC 8 conversion on the host; all 1080 beams return in this world, so the batch is rectangular."""
+    from gtsam_ndt_b200 import synth
+    sc = synth.SCAN_1080
+    cb, sb = synth.beam_table(sc["nbeams"], sc["angle_min"], sc["angle_inc"])
+    assert np.all(ranges > 0)
+    xy = np.stack([ranges * cb[None, :], ranges * sb[None, :]], axis=-1).astype(np.float32)
+    offsets = np.arange(ranges.shape[0] + 1, dtype=np.int64) * ranges.shape[1]
+    return xy.reshape(-1, 2), offsets
+
+
+def eval_bytes(npts, K):
+    return npts * (8 + 32 * K) + 12 + 80
+
+
+def run_reference(args):
+    """Reference arm: the CPU spec oracle (no upstream matcher exists in the mount), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from gtsam_ndt_b200 import synth
+    o = oracle.Oracle(args.res, overlap=args.overlap)
+    o.set_grid(-100.0, -100.0, 200.0, 200.0)
+    cores = o.num_threads()
+    nref = args.ref_scans or max(64, min(args.scans, 16 * cores))
+    ranges, poses, init, map_xy = make_workload(args, 0, count=nref)
+    o.set_target(map_xy)
+    xy, off = to_points(ranges)
+    for _ in range(max(1, min(args.warmup, 1))):
+        o.align_batch(xy, off, init)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = o.align_batch(xy, off, init)
+    dt = time.perf_counter() - t0
+    v = nref * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 per point, f64 sums", "data": "synthetic",
+            "config": workload_config(args, nref, extra={"sample": f"{nref} scans per step"}),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{nref} scans x {args.steps} steps, CPU spec oracle (SPEC.md port; reference mount has no source)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "mean_iterations": float(res["iterations"].mean()), "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, scans, extra=None):
+    K = 4 if args.overlap else 1
+    c = {"workload": "configs[1]: scan-to-map NDT align, 1080-beam scans vs 200x200 m map at %s m cells (K=%d), batch of %d scans per GPU per step"
+         % ("/".join(str(r) for r in args.res), K, scans),
+         "scans_per_step_per_gpu": scans, "points_per_scan": 1080, "cell_res_m": list(args.res), "K": K,
+         "map_points": args.map_scans * 1080, "init_error": {"trans_m": args.perturb[0], "rot_deg": args.perturb[1]},
+         "l2": "per-step scan input %.0f MB > 126 MB L2 (no flush needed); the 200x200 m cell table is L2-resident by design"
+               % (scans * 1080 * 8 / 1e6),
+         "parallelism": "independent scans sharded per GPU, no collective"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import gtsam_ndt_b200 as g
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != max(1, args.gpus):
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the NDT path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    K = 4 if args.overlap else 1
+
+    ranges, poses, init, map_xy = make_workload(args, rank)
+    xy, offsets = to_points(ranges)
+    B, npts = args.scans, 1080
+
+    stream = torch.cuda.current_stream()
+    m = g.NdtMatcher2D(args.res, device=local, stream=stream.cuda_stream, overlap=args.overlap)
+    m.set_grid(-100.0, -100.0, 200.0, 200.0)
+    t0 = time.perf_counter()
+    m.set_target(map_xy)
+    build_ms = (time.perf_counter() - t0) * 1e3
+
+    # device-resident inputs for `value`
+    d_xy = torch.from_numpy(xy).to(dev)
+    d_off = torch.from_numpy(offsets).to(dev)
+    d_init = torch.from_numpy(np.ascontiguousarray(init)).to(dev)
+    d_res = torch.zeros(B * 144, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        m.align_batch_device(d_xy, d_off, B, npts, d_init, d_res)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = m.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = m.kernel_launches - l0
+    res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=g.RESULT_DTYPE)
+    iters = res["iterations"].astype(np.int64)
+
+    # e2e: host buffers through the public C-ABI call, pinned memory, copies inside the timed region
+    if args.input == "xy":
+        h_in = torch.from_numpy(xy).pin_memory()
+        h_off = torch.from_numpy(offsets).pin_memory()
+    else:
+        if args.input == "ranges_u16":
+            r16 = np.round(ranges / 0.004).clip(1, 65535).astype(np.uint16)   # 4 mm quantisation, 262 m max
+            h_in = torch.from_numpy(r16).pin_memory()
+        else:
+            h_in = torch.from_numpy(ranges).pin_memory()
+    h_init = torch.from_numpy(np.ascontiguousarray(init)).pin_memory()
+    h_res = torch.zeros(B * 144, dtype=torch.uint8).pin_memory()
+    res_view = h_res.numpy().view(g.RESULT_DTYPE)
+    from gtsam_ndt_b200 import synth
+    sc = synth.SCAN_1080
+
+    def step_e2e():
+        if args.input == "xy":
+            m.align_batch(h_in.numpy(), h_off.numpy(), h_init.numpy(), out=res_view)
+        else:
+            m.align_batch_ranges(h_in.numpy(), sc["angle_min"], sc["angle_inc"], h_init.numpy(),
+                                 range_scale=0.004 if args.input == "ranges_u16" else 1.0, out=res_view)
+
+    for _ in range(args.warmup):
+        step_e2e()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record(stream)
+    sync_all()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), e2e_wall_ms)   # host-synchronous call: wall clock is the honest figure
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_iters_equal = bool(np.array_equal(res_view["iterations"], res["iterations"])) if args.input == "xy" else None
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        cnt = torch.tensor([float(iters.sum()), float(B)], dtype=torch.float64, device=dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        total_evals_per_step, total_scans = float(cnt[0]), float(cnt[1])
+    else:
+        total_evals_per_step, total_scans = float(iters.sum()), float(B)
+
+    if rank == 0:
+        hbm, peak_src = peaks()
+        value = total_scans * args.steps / (ms / 1e3)
+        e2e_value = total_scans * args.steps / (e2e_ms / 1e3)
+        # roofline of the dominant kernel (k_align), per launch on this rank
+        kernel_ms = ms / args.steps
+        alg_bytes = float(iters.sum()) * eval_bytes(npts, K)
+        achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+        in_bytes = h_in.numel() * h_in.element_size() + h_init.numel() * 8 + (h_off.numel() * 8 if args.input == "xy" else 0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 per point, f64 sums and solver", "data": "synthetic",
+            "config": workload_config(args, B),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(B * 144),
+                    "ms_per_step": e2e_ms / args.steps, "input": args.input, "api": "ndt2d_align_batch" + ("" if args.input == "xy" else "_ranges"),
+                    "iterations_equal_device_run": e2e_iters_equal},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "kernel": "k_align (whole LM loop per scan, one warp per scan)", "peak_source": peak_src,
+                         "convention": "gather traffic: every point read and 32 B cell gather counts, bytes/eval = N*(8+32K)+92; "
+                                       "cells are served by L1/L2, so this is not DRAM utilisation",
+                         "evals_per_launch": float(iters.sum()), "bytes_per_eval": eval_bytes(npts, K),
+                         "evals_per_s": total_evals_per_step * args.steps / (ms / 1e3)},
+            "mean_iterations": float(iters.mean()), "status_counts": np.bincount(res["status"], minlength=4).tolist(),
+            "map_build_ms": build_ms, "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            line["cpu_baseline"] = cpu_baseline(args, xy, offsets, init, map_xy, res)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, xy, offsets, init, map_xy, res_gpu):
+    """The CPU spec oracle on a bounded sample of the same workload, all host threads (reported, not the target)."""
+    import oracle
+    o = oracle.Oracle(args.res, overlap=args.overlap)
+    o.set_grid(-100.0, -100.0, 200.0, 200.0)
+    o.set_target(map_xy)
+    cores = o.num_threads()
+    probe = min(len(offsets) - 1, 8 * cores)
+    t0 = time.perf_counter()
+    o.align_batch(xy, offsets[: probe + 1], init[:probe])
+    rate = probe / (time.perf_counter() - t0)
+    n = args.cpu_sample or int(min(len(offsets) - 1, max(probe, rate * 12.0)))
+    t0 = time.perf_counter()
+    r = o.align_batch(xy, offsets[: n + 1], init[:n])
+    dt = time.perf_counter() - t0
+    dp = np.abs(r["pose"] - res_gpu["pose"][:n]).max()
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n} scans of the step, CPU spec oracle (SPEC.md port), {dt:.1f} s",
+            "max_abs_pose_diff_vs_gpu": float(dp), "iterations_equal": bool(np.array_equal(r["iterations"], res_gpu["iterations"][:n]))}
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -1,0 +1,736 @@
+// C-ABI layer of libndt2d.so (include/ndt2d.h): handle, device buffers, host<->device copies and
+// kernel launches. No CPU compute path exists here: without a CUDA device ndt2d_create fails.
+// Reference interface: none citable (/root/reference/README.md:1 is the whole mount); the entry points
+// implement the matcher operations BASELINE.json's north_star names.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "ndt2d_internal.h"
+
+using namespace ndt2d;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct LevelMem {
+    float4 *cells = nullptr;
+    uint32_t *cnt = nullptr;
+    unsigned long long *sums = nullptr;
+    void release()
+    {
+        if (cells) cudaFree(cells);
+        if (cnt) cudaFree(cnt);
+        if (sums) cudaFree(sums);
+        cells = nullptr; cnt = nullptr; sums = nullptr;
+    }
+};
+
+} // namespace
+
+struct ndt2d_matcher {
+    int device = 0;
+    bool own_stream = false;
+    LaunchCfg cfg{};
+    ndt2d_params prm{};
+    int nlevels = 1;
+    float res[NDT2D_MAX_LEVELS] = {1.0f};
+    bool explicit_grid = false;
+    float gox = 0, goy = 0, gex = 0, gey = 0;
+    bool has_target = false;
+    bool sums_valid = false;
+    LevelDev lv[NDT2D_MAX_LEVELS]{};
+    LevelMem mem[NDT2D_MAX_LEVELS];
+    DevBuf b_xy, b_off, b_init, b_res, b_pose, b_out, b_cnt, b_idx, b_terms, b_hyp, b_scores, b_tki, b_tkv, b_scratch,
+        b_counter, b_beams, b_ranges, b_box;
+    double beams_amin = 0, beams_ainc = 0;
+    int beams_n = 0;
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(ndt2d_matcher *m, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (m) m->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(m, call)                                                                                        \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(m, e_ == cudaErrorMemoryAllocation ? NDT2D_ENOMEM : NDT2D_ECUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e_));                                                           \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+void drop_target(ndt2d_matcher *m)
+{
+    for (int l = 0; l < NDT2D_MAX_LEVELS; ++l) {
+        m->mem[l].release();
+        m->lv[l] = LevelDev{};
+    }
+    m->has_target = false;
+    m->sums_valid = false;
+}
+
+// SPEC 2: geometry of level l. bbox = {xmin, ymin, xmax, ymax}, used for auto-fit only.
+int setup_level(ndt2d_matcher *m, int l, const float bbox[4])
+{
+    LevelDev &L = m->lv[l];
+    L = LevelDev{};
+    L.res = m->res[l];
+    L.ov = m->prm.overlap;
+    L.st = L.ov ? L.res * 0.5f : L.res;
+    L.inv_st = 1.0f / L.st;
+    if (m->explicit_grid) {
+        L.ox = m->gox; L.oy = m->goy;
+        L.nhx = (int)ceilf(m->gex / L.st);
+        L.nhy = (int)ceilf(m->gey / L.st);
+    } else {
+        float xmin = bbox[0], ymin = bbox[1], xmax = bbox[2], ymax = bbox[3];
+        if (!(xmin <= xmax)) { xmin = xmax = ymin = ymax = 0.0f; }
+        L.ox = floorf(xmin / L.res) * L.res - L.res;
+        L.oy = floorf(ymin / L.res) * L.res - L.res;
+        L.nhx = (int)ceilf((xmax - L.ox) / L.st) + 2;
+        L.nhy = (int)ceilf((ymax - L.oy) / L.st) + 2;
+    }
+    if (L.nhx < 1 || L.nhy < 1) return fail(m, NDT2D_EINVAL, "level %d: empty lattice (%d x %d)", l, L.nhx, L.nhy);
+    L.njx = L.nhx + L.ov;
+    L.njy = L.nhy + L.ov;
+    L.nhxf = (float)L.nhx;
+    L.nhyf = (float)L.nhy;
+    int64_t nc = (int64_t)L.njx * L.njy;
+    if (nc >= (int64_t)1 << 31) return fail(m, NDT2D_EINVAL, "level %d: %lld cells exceed 2^31", l, (long long)nc);
+    LevelMem &M = m->mem[l];
+    M.release();
+    CK(m, cudaMalloc(&M.cells, (size_t)nc * 32));
+    CK(m, cudaMalloc(&M.cnt, (size_t)nc * 4));
+    CK(m, cudaMalloc(&M.sums, (size_t)nc * 40));
+    CK(m, cudaMemsetAsync(M.cells, 0, (size_t)nc * 32, m->cfg.stream));
+    CK(m, cudaMemsetAsync(M.cnt, 0, (size_t)nc * 4, m->cfg.stream));
+    CK(m, cudaMemsetAsync(M.sums, 0, (size_t)nc * 40, m->cfg.stream));
+    L.cells = M.cells;
+    L.cnt = M.cnt;
+    L.sums = M.sums;
+    return NDT2D_OK;
+}
+
+int accumulate_and_finalize(ndt2d_matcher *m, const float2 *d_xy, int64_t n)
+{
+    for (int l = 0; l < m->nlevels; ++l) {
+        CK(m, launch_accumulate(m->cfg, m->lv[l], d_xy, n, &m->launches));
+        CK(m, launch_finalize(m->cfg, m->lv[l], m->mem[l].cells, m->prm, &m->launches));
+    }
+    return NDT2D_OK;
+}
+
+int check_level(ndt2d_matcher *m, int level)
+{
+    if (!m) return NDT2D_EINVAL;
+    if (!m->has_target) return fail(m, NDT2D_ENOTARGET, "no target set");
+    if (level < 0 || level >= m->nlevels) return fail(m, NDT2D_EINVAL, "level %d out of range [0, %d)", level, m->nlevels);
+    return NDT2D_OK;
+}
+
+int upload(ndt2d_matcher *m, DevBuf &b, const void *src, size_t bytes)
+{
+    CK(m, b.ensure(bytes ? bytes : 16));
+    if (bytes) CK(m, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, m->cfg.stream));
+    return NDT2D_OK;
+}
+
+// shared-memory slot capacity (points per warp) for the align kernel; 0 = read scans from global memory
+int align_cap_points(const ndt2d_matcher *m, int max_points)
+{
+    int cap = (max_points + 1) & ~1; // keep slots 16-byte aligned
+    if (cap < 2) cap = 2;
+    size_t bytes = (size_t)cap * sizeof(float2) * 8;
+    if (bytes > (size_t)m->cfg.max_smem_optin - 1024) return 0;
+    return cap;
+}
+
+void fill_align_args(ndt2d_matcher *m, AlignArgs &a)
+{
+    memset(&a, 0, sizeof(a));
+    for (int l = 0; l < m->nlevels; ++l) a.lv[l] = m->lv[l];
+    a.nlevels = m->nlevels;
+    a.prm = m->prm;
+    a.counter = m->b_counter.as<unsigned int>();
+}
+
+} // namespace
+
+extern "C" {
+
+int ndt2d_version(void) { return NDT2D_VERSION; }
+
+void ndt2d_default_params(ndt2d_params *p)
+{
+    if (!p) return;
+    p->eig_ratio = 0.01; p->eps_trans = 1e-4; p->eps_rot = 1e-5;
+    p->max_step_trans = 0.5; p->max_step_rot = 0.2;
+    p->lambda_init = 1e-3; p->lambda_min = 1e-9; p->lambda_max = 1e7;
+    p->lambda_up = 10.0; p->lambda_down = 5.0; p->lambda_fail_up = 3.0;
+    p->min_points = 3; p->max_iterations = 30; p->overlap = 0; p->reserved = 0;
+}
+
+int ndt2d_create_on_stream(int device, void *cuda_stream, ndt2d_matcher **out)
+{
+    if (!out) return fail(nullptr, NDT2D_EINVAL, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, NDT2D_ECUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, NDT2D_EINVAL, "device %d out of range [0, %d)", device, ndev);
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, NDT2D_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(nullptr, NDT2D_ECUDA, "device %d is sm_%d%d; libndt2d is built for sm_100a (B200) only", device, prop.major,
+                    prop.minor);
+    ndt2d_matcher *m = new ndt2d_matcher();
+    m->device = device;
+    m->cfg.sm_count = prop.multiProcessorCount;
+    m->cfg.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cuda_stream == (void *)-1) {
+        e = cudaStreamCreateWithFlags(&m->cfg.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete m;
+            return fail(nullptr, NDT2D_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        m->own_stream = true;
+    } else {
+        m->cfg.stream = (cudaStream_t)cuda_stream;
+    }
+    ndt2d_default_params(&m->prm);
+    if (m->b_counter.ensure(16) != cudaSuccess || m->b_box.ensure(16) != cudaSuccess ||
+        m->b_scratch.ensure(sizeof(unsigned long long) * (size_t)topk_scratch_words(m->cfg.sm_count)) != cudaSuccess) {
+        ndt2d_destroy(m);
+        return fail(nullptr, NDT2D_ENOMEM, "device allocation failed");
+    }
+    *out = m;
+    return NDT2D_OK;
+}
+
+int ndt2d_create(int device, ndt2d_matcher **out) { return ndt2d_create_on_stream(device, (void *)-1, out); }
+
+void ndt2d_destroy(ndt2d_matcher *m)
+{
+    if (!m) return;
+    DeviceGuard g(m->device);
+    cudaStreamSynchronize(m->cfg.stream);
+    drop_target(m);
+    DevBuf *bufs[] = {&m->b_xy, &m->b_off, &m->b_init, &m->b_res, &m->b_pose, &m->b_out, &m->b_cnt, &m->b_idx, &m->b_terms,
+                      &m->b_hyp, &m->b_scores, &m->b_tki, &m->b_tkv, &m->b_scratch, &m->b_counter, &m->b_beams, &m->b_ranges,
+                      &m->b_box};
+    for (DevBuf *b : bufs) b->release();
+    if (m->own_stream) cudaStreamDestroy(m->cfg.stream);
+    delete m;
+}
+
+const char *ndt2d_last_error(const ndt2d_matcher *m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+void *ndt2d_stream(const ndt2d_matcher *m) { return m ? (void *)m->cfg.stream : nullptr; }
+int64_t ndt2d_kernel_launches(const ndt2d_matcher *m) { return m ? m->launches : 0; }
+
+int ndt2d_synchronize(ndt2d_matcher *m)
+{
+    if (!m) return NDT2D_EINVAL;
+    DeviceGuard g(m->device);
+    CK(m, cudaStreamSynchronize(m->cfg.stream));
+    return NDT2D_OK;
+}
+
+int ndt2d_set_params(ndt2d_matcher *m, const ndt2d_params *p)
+{
+    if (!m || !p) return NDT2D_EINVAL;
+    if (p->min_points < 2 || p->max_iterations < 1 || (p->overlap != 0 && p->overlap != 1))
+        return fail(m, NDT2D_EINVAL, "bad params: min_points >= 2, max_iterations >= 1, overlap in {0,1}");
+    if (!(p->lambda_up > 1.0) || !(p->lambda_fail_up > 1.0) || !(p->lambda_down >= 1.0))
+        return fail(m, NDT2D_EINVAL, "bad params: lambda_up > 1, lambda_fail_up > 1, lambda_down >= 1");
+    DeviceGuard g(m->device);
+    if (m->has_target && p->overlap != m->prm.overlap) {
+        cudaStreamSynchronize(m->cfg.stream);
+        drop_target(m);
+    }
+    m->prm = *p;
+    return NDT2D_OK;
+}
+
+int ndt2d_get_params(const ndt2d_matcher *m, ndt2d_params *p)
+{
+    if (!m || !p) return NDT2D_EINVAL;
+    *p = m->prm;
+    return NDT2D_OK;
+}
+
+int ndt2d_set_resolutions(ndt2d_matcher *m, const float *res, int nlevels)
+{
+    if (!m || !res) return NDT2D_EINVAL;
+    if (nlevels < 1 || nlevels > NDT2D_MAX_LEVELS) return fail(m, NDT2D_EINVAL, "nlevels %d not in [1, %d]", nlevels, NDT2D_MAX_LEVELS);
+    for (int l = 0; l < nlevels; ++l)
+        if (!(res[l] > 0.0f) || res[l] > 8.0f) return fail(m, NDT2D_EINVAL, "resolution %g not in (0, 8] m", (double)res[l]);
+    DeviceGuard g(m->device);
+    cudaStreamSynchronize(m->cfg.stream);
+    drop_target(m);
+    m->nlevels = nlevels;
+    for (int l = 0; l < nlevels; ++l) m->res[l] = res[l];
+    return NDT2D_OK;
+}
+
+int ndt2d_set_resolution(ndt2d_matcher *m, float res) { return ndt2d_set_resolutions(m, &res, 1); }
+
+int ndt2d_set_grid(ndt2d_matcher *m, float ox, float oy, float ex, float ey)
+{
+    if (!m) return NDT2D_EINVAL;
+    DeviceGuard g(m->device);
+    cudaStreamSynchronize(m->cfg.stream);
+    drop_target(m);
+    m->explicit_grid = (ex > 0.0f && ey > 0.0f);
+    m->gox = ox; m->goy = oy; m->gex = ex; m->gey = ey;
+    return NDT2D_OK;
+}
+
+int ndt2d_set_target_device(ndt2d_matcher *m, const float *d_xy, int64_t n)
+{
+    if (!m || n < 0 || (n > 0 && !d_xy)) return m ? fail(m, NDT2D_EINVAL, "bad target arguments") : NDT2D_EINVAL;
+    DeviceGuard g(m->device);
+    CK(m, cudaStreamSynchronize(m->cfg.stream));
+    drop_target(m);
+    float bbox[4] = {0, 0, 0, 0};
+    if (!m->explicit_grid) {
+        int box[4];
+        CK(m, launch_bbox(m->cfg, reinterpret_cast<const float2 *>(d_xy), n, m->b_box.as<int>(), &m->launches));
+        CK(m, cudaMemcpyAsync(box, m->b_box.p, sizeof(box), cudaMemcpyDeviceToHost, m->cfg.stream));
+        CK(m, cudaStreamSynchronize(m->cfg.stream));
+        for (int i = 0; i < 4; ++i) bbox[i] = bbox_decode(box[i]);
+    }
+    for (int l = 0; l < m->nlevels; ++l) {
+        int rc = setup_level(m, l, bbox);
+        if (rc) {
+            drop_target(m);
+            return rc;
+        }
+    }
+    int rc = accumulate_and_finalize(m, reinterpret_cast<const float2 *>(d_xy), n);
+    if (rc) return rc;
+    m->has_target = true;
+    m->sums_valid = true;
+    return NDT2D_OK;
+}
+
+int ndt2d_add_target_device(ndt2d_matcher *m, const float *d_xy, int64_t n)
+{
+    if (!m || n < 0 || (n > 0 && !d_xy)) return m ? fail(m, NDT2D_EINVAL, "bad target arguments") : NDT2D_EINVAL;
+    if (!m->has_target) return ndt2d_set_target_device(m, d_xy, n);
+    if (!m->sums_valid) return fail(m, NDT2D_EINVAL, "target was loaded with ndt2d_set_cells; it has no sums to extend");
+    DeviceGuard g(m->device);
+    return accumulate_and_finalize(m, reinterpret_cast<const float2 *>(d_xy), n);
+}
+
+int ndt2d_set_target(ndt2d_matcher *m, const float *xy, int64_t n)
+{
+    if (!m || n < 0 || (n > 0 && !xy)) return m ? fail(m, NDT2D_EINVAL, "bad target arguments") : NDT2D_EINVAL;
+    DeviceGuard g(m->device);
+    int rc = upload(m, m->b_xy, xy, (size_t)n * 8);
+    if (rc) return rc;
+    rc = ndt2d_set_target_device(m, m->b_xy.as<float>(), n);
+    if (rc) return rc;
+    return ndt2d_synchronize(m);
+}
+
+int ndt2d_add_target(ndt2d_matcher *m, const float *xy, int64_t n)
+{
+    if (!m || n < 0 || (n > 0 && !xy)) return m ? fail(m, NDT2D_EINVAL, "bad target arguments") : NDT2D_EINVAL;
+    DeviceGuard g(m->device);
+    int rc = upload(m, m->b_xy, xy, (size_t)n * 8);
+    if (rc) return rc;
+    rc = ndt2d_add_target_device(m, m->b_xy.as<float>(), n);
+    if (rc) return rc;
+    return ndt2d_synchronize(m);
+}
+
+int ndt2d_level_geometry(const ndt2d_matcher *m, int level, float geom[5], int32_t dims[4])
+{
+    if (!m || !m->has_target || level < 0 || level >= m->nlevels) return NDT2D_EINVAL;
+    const LevelDev &L = m->lv[level];
+    geom[0] = L.res; geom[1] = L.st; geom[2] = L.inv_st; geom[3] = L.ox; geom[4] = L.oy;
+    dims[0] = L.nhx; dims[1] = L.nhy; dims[2] = L.njx; dims[3] = L.njy;
+    return NDT2D_OK;
+}
+
+int ndt2d_get_cells(ndt2d_matcher *m, int level, float *cells)
+{
+    int rc = check_level(m, level);
+    if (rc) return rc;
+    DeviceGuard g(m->device);
+    const LevelDev &L = m->lv[level];
+    CK(m, cudaMemcpyAsync(cells, L.cells, (size_t)L.njx * L.njy * 32, cudaMemcpyDeviceToHost, m->cfg.stream));
+    return ndt2d_synchronize(m);
+}
+
+int ndt2d_get_sums(ndt2d_matcher *m, int level, uint32_t *n, int64_t *sums)
+{
+    int rc = check_level(m, level);
+    if (rc) return rc;
+    if (!m->sums_valid) return fail(m, NDT2D_EINVAL, "target was loaded with ndt2d_set_cells; no sums");
+    DeviceGuard g(m->device);
+    const LevelDev &L = m->lv[level];
+    size_t nc = (size_t)L.njx * L.njy;
+    CK(m, cudaMemcpyAsync(n, L.cnt, nc * 4, cudaMemcpyDeviceToHost, m->cfg.stream));
+    CK(m, cudaMemcpyAsync(sums, L.sums, nc * 40, cudaMemcpyDeviceToHost, m->cfg.stream));
+    return ndt2d_synchronize(m);
+}
+
+const float *ndt2d_cells_device(const ndt2d_matcher *m, int level)
+{
+    if (!m || !m->has_target || level < 0 || level >= m->nlevels) return nullptr;
+    return reinterpret_cast<const float *>(m->lv[level].cells);
+}
+
+int ndt2d_set_cells(ndt2d_matcher *m, int level, const float *cells)
+{
+    if (!m || !cells) return NDT2D_EINVAL;
+    DeviceGuard g(m->device);
+    if (!m->has_target) {
+        if (!m->explicit_grid) return fail(m, NDT2D_EINVAL, "ndt2d_set_cells needs ndt2d_set_grid first");
+        float bbox[4] = {0, 0, 0, 0};
+        for (int l = 0; l < m->nlevels; ++l) {
+            int rc = setup_level(m, l, bbox);
+            if (rc) {
+                drop_target(m);
+                return rc;
+            }
+        }
+        m->has_target = true;
+    }
+    if (level < 0 || level >= m->nlevels) return fail(m, NDT2D_EINVAL, "level %d out of range", level);
+    m->sums_valid = false;
+    const LevelDev &L = m->lv[level];
+    CK(m, cudaMemcpyAsync(m->mem[level].cells, cells, (size_t)L.njx * L.njy * 32, cudaMemcpyHostToDevice, m->cfg.stream));
+    return ndt2d_synchronize(m);
+}
+
+int ndt2d_cell_index(ndt2d_matcher *m, int level, const float *xy, int n, const double *pose, int32_t *idx)
+{
+    int rc = check_level(m, level);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!xy || !idx))) return fail(m, NDT2D_EINVAL, "bad arguments");
+    if (n == 0) return NDT2D_OK;
+    DeviceGuard g(m->device);
+    if ((rc = upload(m, m->b_xy, xy, (size_t)n * 8))) return rc;
+    if (pose && (rc = upload(m, m->b_pose, pose, 24))) return rc;
+    CK(m, m->b_idx.ensure((size_t)n * 4));
+    CK(m, launch_cell_index(m->cfg, m->lv[level], m->b_xy.as<float2>(), n, pose ? m->b_pose.as<double>() : nullptr,
+                            m->b_idx.as<int32_t>(), &m->launches));
+    CK(m, cudaMemcpyAsync(idx, m->b_idx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, m->cfg.stream));
+    return ndt2d_synchronize(m);
+}
+
+int ndt2d_evaluate_device(ndt2d_matcher *m, int level, const float *d_xy, int n, const double *d_poses, int npose,
+                          double *d_out, int32_t *d_count)
+{
+    int rc = check_level(m, level);
+    if (rc) return rc;
+    if (n < 0 || npose < 0 || !d_out || (npose > 0 && !d_poses)) return fail(m, NDT2D_EINVAL, "bad arguments");
+    DeviceGuard g(m->device);
+    CK(m, launch_eval_poses(m->cfg, m->lv[level], reinterpret_cast<const float2 *>(d_xy), n, d_poses, 0, npose, 1, d_out, 10,
+                            d_count, &m->launches));
+    return NDT2D_OK;
+}
+
+int ndt2d_evaluate(ndt2d_matcher *m, int level, const float *xy, int n, const double *poses, int npose, double *out,
+                   int32_t *count)
+{
+    int rc = check_level(m, level);
+    if (rc) return rc;
+    if (n < 0 || npose < 0 || !out || (npose > 0 && !poses) || (n > 0 && !xy)) return fail(m, NDT2D_EINVAL, "bad arguments");
+    if (npose == 0) return NDT2D_OK;
+    DeviceGuard g(m->device);
+    if ((rc = upload(m, m->b_xy, xy, (size_t)n * 8))) return rc;
+    if ((rc = upload(m, m->b_pose, poses, (size_t)npose * 24))) return rc;
+    CK(m, m->b_out.ensure((size_t)npose * 80));
+    CK(m, m->b_cnt.ensure((size_t)npose * 4));
+    rc = ndt2d_evaluate_device(m, level, m->b_xy.as<float>(), n, m->b_pose.as<double>(), npose, m->b_out.as<double>(),
+                               m->b_cnt.as<int32_t>());
+    if (rc) return rc;
+    CK(m, cudaMemcpyAsync(out, m->b_out.p, (size_t)npose * 80, cudaMemcpyDeviceToHost, m->cfg.stream));
+    if (count) CK(m, cudaMemcpyAsync(count, m->b_cnt.p, (size_t)npose * 4, cudaMemcpyDeviceToHost, m->cfg.stream));
+    return ndt2d_synchronize(m);
+}
+
+int ndt2d_point_terms(ndt2d_matcher *m, int level, const float *xy, int n, const double *pose, float *terms)
+{
+    int rc = check_level(m, level);
+    if (rc) return rc;
+    if (n < 0 || !pose || (n > 0 && (!xy || !terms))) return fail(m, NDT2D_EINVAL, "bad arguments");
+    if (n == 0) return NDT2D_OK;
+    DeviceGuard g(m->device);
+    const int K = m->prm.overlap ? 4 : 1;
+    if ((rc = upload(m, m->b_xy, xy, (size_t)n * 8))) return rc;
+    if ((rc = upload(m, m->b_pose, pose, 24))) return rc;
+    CK(m, m->b_terms.ensure((size_t)n * K * 40));
+    CK(m, launch_point_terms(m->cfg, m->lv[level], m->b_xy.as<float2>(), n, m->b_pose.as<double>(), m->b_terms.as<float>(),
+                             &m->launches));
+    CK(m, cudaMemcpyAsync(terms, m->b_terms.p, (size_t)n * K * 40, cudaMemcpyDeviceToHost, m->cfg.stream));
+    return ndt2d_synchronize(m);
+}
+
+int ndt2d_align_batch_device(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, int nscans, int max_points,
+                             const double *d_init, ndt2d_result *d_res)
+{
+    if (!m) return NDT2D_EINVAL;
+    if (!m->has_target) return fail(m, NDT2D_ENOTARGET, "no target set");
+    if (nscans < 0 || max_points < 0 || (nscans > 0 && (!d_offsets || !d_init || !d_res)))
+        return fail(m, NDT2D_EINVAL, "bad arguments");
+    if (nscans == 0) return NDT2D_OK;
+    DeviceGuard g(m->device);
+    AlignArgs a;
+    fill_align_args(m, a);
+    a.xy = reinterpret_cast<const float2 *>(d_xy);
+    if (!a.xy) a.xy = m->b_counter.as<float2>(); // all scans empty: any non-null pointer selects the xy path
+    a.offsets = d_offsets;
+    a.init = d_init;
+    a.res = d_res;
+    a.nscans = nscans;
+    a.cap_points = align_cap_points(m, max_points);
+    CK(m, launch_align(m->cfg, a, &m->launches));
+    return NDT2D_OK;
+}
+
+int ndt2d_align_batch(ndt2d_matcher *m, const float *xy, const int64_t *offsets, int nscans, const double *init,
+                      ndt2d_result *res)
+{
+    if (!m) return NDT2D_EINVAL;
+    if (!m->has_target) return fail(m, NDT2D_ENOTARGET, "no target set");
+    if (nscans < 0 || (nscans > 0 && (!offsets || !init || !res))) return fail(m, NDT2D_EINVAL, "bad arguments");
+    if (nscans == 0) return NDT2D_OK;
+    int64_t maxn = 0;
+    for (int b = 0; b < nscans; ++b) {
+        int64_t nb = offsets[b + 1] - offsets[b];
+        if (nb < 0 || nb > 0x7fffffff) return fail(m, NDT2D_EINVAL, "offsets not monotone at scan %d", b);
+        if (nb > maxn) maxn = nb;
+    }
+    int64_t total = offsets[nscans];
+    if (offsets[0] < 0 || (total > 0 && !xy)) return fail(m, NDT2D_EINVAL, "bad offsets / xy");
+    DeviceGuard g(m->device);
+    int rc;
+    if ((rc = upload(m, m->b_xy, xy, (size_t)total * 8))) return rc;
+    if ((rc = upload(m, m->b_off, offsets, (size_t)(nscans + 1) * 8))) return rc;
+    if ((rc = upload(m, m->b_init, init, (size_t)nscans * 24))) return rc;
+    CK(m, m->b_res.ensure((size_t)nscans * sizeof(ndt2d_result)));
+    rc = ndt2d_align_batch_device(m, m->b_xy.as<float>(), m->b_off.as<int64_t>(), nscans, (int)maxn, m->b_init.as<double>(),
+                                  m->b_res.as<ndt2d_result>());
+    if (rc) return rc;
+    CK(m, cudaMemcpyAsync(res, m->b_res.p, (size_t)nscans * sizeof(ndt2d_result), cudaMemcpyDeviceToHost, m->cfg.stream));
+    return ndt2d_synchronize(m);
+}
+
+int ndt2d_align(ndt2d_matcher *m, const float *xy, int n, const double init[3], ndt2d_result *res)
+{
+    if (n < 0) return m ? fail(m, NDT2D_EINVAL, "n < 0") : NDT2D_EINVAL;
+    int64_t off[2] = {0, n};
+    return ndt2d_align_batch(m, xy, off, 1, init, res);
+}
+
+int ndt2d_align_batch_ranges_device(ndt2d_matcher *m, const void *d_ranges, int ranges_are_u16, int nscans, int nbeams,
+                                    double angle_min, double angle_inc, float range_scale, float range_min, float range_max,
+                                    const double *d_init, ndt2d_result *d_res)
+{
+    if (!m) return NDT2D_EINVAL;
+    if (!m->has_target) return fail(m, NDT2D_ENOTARGET, "no target set");
+    if (nscans < 0 || nbeams < 1 || (nscans > 0 && (!d_ranges || !d_init || !d_res)))
+        return fail(m, NDT2D_EINVAL, "bad arguments");
+    if (nscans == 0) return NDT2D_OK;
+    DeviceGuard g(m->device);
+    int cap = align_cap_points(m, nbeams);
+    if (cap == 0) return fail(m, NDT2D_EINVAL, "nbeams %d exceeds the shared-memory staging limit", nbeams);
+    // SPEC 8 beam table, computed on the host with libm in f64 and rounded once, then cached
+    if (m->beams_n != nbeams || m->beams_amin != angle_min || m->beams_ainc != angle_inc) {
+        std::vector<float> tab((size_t)nbeams * 2);
+        for (int i = 0; i < nbeams; ++i) {
+            double phi = angle_min + (double)i * angle_inc;
+            tab[2 * i] = (float)cos(phi);
+            tab[2 * i + 1] = (float)sin(phi);
+        }
+        int rc = upload(m, m->b_beams, tab.data(), tab.size() * 4);
+        if (rc) return rc;
+        CK(m, cudaStreamSynchronize(m->cfg.stream)); // tab goes out of scope
+        m->beams_n = nbeams; m->beams_amin = angle_min; m->beams_ainc = angle_inc;
+    }
+    AlignArgs a;
+    fill_align_args(m, a);
+    a.xy = nullptr;
+    a.ranges = d_ranges;
+    a.beams = m->b_beams.as<float2>();
+    a.ranges_u16 = ranges_are_u16 ? 1 : 0;
+    a.nbeams = nbeams;
+    a.range_scale = range_scale; a.range_min = range_min; a.range_max = range_max;
+    a.init = d_init;
+    a.res = d_res;
+    a.nscans = nscans;
+    a.cap_points = cap;
+    CK(m, launch_align(m->cfg, a, &m->launches));
+    return NDT2D_OK;
+}
+
+int ndt2d_align_batch_ranges(ndt2d_matcher *m, const void *ranges, int ranges_are_u16, int nscans, int nbeams,
+                             double angle_min, double angle_inc, float range_scale, float range_min, float range_max,
+                             const double *init, ndt2d_result *res)
+{
+    if (!m) return NDT2D_EINVAL;
+    if (!m->has_target) return fail(m, NDT2D_ENOTARGET, "no target set");
+    if (nscans < 0 || nbeams < 1 || (nscans > 0 && (!ranges || !init || !res))) return fail(m, NDT2D_EINVAL, "bad arguments");
+    if (nscans == 0) return NDT2D_OK;
+    DeviceGuard g(m->device);
+    int rc;
+    size_t rbytes = (size_t)nscans * nbeams * (ranges_are_u16 ? 2 : 4);
+    if ((rc = upload(m, m->b_ranges, ranges, rbytes))) return rc;
+    if ((rc = upload(m, m->b_init, init, (size_t)nscans * 24))) return rc;
+    CK(m, m->b_res.ensure((size_t)nscans * sizeof(ndt2d_result)));
+    rc = ndt2d_align_batch_ranges_device(m, m->b_ranges.p, ranges_are_u16, nscans, nbeams, angle_min, angle_inc, range_scale,
+                                         range_min, range_max, m->b_init.as<double>(), m->b_res.as<ndt2d_result>());
+    if (rc) return rc;
+    CK(m, cudaMemcpyAsync(res, m->b_res.p, (size_t)nscans * sizeof(ndt2d_result), cudaMemcpyDeviceToHost, m->cfg.stream));
+    return ndt2d_synchronize(m);
+}
+
+int ndt2d_sweep_device(ndt2d_matcher *m, int level, const float *d_xy, int n, const float *d_hyp, int64_t nhyp,
+                       double *d_scores, int k, int64_t *d_best_idx, double *d_best_score)
+{
+    int rc = check_level(m, level);
+    if (rc) return rc;
+    if (n < 0 || nhyp < 0 || k < 0 || k > 1024 || (nhyp > 0 && !d_hyp) || (k > 0 && (!d_best_idx || !d_best_score)))
+        return fail(m, NDT2D_EINVAL, "bad arguments");
+    DeviceGuard g(m->device);
+    if (!d_scores) {
+        CK(m, m->b_scores.ensure((size_t)(nhyp ? nhyp : 1) * 8));
+        d_scores = m->b_scores.as<double>();
+    }
+    CK(m, launch_eval_poses(m->cfg, m->lv[level], reinterpret_cast<const float2 *>(d_xy), n, d_hyp, 1, nhyp, 0, d_scores, 1,
+                            nullptr, &m->launches));
+    if (k > 0) CK(m, launch_topk(m->cfg, d_scores, nhyp, k, d_best_idx, d_best_score, m->b_scratch.as<unsigned long long>(), &m->launches));
+    return NDT2D_OK;
+}
+
+int ndt2d_sweep(ndt2d_matcher *m, int level, const float *xy, int n, const float *hyp, int64_t nhyp, double *scores, int k,
+                int64_t *best_idx, double *best_score)
+{
+    int rc = check_level(m, level);
+    if (rc) return rc;
+    if (n < 0 || nhyp < 0 || k < 0 || k > 1024 || (n > 0 && !xy) || (nhyp > 0 && !hyp) || (k > 0 && (!best_idx || !best_score)))
+        return fail(m, NDT2D_EINVAL, "bad arguments");
+    DeviceGuard g(m->device);
+    if ((rc = upload(m, m->b_xy, xy, (size_t)n * 8))) return rc;
+    if ((rc = upload(m, m->b_hyp, hyp, (size_t)nhyp * 12))) return rc;
+    CK(m, m->b_scores.ensure((size_t)(nhyp ? nhyp : 1) * 8));
+    CK(m, m->b_tki.ensure((size_t)(k ? k : 1) * 8));
+    CK(m, m->b_tkv.ensure((size_t)(k ? k : 1) * 8));
+    rc = ndt2d_sweep_device(m, level, m->b_xy.as<float>(), n, m->b_hyp.as<float>(), nhyp, m->b_scores.as<double>(), k,
+                            m->b_tki.as<int64_t>(), m->b_tkv.as<double>());
+    if (rc) return rc;
+    if (scores && nhyp) CK(m, cudaMemcpyAsync(scores, m->b_scores.p, (size_t)nhyp * 8, cudaMemcpyDeviceToHost, m->cfg.stream));
+    if (k > 0) {
+        CK(m, cudaMemcpyAsync(best_idx, m->b_tki.p, (size_t)k * 8, cudaMemcpyDeviceToHost, m->cfg.stream));
+        CK(m, cudaMemcpyAsync(best_score, m->b_tkv.p, (size_t)k * 8, cudaMemcpyDeviceToHost, m->cfg.stream));
+    }
+    return ndt2d_synchronize(m);
+}
+
+int ndt2d_relocalize(ndt2d_matcher *m, int level, const float *xy, int n, const float *hyp, int64_t nhyp, int k,
+                     int64_t *best_idx, ndt2d_result *res)
+{
+    if (!m) return NDT2D_EINVAL;
+    if (k < 1 || k > 1024 || !best_idx || !res) return fail(m, NDT2D_EINVAL, "bad arguments");
+    std::vector<double> best_score((size_t)k);
+    int rc = ndt2d_sweep(m, level, xy, n, hyp, nhyp, nullptr, k, best_idx, best_score.data());
+    if (rc) return rc;
+    // refine each of the k best with the full pyramid align; the scan is replicated k times
+    int kk = 0;
+    while (kk < k && best_idx[kk] >= 0) ++kk;
+    std::vector<float> rep((size_t)kk * n * 2);
+    std::vector<int64_t> off((size_t)kk + 1, 0);
+    std::vector<double> init((size_t)kk * 3);
+    for (int j = 0; j < kk; ++j) {
+        if (n) memcpy(rep.data() + (size_t)j * n * 2, xy, (size_t)n * 8);
+        off[j + 1] = (int64_t)(j + 1) * n;
+        for (int t = 0; t < 3; ++t) init[3 * j + t] = (double)hyp[3 * best_idx[j] + t];
+    }
+    rc = ndt2d_align_batch(m, rep.data(), off.data(), kk, init.data(), res);
+    if (rc) return rc;
+    for (int j = kk; j < k; ++j) {
+        memset(res + j, 0, sizeof(ndt2d_result));
+        res[j].status = NDT2D_NO_OVERLAP;
+    }
+    return NDT2D_OK;
+}
+
+int ndt2d_host_alloc(void **p, size_t bytes)
+{
+    if (!p) return NDT2D_EINVAL;
+    cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        fail(nullptr, NDT2D_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+        return NDT2D_ENOMEM;
+    }
+    return NDT2D_OK;
+}
+
+int ndt2d_host_free(void *p)
+{
+    if (!p) return NDT2D_OK;
+    return cudaFreeHost(p) == cudaSuccess ? NDT2D_OK : NDT2D_ECUDA;
+}
+
+} // extern "C"

@@ -1,0 +1,64 @@
+// Internal (non-ABI) declarations shared by the kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ndt2d.h"
+
+namespace ndt2d {
+
+// One pyramid level as the kernels see it (SPEC 2). Passed by value in kernel parameters.
+struct LevelDev {
+    const float4 *cells;      // njx*njy records, two float4 each
+    uint32_t *cnt;            // njx*njy
+    unsigned long long *sums; // njx*njy*5, two's-complement i64
+    float res, st, inv_st, ox, oy;
+    float nhxf, nhyf;         // (float)nhx, (float)nhy
+    int nhx, nhy, njx, njy, ov;
+};
+
+struct AlignArgs {
+    LevelDev lv[NDT2D_MAX_LEVELS];
+    int nlevels;
+    ndt2d_params prm;
+    const float2 *xy;        // packed scans (xy mode)
+    const int64_t *offsets;  // nscans+1 (xy mode)
+    // ranges mode (SPEC 8): xy == nullptr
+    const void *ranges;
+    const float2 *beams;     // (cb, sb) per beam
+    int ranges_u16, nbeams;
+    float range_scale, range_min, range_max;
+    const double *init;
+    ndt2d_result *res;
+    int nscans;
+    int cap_points;          // shared-memory slot capacity in points (0: read scans from global memory)
+    unsigned int *counter;   // work queue head, zeroed before launch
+};
+
+struct LaunchCfg {
+    int sm_count;
+    int max_smem_optin;
+    cudaStream_t stream;
+};
+
+// all launchers return the cudaError_t of the launch; *launches is incremented per kernel launched
+cudaError_t launch_accumulate(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int64_t n, int64_t *launches);
+cudaError_t launch_finalize(const LaunchCfg &c, const LevelDev &L, float4 *cells_out, const ndt2d_params &p, int64_t *launches);
+cudaError_t launch_cell_index(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const double *d_pose,
+                              int32_t *d_idx, int64_t *launches);
+cudaError_t launch_point_terms(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const double *d_pose,
+                               float *d_terms, int64_t *launches);
+// poses: f64 x3 (poses_f32 == 0) or f32 x3 (sweep hypotheses). full: 10 sums, else score only.
+cudaError_t launch_eval_poses(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const void *d_poses,
+                              int poses_f32, int64_t npose, int full, double *d_out, int out_stride, int32_t *d_count,
+                              int64_t *launches);
+cudaError_t launch_align(const LaunchCfg &c, const AlignArgs &a, int64_t *launches);
+// top-k of scores by (-score, index); k small. d_work: nhyp bytes of scratch (mask).
+cudaError_t launch_topk(const LaunchCfg &c, const double *d_scores, int64_t nhyp, int k, int64_t *d_idx, double *d_val,
+                        unsigned long long *d_scratch, int64_t *launches);
+int topk_scratch_words(int sm_count);
+// finite bounding box of points: d_box[4] = ordered-int encoded {xmin, ymin, xmax, ymax} (see bbox_decode)
+cudaError_t launch_bbox(const LaunchCfg &c, const float2 *d_xy, int64_t n, int *d_box, int64_t *launches);
+float bbox_decode(int v);
+
+} // namespace ndt2d

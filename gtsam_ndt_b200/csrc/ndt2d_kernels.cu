@@ -1,0 +1,629 @@
+// Hand-written sm_100a kernels of the 2D NDT hot path (BASELINE.json north_star items 1-3):
+//   (1) grid build: integer accumulation with warp-level segmented reduction + finalise (SPEC 3)
+//   (2) Newton-step evaluation and the whole Levenberg-Marquardt loop on the device (SPEC 4, 5)
+//   (3) batched multi-hypothesis scoring and top-k (SPEC 6)
+// These are gather-bound kernels over an L2-resident cell table: no tensor cores (north_star).
+// Reference file:line: none (the mount is /root/reference/README.md:1 only); arithmetic follows SPEC.md.
+#include "ndt2d_device.cuh"
+
+#include <math.h>
+#include <string.h>
+
+namespace ndt2d {
+
+static constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// (1) grid build
+// ------------------------------------------------------------------------------------------------
+
+// SPEC 3 accumulation. One point per lane; for each of the K cells of the point, lanes holding the
+// same cell in consecutive positions (laser scans are spatially coherent) are combined with a
+// segmented shuffle reduction and only the head of each run issues the integer atomics. Integer
+// sums are associative, so the result is independent of the order of points, warps and atomics.
+template <int OV>
+__global__ void __launch_bounds__(256) k_accumulate(const LevelDev L, const float2 *__restrict__ xy, int64_t n)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    constexpr int K = OV ? 2 : 1;
+    for (int64_t base = warp_id * 32; base < n; base += warps_total * 32) {
+        int64_t i = base + lane;
+        float X = 0.0f, Y = 0.0f;
+        bool inside = false;
+        int hx = 0, hy = 0;
+        if (i < n) {
+            float2 p = __ldg(xy + i);
+            X = p.x;
+            Y = p.y;
+            inside = lattice(L, X, Y, hx, hy);
+        }
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+                int jx = hx + a, jy = hy + b;
+                int key = inside ? jy * L.njx + jx : -1;
+                double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
+                double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
+                double dx = (double)X - cx, dy = (double)Y - cy;
+                long long qx = inside ? __double2ll_rn(dx * 1048576.0) : 0;
+                long long qy = inside ? __double2ll_rn(dy * 1048576.0) : 0;
+                int c = inside ? 1 : 0;
+                long long sx = qx, sy = qy, sxx = qx * qx, sxy = qx * qy, syy = qy * qy;
+                // run id: number of run heads at or below this lane
+                int prev = __shfl_up_sync(FULL_MASK, key, 1);
+                bool head = (lane == 0) || (prev != key);
+                unsigned heads = __ballot_sync(FULL_MASK, head);
+                int rid = __popc(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int rid2 = __shfl_down_sync(FULL_MASK, rid, d);
+                    int c2 = __shfl_down_sync(FULL_MASK, c, d);
+                    long long sx2 = __shfl_down_sync(FULL_MASK, sx, d);
+                    long long sy2 = __shfl_down_sync(FULL_MASK, sy, d);
+                    long long sxx2 = __shfl_down_sync(FULL_MASK, sxx, d);
+                    long long sxy2 = __shfl_down_sync(FULL_MASK, sxy, d);
+                    long long syy2 = __shfl_down_sync(FULL_MASK, syy, d);
+                    if (lane + d < 32 && rid2 == rid) {
+                        c += c2; sx += sx2; sy += sy2; sxx += sxx2; sxy += sxy2; syy += syy2;
+                    }
+                }
+                if (head && key >= 0) {
+                    atomicAdd(L.cnt + key, (unsigned)c);
+                    unsigned long long *s = L.sums + 5 * (size_t)key;
+                    atomicAdd(s + 0, (unsigned long long)sx);
+                    atomicAdd(s + 1, (unsigned long long)sy);
+                    atomicAdd(s + 2, (unsigned long long)sxx);
+                    atomicAdd(s + 3, (unsigned long long)sxy);
+                    atomicAdd(s + 4, (unsigned long long)syy);
+                }
+            }
+        }
+    }
+}
+
+// SPEC 3 finalisation: one thread per cell, f64, operations in the order the spec lists them.
+__global__ void __launch_bounds__(256) k_finalize(const LevelDev L, float4 *__restrict__ cells, int min_points, double eig_ratio)
+{
+    const int64_t nc = (int64_t)L.njx * L.njy;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+        unsigned n = L.cnt[c];
+        if (n >= (unsigned)min_points) {
+            const long long *s = reinterpret_cast<const long long *>(L.sums) + 5 * c;
+            const double U = 1.0 / 1048576.0;
+            double N = (double)n;
+            long long s0 = s[0], s1 = s[1];
+            double mx = (double)s0 / N, my = (double)s1 / N;
+            double cxx = ((double)s[2] - (double)s0 * mx) / (N - 1.0);
+            double cxy = ((double)s[3] - (double)s0 * my) / (N - 1.0);
+            double cyy = ((double)s[4] - (double)s1 * my) / (N - 1.0);
+            mx *= U; my *= U; cxx *= U * U; cxy *= U * U; cyy *= U * U;
+            double tr = cxx + cyy, hd = 0.5 * (cxx - cyy), rad = sqrt(hd * hd + cxy * cxy);
+            double l1 = 0.5 * tr + rad, l2 = 0.5 * tr - rad;
+            if (l1 > 1e-10) {
+                if (l2 < eig_ratio * l1) {
+                    double l2n = eig_ratio * l1, vx, vy;
+                    if (hd >= 0.0) { vx = hd + rad; vy = cxy; } else { vx = cxy; vy = rad - hd; }
+                    double nn = vx * vx + vy * vy, dl = l1 - l2n;
+                    cxx = l2n + dl * (vx * vx) / nn;
+                    cxy = dl * (vx * vy) / nn;
+                    cyy = l2n + dl * (vy * vy) / nn;
+                }
+                double det = cxx * cyy - cxy * cxy;
+                int jx = (int)(c % L.njx), jy = (int)(c / L.njx);
+                double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
+                double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
+                ra = make_float4((float)(cx + mx), (float)(cy + my), (float)(cyy / det), (float)(-(cxy / det)));
+                rb = make_float4((float)(cxx / det), (float)det, (float)n, 1.0f);
+            }
+        }
+        cells[2 * c] = ra;
+        cells[2 * c + 1] = rb;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (2a) small per-point kernels used by the API's diagnostic entry points
+// ------------------------------------------------------------------------------------------------
+
+__global__ void k_cell_index(const LevelDev L, const float2 *__restrict__ xy, int n, const double *__restrict__ pose,
+                             int32_t *__restrict__ idx)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float2 p = xy[i];
+    float X = p.x, Y = p.y;
+    if (pose) {
+        Pose32 q = pose_to_f32(pose[0], pose[1], pose[2]);
+        float rx = __fmaf_rn(q.c, p.x, -__fmul_rn(q.s, p.y));
+        float ry = __fmaf_rn(q.s, p.x, __fmul_rn(q.c, p.y));
+        X = __fadd_rn(rx, q.tx);
+        Y = __fadd_rn(ry, q.ty);
+    }
+    int hx, hy;
+    idx[i] = lattice(L, X, Y, hx, hy) ? hy * L.nhx + hx : -1;
+}
+
+template <int OV>
+__global__ void k_point_terms(const LevelDev L, const float2 *__restrict__ xy, int n, const double *__restrict__ pose,
+                              float *__restrict__ terms)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int K = OV ? 4 : 1;
+    Pose32 q = pose_to_f32(pose[0], pose[1], pose[2]);
+    float2 p = xy[i];
+    float rx = __fmaf_rn(q.c, p.x, -__fmul_rn(q.s, p.y));
+    float ry = __fmaf_rn(q.s, p.x, __fmul_rn(q.c, p.y));
+    float X = __fadd_rn(rx, q.tx), Y = __fadd_rn(ry, q.ty);
+    float *out = terms + (size_t)i * K * 10;
+    for (int t = 0; t < K * 10; ++t) out[t] = 0.0f;
+    int hx, hy;
+    if (!lattice(L, X, Y, hx, hy)) return;
+    for (int k = 0; k < K; ++k) {
+        size_t cidx = (size_t)(hy + (k >> 1)) * L.njx + (size_t)(hx + (k & 1));
+        CellRec rec = load_cell(L.cells, cidx);
+        float T[10];
+        if (pair_terms<true>(rec, rx, ry, X, Y, T))
+            for (int t = 0; t < 10; ++t) out[k * 10 + t] = T[t];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (2b)/(3) one scan against many poses: the Newton-step evaluation and the sweep
+// ------------------------------------------------------------------------------------------------
+
+static constexpr int EVAL_THREADS = 256;
+
+// Block stages the scan in shared memory once (coalesced float2 loads), then each warp takes poses
+// from a grid-stride loop. FULL: ten f64 sums per pose; otherwise the score only (sweep).
+template <int OV, bool FULL, bool F32POSE, bool STAGED>
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_poses(const LevelDev L, const float2 *__restrict__ xy, int n,
+                                                               const void *__restrict__ poses, int64_t npose,
+                                                               double *__restrict__ out, int out_stride,
+                                                               int32_t *__restrict__ count)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float2 *pts = xy;
+    if (STAGED) {
+        float2 *s = reinterpret_cast<float2 *>(smem_raw);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = __ldg(xy + i);
+        __syncthreads();
+        pts = s;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (EVAL_THREADS / 32);
+    for (int64_t j = (int64_t)blockIdx.x * (EVAL_THREADS / 32) + (threadIdx.x >> 5); j < npose; j += warps_total) {
+        double tx, ty, th;
+        if (F32POSE) {
+            const float *h = reinterpret_cast<const float *>(poses) + 3 * j;
+            tx = (double)__ldg(h); ty = (double)__ldg(h + 1); th = (double)__ldg(h + 2);
+        } else {
+            const double *h = reinterpret_cast<const double *>(poses) + 3 * j;
+            tx = __ldg(h); ty = __ldg(h + 1); th = __ldg(h + 2);
+        }
+        Pose32 q = pose_to_f32(tx, ty, th);
+        Eval E;
+        eval_warp<OV, FULL>(L, pts, n, q, lane, E);
+        if (lane == 0) {
+            if (FULL) {
+#pragma unroll
+                for (int t = 0; t < 10; ++t) out[(size_t)j * out_stride + t] = E.v[t];
+            } else {
+                out[(size_t)j * out_stride] = E.v[0];
+            }
+            if (count) count[j] = E.count;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (2c) batched align: one warp per scan, the whole LM loop on the device
+// ------------------------------------------------------------------------------------------------
+
+static constexpr int ALIGN_THREADS = 256;
+
+// SPEC 5, one pyramid level. Every lane carries the same f64 state (the butterfly reduction gives
+// all lanes identical sums), so the control flow is warp-uniform and needs no broadcast.
+template <int OV>
+__device__ __forceinline__ int align_level(const LevelDev &L, const ndt2d_params &P, const float2 *pts, int n, double p[3],
+                                           Eval &E, int &evals_total, int lane)
+{
+    double lambda = P.lambda_init;
+    eval_warp<OV, true>(L, pts, n, pose_to_f32(p[0], p[1], p[2]), lane, E);
+    int evals = 1, status = NDT2D_MAX_ITERATIONS;
+    if (n == 0 || E.count == 0) {
+        evals_total += evals;
+        return NDT2D_NO_OVERLAP;
+    }
+    for (;;) {
+        if (evals >= P.max_iterations) break;
+        double d[3];
+        bool stalled = false;
+        while (!solve3(&E.v[1], &E.v[4], lambda, d)) {
+            lambda = lambda * P.lambda_fail_up;
+            if (lambda > P.lambda_max) { stalled = true; break; }
+        }
+        if (stalled) { status = NDT2D_STALLED; break; }
+        double nt = sqrt(d[0] * d[0] + d[1] * d[1]);
+        if (nt > P.max_step_trans) {
+            double sc = P.max_step_trans / nt;
+            d[0] *= sc; d[1] *= sc; d[2] *= sc; nt = P.max_step_trans;
+        }
+        if (fabs(d[2]) > P.max_step_rot) {
+            double sc = P.max_step_rot / fabs(d[2]);
+            d[0] *= sc; d[1] *= sc; d[2] *= sc; nt *= sc;
+        }
+        bool small = (nt < P.eps_trans) && (fabs(d[2]) < P.eps_rot);
+        double pn0 = p[0] + d[0], pn1 = p[1] + d[1], pn2 = p[2] + d[2];
+        Eval En;
+        eval_warp<OV, true>(L, pts, n, pose_to_f32(pn0, pn1, pn2), lane, En);
+        evals += 1;
+        if (En.v[0] > E.v[0]) {
+            p[0] = pn0; p[1] = pn1; p[2] = pn2;
+            E = En;
+            lambda = fmax(lambda / P.lambda_down, P.lambda_min);
+            if (small) { status = NDT2D_CONVERGED; break; }
+        } else {
+            if (small) { status = NDT2D_CONVERGED; break; }
+            lambda = lambda * P.lambda_up;
+            if (lambda > P.lambda_max) { status = NDT2D_STALLED; break; }
+        }
+    }
+    evals_total += evals;
+    return status;
+}
+
+// Persistent kernel: warps pull scan indices from a global counter until the batch is drained.
+// STAGED: the scan is copied once into this warp's shared-memory slot and re-read from there on
+// every iteration (an align touches its points 10-30 times, its HBM bytes once).
+// RANGES: the scan arrives as LaserScan ranges and is converted in the staging step (SPEC 8).
+template <int OV, bool STAGED, bool RANGES>
+__global__ void __launch_bounds__(ALIGN_THREADS) k_align(const __grid_constant__ AlignArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2 *slot = reinterpret_cast<float2 *>(smem_raw) + (size_t)warp * a.cap_points;
+    for (;;) {
+        unsigned job = 0;
+        if (lane == 0) job = atomicAdd(a.counter, 1u);
+        job = __shfl_sync(FULL_MASK, job, 0);
+        if (job >= (unsigned)a.nscans) break;
+        const float2 *pts;
+        int n;
+        if (RANGES) {
+            // SPEC 8: keep beams with range_min <= rho <= range_max, in beam order
+            int kept = 0;
+            for (int b0 = 0; b0 < a.nbeams; b0 += 32) {
+                int b = b0 + lane;
+                float rho = 0.0f;
+                bool ok = false;
+                if (b < a.nbeams) {
+                    if (a.ranges_u16) {
+                        unsigned short u = __ldg(reinterpret_cast<const unsigned short *>(a.ranges) + (size_t)job * a.nbeams + b);
+                        rho = __fmul_rn((float)u, a.range_scale);
+                        ok = (u != 0);
+                    } else {
+                        rho = __ldg(reinterpret_cast<const float *>(a.ranges) + (size_t)job * a.nbeams + b);
+                        ok = true;
+                    }
+                    ok = ok && (rho >= a.range_min) && (rho <= a.range_max);
+                }
+                unsigned m = __ballot_sync(FULL_MASK, ok);
+                if (ok) {
+                    float2 bt = __ldg(a.beams + b);
+                    slot[kept + __popc(m & ((1u << lane) - 1u))] = make_float2(__fmul_rn(rho, bt.x), __fmul_rn(rho, bt.y));
+                }
+                kept += __popc(m);
+            }
+            __syncwarp();
+            pts = slot;
+            n = kept;
+        } else {
+            int64_t o0 = __ldg(a.offsets + job), o1 = __ldg(a.offsets + job + 1);
+            n = (int)(o1 - o0);
+            const float2 *src = a.xy + o0;
+            if (STAGED) {
+                for (int i = lane; i < n; i += 32) slot[i] = __ldg(src + i);
+                __syncwarp();
+                pts = slot;
+            } else {
+                pts = src;
+            }
+        }
+        double p[3] = {__ldg(a.init + 3 * (size_t)job), __ldg(a.init + 3 * (size_t)job + 1), __ldg(a.init + 3 * (size_t)job + 2)};
+        Eval E;
+#pragma unroll
+        for (int t = 0; t < 10; ++t) E.v[t] = 0.0;
+        E.count = 0;
+        int evals = 0, status = NDT2D_NO_OVERLAP;
+        for (int l = 0; l < a.nlevels; ++l) status = align_level<OV>(a.lv[l], a.prm, pts, n, p, E, evals, lane);
+        if (lane == 0) {
+            ndt2d_result *r = a.res + job;
+            const double TWO_PI = 6.283185307179586476925286766559;
+            r->pose[0] = p[0];
+            r->pose[1] = p[1];
+            r->pose[2] = p[2] - TWO_PI * rint(p[2] / TWO_PI);
+            r->score = E.v[0];
+            r->grad[0] = E.v[1]; r->grad[1] = E.v[2]; r->grad[2] = E.v[3];
+            r->hessian[0] = E.v[4]; r->hessian[1] = E.v[5]; r->hessian[2] = E.v[6];
+            r->hessian[3] = E.v[5]; r->hessian[4] = E.v[7]; r->hessian[5] = E.v[8];
+            r->hessian[6] = E.v[6]; r->hessian[7] = E.v[8]; r->hessian[8] = E.v[9];
+            r->iterations = evals;
+            r->status = status;
+            r->count = E.count;
+            r->reserved = 0;
+        }
+        __syncwarp(); // the slot is rewritten by the next job
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (3) top-k of the sweep scores: k passes of a grid-wide arg-max (ties to the smaller index)
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ bool better(double s1, long long i1, double s2, long long i2)
+{
+    // order by (-score, index); an empty candidate has index -1
+    if (i2 < 0) return i1 >= 0;
+    if (i1 < 0) return false;
+    return (s1 > s2) || (s1 == s2 && i1 < i2);
+}
+
+// scratch layout: [0] ticket counter, then per block {score bits, index}
+__global__ void __launch_bounds__(256) k_argmax_pass(const double *__restrict__ scores, int64_t n, int pass,
+                                                     int64_t *__restrict__ best_idx, double *__restrict__ best_val,
+                                                     unsigned long long *__restrict__ scratch)
+{
+    __shared__ double s_val[8];
+    __shared__ long long s_idx[8];
+    __shared__ bool s_last;
+    double bv = 0.0;
+    long long bi = -1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        bool taken = false;
+        for (int t = 0; t < pass; ++t) taken |= (best_idx[t] == i);
+        double v = scores[i];
+        if (!taken && !(v != v) && better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+    auto warp_best = [&]() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double v2 = __shfl_xor_sync(FULL_MASK, bv, o);
+            long long i2 = __shfl_xor_sync(FULL_MASK, bi, o);
+            if (better(v2, i2, bv, bi)) { bv = v2; bi = i2; }
+        }
+    };
+    warp_best();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        bv = lane < 8 ? s_val[lane] : 0.0;
+        bi = lane < 8 ? s_idx[lane] : -1;
+        warp_best();
+        if (lane == 0) {
+            scratch[1 + 2 * blockIdx.x] = (unsigned long long)__double_as_longlong(bv);
+            scratch[2 + 2 * blockIdx.x] = (unsigned long long)bi;
+            __threadfence();
+            unsigned long long ticket = atomicAdd(scratch, 1ull);
+            s_last = (ticket == (unsigned long long)gridDim.x - 1ull);
+        }
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+        __threadfence();
+        bv = 0.0;
+        bi = -1;
+        for (int b = lane; b < (int)gridDim.x; b += 32) {
+            double v = __longlong_as_double((long long)scratch[1 + 2 * b]);
+            long long i = (long long)scratch[2 + 2 * b];
+            if (better(v, i, bv, bi)) { bv = v; bi = i; }
+        }
+        warp_best();
+        if (lane == 0) {
+            best_idx[pass] = bi;
+            best_val[pass] = bi >= 0 ? bv : 0.0;
+            scratch[0] = 0ull; // ready for the next pass
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+
+static inline int grid_for(int64_t items, int per_block, int sm_count, int blocks_per_sm)
+{
+    int64_t need = (items + per_block - 1) / per_block;
+    int64_t cap = (int64_t)sm_count * blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+cudaError_t launch_accumulate(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int64_t n, int64_t *launches)
+{
+    if (n <= 0) return cudaSuccess;
+    int grid = grid_for(n, 256, c.sm_count, 8);
+    if (L.ov) k_accumulate<1><<<grid, 256, 0, c.stream>>>(L, d_xy, n);
+    else k_accumulate<0><<<grid, 256, 0, c.stream>>>(L, d_xy, n);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const LaunchCfg &c, const LevelDev &L, float4 *cells_out, const ndt2d_params &p, int64_t *launches)
+{
+    int grid = grid_for((int64_t)L.njx * L.njy, 256, c.sm_count, 8);
+    k_finalize<<<grid, 256, 0, c.stream>>>(L, cells_out, p.min_points, p.eig_ratio);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cell_index(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const double *d_pose,
+                              int32_t *d_idx, int64_t *launches)
+{
+    if (n <= 0) return cudaSuccess;
+    k_cell_index<<<(n + 255) / 256, 256, 0, c.stream>>>(L, d_xy, n, d_pose, d_idx);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_point_terms(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const double *d_pose,
+                               float *d_terms, int64_t *launches)
+{
+    if (n <= 0) return cudaSuccess;
+    if (L.ov) k_point_terms<1><<<(n + 127) / 128, 128, 0, c.stream>>>(L, d_xy, n, d_pose, d_terms);
+    else k_point_terms<0><<<(n + 127) / 128, 128, 0, c.stream>>>(L, d_xy, n, d_pose, d_terms);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+template <int OV, bool FULL, bool F32POSE>
+static cudaError_t launch_eval_t(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const void *d_poses,
+                                 int64_t npose, double *d_out, int out_stride, int32_t *d_count)
+{
+    size_t smem = (size_t)n * sizeof(float2);
+    int grid = grid_for(npose, EVAL_THREADS / 32, c.sm_count, 4);
+    if (smem <= (size_t)c.max_smem_optin - 1024) {
+        auto kern = k_eval_poses<OV, FULL, F32POSE, true>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, EVAL_THREADS, smem, c.stream>>>(L, d_xy, n, d_poses, npose, d_out, out_stride, d_count);
+    } else {
+        k_eval_poses<OV, FULL, F32POSE, false><<<grid, EVAL_THREADS, 0, c.stream>>>(L, d_xy, n, d_poses, npose, d_out,
+                                                                                   out_stride, d_count);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eval_poses(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const void *d_poses,
+                              int poses_f32, int64_t npose, int full, double *d_out, int out_stride, int32_t *d_count,
+                              int64_t *launches)
+{
+    if (npose <= 0) return cudaSuccess;
+    ++*launches;
+    if (L.ov) {
+        if (full) return poses_f32 ? launch_eval_t<1, true, true>(c, L, d_xy, n, d_poses, npose, d_out, out_stride, d_count)
+                                   : launch_eval_t<1, true, false>(c, L, d_xy, n, d_poses, npose, d_out, out_stride, d_count);
+        return poses_f32 ? launch_eval_t<1, false, true>(c, L, d_xy, n, d_poses, npose, d_out, out_stride, d_count)
+                         : launch_eval_t<1, false, false>(c, L, d_xy, n, d_poses, npose, d_out, out_stride, d_count);
+    }
+    if (full) return poses_f32 ? launch_eval_t<0, true, true>(c, L, d_xy, n, d_poses, npose, d_out, out_stride, d_count)
+                               : launch_eval_t<0, true, false>(c, L, d_xy, n, d_poses, npose, d_out, out_stride, d_count);
+    return poses_f32 ? launch_eval_t<0, false, true>(c, L, d_xy, n, d_poses, npose, d_out, out_stride, d_count)
+                     : launch_eval_t<0, false, false>(c, L, d_xy, n, d_poses, npose, d_out, out_stride, d_count);
+}
+
+template <int OV, bool STAGED, bool RANGES>
+static cudaError_t launch_align_t(const LaunchCfg &c, const AlignArgs &a)
+{
+    auto kern = k_align<OV, STAGED, RANGES>;
+    size_t smem = (STAGED || RANGES) ? (size_t)a.cap_points * sizeof(float2) * (ALIGN_THREADS / 32) : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ALIGN_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int grid = grid_for(a.nscans, ALIGN_THREADS / 32, c.sm_count, per_sm);
+    kern<<<grid, ALIGN_THREADS, smem, c.stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_align(const LaunchCfg &c, const AlignArgs &a, int64_t *launches)
+{
+    if (a.nscans <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), c.stream);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+    const bool ranges = (a.xy == nullptr);
+    const bool staged = a.cap_points > 0;
+    if (a.prm.overlap) {
+        if (ranges) return launch_align_t<1, true, true>(c, a);
+        return staged ? launch_align_t<1, true, false>(c, a) : launch_align_t<1, false, false>(c, a);
+    }
+    if (ranges) return launch_align_t<0, true, true>(c, a);
+    return staged ? launch_align_t<0, true, false>(c, a) : launch_align_t<0, false, false>(c, a);
+}
+
+cudaError_t launch_topk(const LaunchCfg &c, const double *d_scores, int64_t nhyp, int k, int64_t *d_idx, double *d_val,
+                        unsigned long long *d_scratch, int64_t *launches)
+{
+    int grid = grid_for(nhyp, 256 * 4, c.sm_count, 4);
+    cudaError_t e = cudaMemsetAsync(d_scratch, 0, sizeof(unsigned long long), c.stream);
+    if (e != cudaSuccess) return e;
+    for (int pass = 0; pass < k; ++pass) {
+        k_argmax_pass<<<grid, 256, 0, c.stream>>>(d_scores, nhyp, pass, d_idx, d_val, d_scratch);
+        ++*launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+int topk_scratch_words(int sm_count) { return 1 + 2 * sm_count * 4; }
+
+// order-preserving float <-> int map so that integer atomicMin/atomicMax order floats
+__host__ __device__ static inline int float_to_ordered(float f)
+{
+    int i;
+#ifdef __CUDA_ARCH__
+    i = __float_as_int(f);
+#else
+    memcpy(&i, &f, 4);
+#endif
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+
+float bbox_decode(int v)
+{
+    int i = v >= 0 ? v : v ^ 0x7fffffff;
+    float f;
+    memcpy(&f, &i, 4);
+    return f;
+}
+
+// auto-fit (SPEC 2): bounding box of the finite points; min/max are order-independent
+__global__ void __launch_bounds__(256) k_bbox(const float2 *__restrict__ xy, int64_t n, int *__restrict__ box)
+{
+    float xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float2 p = __ldg(xy + i);
+        if (!isfinite(p.x) || !isfinite(p.y)) continue;
+        xmin = fminf(xmin, p.x); xmax = fmaxf(xmax, p.x);
+        ymin = fminf(ymin, p.y); ymax = fmaxf(ymax, p.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(FULL_MASK, xmin, o));
+        ymin = fminf(ymin, __shfl_xor_sync(FULL_MASK, ymin, o));
+        xmax = fmaxf(xmax, __shfl_xor_sync(FULL_MASK, xmax, o));
+        ymax = fmaxf(ymax, __shfl_xor_sync(FULL_MASK, ymax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(box + 0, float_to_ordered(xmin));
+        atomicMin(box + 1, float_to_ordered(ymin));
+        atomicMax(box + 2, float_to_ordered(xmax));
+        atomicMax(box + 3, float_to_ordered(ymax));
+    }
+}
+
+cudaError_t launch_bbox(const LaunchCfg &c, const float2 *d_xy, int64_t n, int *d_box, int64_t *launches)
+{
+    int init[4] = {float_to_ordered(INFINITY), float_to_ordered(INFINITY), float_to_ordered(-INFINITY),
+                   float_to_ordered(-INFINITY)};
+    cudaError_t e = cudaMemcpyAsync(d_box, init, sizeof(init), cudaMemcpyHostToDevice, c.stream);
+    if (e != cudaSuccess || n <= 0) return e;
+    k_bbox<<<grid_for(n, 256 * 4, c.sm_count, 4), 256, 0, c.stream>>>(d_xy, n, d_box);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+} // namespace ndt2d

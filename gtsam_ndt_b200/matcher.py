@@ -1,0 +1,228 @@
+"""Host-side mirror of the matcher interface named by BASELINE.json's north_star: set target map or scan,
+set cell resolution, align(scan, initial pose) -> pose, score, Hessian; plus the batched and sweep paths.
+
+Python front end over the C ABI (include/ndt2d.h); the C++ mirror is include/ndt2d.hpp. Reference
+class/signature: none citable (the mount is /root/reference/README.md:1 only).
+All compute runs in libndt2d.so on the GPU; nothing here (or below) falls back to the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+RESULT_DTYPE = np.dtype([("pose", "f8", 3), ("score", "f8"), ("grad", "f8", 3), ("hessian", "f8", (3, 3)),
+                         ("iterations", "i4"), ("status", "i4"), ("count", "i4"), ("reserved", "i4")])
+assert RESULT_DTYPE.itemsize == 144
+
+CONVERGED, MAX_ITERATIONS, STALLED, NO_OVERLAP = 0, 1, 2, 3
+
+
+class NdtError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):            # torch tensor (device or pinned host): plumbing only
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(int(a))
+
+
+class NdtMatcher2D:
+    """One handle = one CUDA device + one stream (not thread-safe)."""
+
+    def __init__(self, resolutions=(1.0,), device=0, stream=None, **params):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        rc = (self._L.ndt2d_create(device, C.byref(h)) if stream is None
+              else self._L.ndt2d_create_on_stream(device, C.c_void_p(stream), C.byref(h)))
+        if rc != 0:
+            raise NdtError(f"ndt2d_create failed ({rc}): {self._L.ndt2d_last_error(None).decode()}")
+        self._h = h
+        self.device = device
+        self.params = _lib.Params()
+        self._L.ndt2d_default_params(C.byref(self.params))
+        if params:
+            self.set_params(**params)
+        self.set_resolutions(resolutions)
+
+    # -- lifecycle -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ndt2d_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise NdtError(f"libndt2d error {rc}: {self._L.ndt2d_last_error(self._h).decode()}")
+
+    def synchronize(self):
+        self._ck(self._L.ndt2d_synchronize(self._h))
+
+    @property
+    def stream(self):
+        return self._L.ndt2d_stream(self._h) or 0
+
+    @property
+    def kernel_launches(self):
+        return self._L.ndt2d_kernel_launches(self._h)
+
+    # -- configuration ---------------------------------------------------------------------------
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise AttributeError(k)
+            setattr(self.params, k, v)
+        self._ck(self._L.ndt2d_set_params(self._h, C.byref(self.params)))
+
+    def set_resolution(self, res):
+        self.set_resolutions([res])
+
+    def set_resolutions(self, res):
+        r = np.ascontiguousarray(np.atleast_1d(res), np.float32)
+        self.nlevels = len(r)
+        self._ck(self._L.ndt2d_set_resolutions(self._h, r.ctypes.data_as(_lib.c_f32p), len(r)))
+
+    def set_grid(self, ox, oy, extent_x, extent_y):
+        self._ck(self._L.ndt2d_set_grid(self._h, ox, oy, extent_x, extent_y))
+
+    # -- target ----------------------------------------------------------------------------------
+    def set_target(self, xy):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        self._ck(self._L.ndt2d_set_target(self._h, _ptr(xy), len(xy)))
+
+    def add_target(self, xy):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        self._ck(self._L.ndt2d_add_target(self._h, _ptr(xy), len(xy)))
+
+    def set_target_device(self, d_xy, n):
+        self._ck(self._L.ndt2d_set_target_device(self._h, _ptr(d_xy), n))
+
+    def add_target_device(self, d_xy, n):
+        self._ck(self._L.ndt2d_add_target_device(self._h, _ptr(d_xy), n))
+
+    def geometry(self, level=0):
+        g = np.zeros(5, np.float32)
+        d = np.zeros(4, np.int32)
+        self._ck(self._L.ndt2d_level_geometry(self._h, level, g.ctypes.data_as(_lib.c_f32p), d.ctypes.data_as(_lib.c_i32p)))
+        return dict(res=g[0], st=g[1], inv_st=g[2], ox=g[3], oy=g[4], nhx=int(d[0]), nhy=int(d[1]), njx=int(d[2]), njy=int(d[3]))
+
+    def cells(self, level=0):
+        g = self.geometry(level)
+        out = np.zeros((g["njy"], g["njx"], 8), np.float32)
+        self._ck(self._L.ndt2d_get_cells(self._h, level, _ptr(out)))
+        return out
+
+    def set_cells(self, cells, level=0):
+        cells = np.ascontiguousarray(cells, np.float32)
+        self._ck(self._L.ndt2d_set_cells(self._h, level, _ptr(cells)))
+
+    def sums(self, level=0):
+        g = self.geometry(level)
+        n = np.zeros((g["njy"], g["njx"]), np.uint32)
+        s = np.zeros((g["njy"], g["njx"], 5), np.int64)
+        self._ck(self._L.ndt2d_get_sums(self._h, level, _ptr(n), _ptr(s)))
+        return n, s
+
+    def cells_device(self, level=0):
+        return self._L.ndt2d_cells_device(self._h, level)
+
+    # -- evaluation ------------------------------------------------------------------------------
+    def cell_index(self, xy, pose=None, level=0):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        idx = np.zeros(len(xy), np.int32)
+        pose = None if pose is None else np.ascontiguousarray(pose, np.float64)
+        self._ck(self._L.ndt2d_cell_index(self._h, level, _ptr(xy), len(xy), _ptr(pose), _ptr(idx)))
+        return idx
+
+    def evaluate(self, xy, poses, level=0):
+        """poses (3,) or (m,3) -> (out[10] or out[m,10], count)."""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        p = np.ascontiguousarray(poses, np.float64)
+        single = p.ndim == 1
+        p = p.reshape(-1, 3)
+        out = np.zeros((len(p), 10), np.float64)
+        cnt = np.zeros(len(p), np.int32)
+        self._ck(self._L.ndt2d_evaluate(self._h, level, _ptr(xy), len(xy), _ptr(p), len(p), _ptr(out), _ptr(cnt)))
+        return (out[0], int(cnt[0])) if single else (out, cnt)
+
+    def evaluate_device(self, d_xy, n, d_poses, npose, d_out, d_count=None, level=0):
+        self._ck(self._L.ndt2d_evaluate_device(self._h, level, _ptr(d_xy), n, _ptr(d_poses), npose, _ptr(d_out), _ptr(d_count)))
+
+    def point_terms(self, xy, pose, level=0):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        pose = np.ascontiguousarray(pose, np.float64)
+        K = 4 if self.params.overlap else 1
+        out = np.zeros((len(xy), K, 10), np.float32)
+        self._ck(self._L.ndt2d_point_terms(self._h, level, _ptr(xy), len(xy), _ptr(pose), _ptr(out)))
+        return out
+
+    # -- align -----------------------------------------------------------------------------------
+    def align(self, xy, init):
+        """align(scan, initial pose) -> record with pose, score, hessian (+ grad, iterations, status, count)."""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        init = np.ascontiguousarray(init, np.float64)
+        r = np.zeros(1, RESULT_DTYPE)
+        self._ck(self._L.ndt2d_align(self._h, _ptr(xy), len(xy), _ptr(init), _ptr(r)))
+        return r[0]
+
+    def align_batch(self, xy, offsets, init, out=None):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        init = np.ascontiguousarray(init, np.float64).reshape(-1, 3)
+        nb = len(offsets) - 1
+        if len(init) != nb or (nb and offsets[-1] > len(xy)):
+            raise ValueError("offsets / init / xy sizes disagree")
+        r = np.zeros(nb, RESULT_DTYPE) if out is None else out
+        self._ck(self._L.ndt2d_align_batch(self._h, _ptr(xy), _ptr(offsets), nb, _ptr(init), _ptr(r)))
+        return r
+
+    def align_batch_device(self, d_xy, d_offsets, nscans, max_points, d_init, d_res):
+        self._ck(self._L.ndt2d_align_batch_device(self._h, _ptr(d_xy), _ptr(d_offsets), nscans, max_points, _ptr(d_init), _ptr(d_res)))
+
+    def align_batch_ranges(self, ranges, angle_min, angle_inc, init, range_scale=0.001, range_min=0.0,
+                           range_max=3.0e38, out=None):
+        """LaserScan input: ranges[nscans, nbeams] float32 metres or uint16 * range_scale (SPEC.md section 8)."""
+        r = np.ascontiguousarray(ranges)
+        if r.dtype not in (np.float32, np.uint16):
+            r = r.astype(np.float32)
+        r = np.atleast_2d(r)
+        init = np.ascontiguousarray(init, np.float64).reshape(-1, 3)
+        res = np.zeros(len(r), RESULT_DTYPE) if out is None else out
+        self._ck(self._L.ndt2d_align_batch_ranges(self._h, _ptr(r), int(r.dtype == np.uint16), r.shape[0], r.shape[1],
+                                                  angle_min, angle_inc, range_scale, range_min, range_max, _ptr(init), _ptr(res)))
+        return res
+
+    def align_batch_ranges_device(self, d_ranges, is_u16, nscans, nbeams, angle_min, angle_inc, d_init, d_res,
+                                  range_scale=0.001, range_min=0.0, range_max=3.0e38):
+        self._ck(self._L.ndt2d_align_batch_ranges_device(self._h, _ptr(d_ranges), int(is_u16), nscans, nbeams, angle_min,
+                                                         angle_inc, range_scale, range_min, range_max, _ptr(d_init), _ptr(d_res)))
+
+    # -- sweep -----------------------------------------------------------------------------------
+    def sweep(self, xy, hyp, k=1, level=0, want_scores=True):
+        """hyp[m,3] f32 -> (scores[m] or None, best_idx[k], best_score[k])."""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        hyp = np.ascontiguousarray(hyp, np.float32).reshape(-1, 3)
+        scores = np.zeros(len(hyp), np.float64) if want_scores else None
+        bi = np.full(max(k, 1), -1, np.int64)
+        bs = np.zeros(max(k, 1), np.float64)
+        self._ck(self._L.ndt2d_sweep(self._h, level, _ptr(xy), len(xy), _ptr(hyp), len(hyp), _ptr(scores), k, _ptr(bi), _ptr(bs)))
+        return scores, bi[:k], bs[:k]
+
+    def sweep_device(self, d_xy, n, d_hyp, nhyp, d_scores, k, d_best_idx, d_best_score, level=0):
+        self._ck(self._L.ndt2d_sweep_device(self._h, level, _ptr(d_xy), n, _ptr(d_hyp), nhyp, _ptr(d_scores), k,
+                                            _ptr(d_best_idx), _ptr(d_best_score)))
+
+    def relocalize(self, xy, hyp, k=4, level=0):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        hyp = np.ascontiguousarray(hyp, np.float32).reshape(-1, 3)
+        bi = np.full(k, -1, np.int64)
+        res = np.zeros(k, RESULT_DTYPE)
+        self._ck(self._L.ndt2d_relocalize(self._h, level, _ptr(xy), len(xy), _ptr(hyp), len(hyp), k, _ptr(bi), _ptr(res)))
+        return bi, res

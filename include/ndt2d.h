@@ -1,0 +1,178 @@
+/*
+ * ndt2d.h — C ABI of the B200-native 2D NDT scan matcher (libndt2d.so).
+ *
+ * Drop-in boundary for the matcher role in a GTSAM/iSAM 2D SLAM pipeline, as named by
+ * BASELINE.json `north_star`: "set target map or scan, set cell resolution,
+ * align(scan, initial pose) returning pose, score and Hessian".
+ *
+ * Reference interface replaced: NONE CITABLE. The reference mount holds a single file,
+ * /root/reference/README.md:1 ("# GTSAM-NDT"); there is no matcher header, class or signature to
+ * bind against. Each entry point below therefore cites the north_star
+ * operation it serves and the SPEC.md section that fixes its arithmetic. INTEGRATION.md shows the
+ * C++ binding a GTSAM-side maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ or torch types. All functions return 0 on success or an
+ *    NDT2D_E* code; ndt2d_last_error() gives the text. No exceptions cross this boundary.
+ *  - "host" pointers are ordinary (pageable or pinned) memory; functions with the _device suffix
+ *    take CUDA device pointers on the handle's device and enqueue on the handle's stream without
+ *    synchronising (call ndt2d_synchronize, or order your own work on ndt2d_stream()).
+ *  - a point is two floats (x, y) in metres; a pose is three doubles (tx, ty, theta);
+ *    x' = R(theta) x + t.
+ *  - the caller owns every buffer it passes; the library owns all device memory behind the handle.
+ *  - one handle = one CUDA device + one stream; a handle is not thread-safe, distinct handles are.
+ *  - there is NO CPU fallback: without a CUDA device ndt2d_create fails with NDT2D_ECUDA.
+ */
+#ifndef NDT2D_H
+#define NDT2D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDT2D_VERSION 100
+#define NDT2D_MAX_LEVELS 8
+
+enum {
+    NDT2D_OK = 0,
+    NDT2D_EINVAL = 1,   /* bad argument */
+    NDT2D_ECUDA = 2,    /* CUDA runtime error (no device, launch failure, ...) */
+    NDT2D_ENOTARGET = 3,/* align/evaluate/sweep before set_target */
+    NDT2D_ENOMEM = 4
+};
+
+/* align status, SPEC.md section 5 */
+enum {
+    NDT2D_CONVERGED = 0,
+    NDT2D_MAX_ITERATIONS = 1,
+    NDT2D_STALLED = 2,
+    NDT2D_NO_OVERLAP = 3
+};
+
+/* SPEC.md section 1 */
+typedef struct ndt2d_params {
+    double eig_ratio;       /* [0.01]  smaller covariance eigenvalue >= eig_ratio * larger */
+    double eps_trans;       /* [1e-4]  m   */
+    double eps_rot;         /* [1e-5]  rad */
+    double max_step_trans;  /* [0.5]   m   */
+    double max_step_rot;    /* [0.2]   rad */
+    double lambda_init;     /* [1e-3] */
+    double lambda_min;      /* [1e-9] */
+    double lambda_max;      /* [1e7]  */
+    double lambda_up;       /* [10]   */
+    double lambda_down;     /* [5]    */
+    double lambda_fail_up;  /* [3]    */
+    int32_t min_points;     /* [3]  */
+    int32_t max_iterations; /* [30] evaluations per pyramid level */
+    int32_t overlap;        /* [0]  0: K = 1 cell per point; 1: four half-shifted grids, K = 4 */
+    int32_t reserved;
+} ndt2d_params;
+
+/* what align returns: pose, score and Hessian (north_star), plus gradient and diagnostics */
+typedef struct ndt2d_result {
+    double pose[3];     /* tx, ty, theta in (-pi, pi] */
+    double score;       /* S = sum of Gaussian likelihoods, higher is better */
+    double grad[3];     /* gradient of f = -S at pose */
+    double hessian[9];  /* Hessian of f = -S at pose, row-major 3x3, symmetric */
+    int32_t iterations; /* evaluations used, all levels */
+    int32_t status;     /* NDT2D_CONVERGED ... */
+    int32_t count;      /* (point, cell) pairs that contributed at pose */
+    int32_t reserved;
+} ndt2d_result;
+
+typedef struct ndt2d_matcher ndt2d_matcher;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int ndt2d_version(void);
+/* device: CUDA ordinal. The handle creates its own non-blocking stream. */
+int ndt2d_create(int device, ndt2d_matcher **out);
+/* same, but enqueue on the caller's cudaStream_t (passed as void*; NULL = default stream) */
+int ndt2d_create_on_stream(int device, void *cuda_stream, ndt2d_matcher **out);
+void ndt2d_destroy(ndt2d_matcher *m);
+/* text of the last error on this handle (m == NULL: last ndt2d_create error in this thread) */
+const char *ndt2d_last_error(const ndt2d_matcher *m);
+void *ndt2d_stream(const ndt2d_matcher *m);
+int ndt2d_synchronize(ndt2d_matcher *m);
+/* number of this library's kernels launched through this handle so far */
+int64_t ndt2d_kernel_launches(const ndt2d_matcher *m);
+
+/* ---- configuration (north_star: "set cell resolution") -------------------------------------- */
+void ndt2d_default_params(ndt2d_params *p);
+int ndt2d_set_params(ndt2d_matcher *m, const ndt2d_params *p);
+int ndt2d_get_params(const ndt2d_matcher *m, ndt2d_params *p);
+/* one level of cell size `res` metres (SPEC 2). Drops the current target. */
+int ndt2d_set_resolution(ndt2d_matcher *m, float res);
+/* multi-resolution pyramid, coarse to fine (BASELINE.json configs[2]: 2.0/1.0/0.5 m) */
+int ndt2d_set_resolutions(ndt2d_matcher *m, const float *res, int nlevels);
+/* explicit lattice origin/extent in metres for every level; extent <= 0 restores auto-fit (SPEC 2) */
+int ndt2d_set_grid(ndt2d_matcher *m, float ox, float oy, float extent_x, float extent_y);
+
+/* ---- target (north_star: "set target map or scan"; kernel stage 1, SPEC 3) -------------------- */
+int ndt2d_set_target(ndt2d_matcher *m, const float *xy, int64_t n);
+int ndt2d_set_target_device(ndt2d_matcher *m, const float *d_xy, int64_t n);
+/* incremental update (SPEC 7): same cells as a rebuild from the union. Needs an explicit grid
+ * or points inside the current lattice; points outside are ignored. */
+int ndt2d_add_target(ndt2d_matcher *m, const float *xy, int64_t n);
+int ndt2d_add_target_device(ndt2d_matcher *m, const float *d_xy, int64_t n);
+/* geom = {res, st, inv_st, ox, oy}; dims = {nhx, nhy, njx, njy} */
+int ndt2d_level_geometry(const ndt2d_matcher *m, int level, float geom[5], int32_t dims[4]);
+/* cell table: njx*njy records of 8 floats {mux, muy, B00, B01, B11, det, n, valid} */
+int ndt2d_get_cells(ndt2d_matcher *m, int level, float *cells);
+/* raw accumulators: n[njx*njy] and sums[njx*njy*5] = {sx, sy, sxx, sxy, syy} in 2^-20 m units */
+int ndt2d_get_sums(ndt2d_matcher *m, int level, uint32_t *n, int64_t *sums);
+/* device pointer to the cell table of a level (valid until the target changes) */
+const float *ndt2d_cells_device(const ndt2d_matcher *m, int level);
+/* load a cell table computed elsewhere (e.g. saved by ndt2d_get_cells); geometry must be explicit */
+int ndt2d_set_cells(ndt2d_matcher *m, int level, const float *cells);
+
+/* ---- evaluation (kernel stage 2, the Newton-step unit of work, SPEC 2 and 4) ------------------ */
+/* lattice index hy*nhx+hx (or -1) of each point after the optional pose (NULL = none) */
+int ndt2d_cell_index(ndt2d_matcher *m, int level, const float *xy, int n, const double *pose, int32_t *idx);
+/* out[10*j..] = {S, g0,g1,g2, H00,H01,H02,H11,H12,H22} and count[j] for pose j of npose */
+int ndt2d_evaluate(ndt2d_matcher *m, int level, const float *xy, int n, const double *poses, int npose,
+                   double *out, int32_t *count);
+int ndt2d_evaluate_device(ndt2d_matcher *m, int level, const float *d_xy, int n, const double *d_poses,
+                          int npose, double *d_out, int32_t *d_count);
+/* the ten f32 terms of every (point, cell) pair: terms[n*K*10], zeros where skipped (tests) */
+int ndt2d_point_terms(ndt2d_matcher *m, int level, const float *xy, int n, const double *pose, float *terms);
+
+/* ---- align (north_star: "align(scan, initial pose) returning pose, score and Hessian", SPEC 5) - */
+int ndt2d_align(ndt2d_matcher *m, const float *xy, int n, const double init[3], ndt2d_result *res);
+/* independent scans in one launch: scan b is points offsets[b] .. offsets[b+1]-1 of xy */
+int ndt2d_align_batch(ndt2d_matcher *m, const float *xy, const int64_t *offsets, int nscans,
+                      const double *init, ndt2d_result *res);
+/* all-device variant; max_points >= longest scan (sizes the shared-memory staging) */
+int ndt2d_align_batch_device(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, int nscans,
+                             int max_points, const double *d_init, ndt2d_result *d_res);
+/* LaserScan input (SPEC 8): ranges[nscans*nbeams], f32 metres or u16 * range_scale; beams outside
+ * [range_min, range_max] (and u16 zeros) are dropped on the device */
+int ndt2d_align_batch_ranges(ndt2d_matcher *m, const void *ranges, int ranges_are_u16, int nscans, int nbeams,
+                             double angle_min, double angle_inc, float range_scale, float range_min,
+                             float range_max, const double *init, ndt2d_result *res);
+int ndt2d_align_batch_ranges_device(ndt2d_matcher *m, const void *d_ranges, int ranges_are_u16, int nscans,
+                                    int nbeams, double angle_min, double angle_inc, float range_scale,
+                                    float range_min, float range_max, const double *d_init,
+                                    ndt2d_result *d_res);
+
+/* ---- sweep (kernel stage 3: multi-hypothesis search for relocalisation / loop closure, SPEC 6) - */
+/* hyp[3*j..] = (tx, ty, theta) f32. scores (optional, nhyp doubles). Top-k (k >= 1) by
+ * (-score, index) into best_idx[k], best_score[k]. */
+int ndt2d_sweep(ndt2d_matcher *m, int level, const float *xy, int n, const float *hyp, int64_t nhyp,
+                double *scores, int k, int64_t *best_idx, double *best_score);
+int ndt2d_sweep_device(ndt2d_matcher *m, int level, const float *d_xy, int n, const float *d_hyp,
+                       int64_t nhyp, double *d_scores, int k, int64_t *d_best_idx, double *d_best_score);
+/* sweep, then full align from each of the k best hypotheses; res[k] sorted like the top-k */
+int ndt2d_relocalize(ndt2d_matcher *m, int level, const float *xy, int n, const float *hyp, int64_t nhyp,
+                     int k, int64_t *best_idx, ndt2d_result *res);
+
+/* ---- pinned host memory for callers that want full-speed copies ------------------------------ */
+int ndt2d_host_alloc(void **p, size_t bytes);
+int ndt2d_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDT2D_H */

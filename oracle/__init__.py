@@ -24,7 +24,7 @@ def build(force=False):
 
 class Params(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("eig_ratio", "eps_trans", "eps_rot", "max_step_trans", "max_step_rot",
-                                          "lambda_init", "lambda_min", "lambda_max")] + \
+                                          "lambda_init", "lambda_min", "lambda_max", "lambda_up", "lambda_down", "lambda_fail_up")] + \
                [(n, C.c_int32) for n in ("min_points", "max_iterations", "overlap", "reserved")]
 
 

@@ -48,9 +48,10 @@ static void level_free(level_t *L)
 void oracle_default_params(oracle_params *p)
 {
     /* SPEC 1 defaults */
-    p->eig_ratio = 0.001; p->eps_trans = 1e-4; p->eps_rot = 1e-5;
+    p->eig_ratio = 0.01; p->eps_trans = 1e-4; p->eps_rot = 1e-5;
     p->max_step_trans = 0.5; p->max_step_rot = 0.2;
     p->lambda_init = 1e-3; p->lambda_min = 1e-9; p->lambda_max = 1e7;
+    p->lambda_up = 10.0; p->lambda_down = 5.0; p->lambda_fail_up = 3.0;
     p->min_points = 3; p->max_iterations = 30; p->overlap = 0; p->reserved = 0;
 }
 
@@ -79,6 +80,7 @@ void oracle_destroy(oracle_matcher *m)
 int oracle_set_params(oracle_matcher *m, const oracle_params *p)
 {
     if (p->min_points < 2 || p->max_iterations < 1 || (p->overlap != 0 && p->overlap != 1)) return 1;
+    if (!(p->lambda_up > 1.0) || !(p->lambda_fail_up > 1.0) || !(p->lambda_down >= 1.0)) return 1;
     if (m->has_target && p->overlap != m->prm.overlap) drop_target(m);
     m->prm = *p;
     return 0;
@@ -428,7 +430,7 @@ static int align_level(const level_t *L, const oracle_params *P, const float *xy
         double d[3];
         int stalled = 0;
         while (!oracle_solve(&E->v[1], &E->v[4], lambda, d)) {
-            lambda = lambda * 10.0;
+            lambda = lambda * P->lambda_fail_up;
             if (lambda > P->lambda_max) { stalled = 1; break; }
         }
         if (stalled) { status = 2; break; }
@@ -449,11 +451,11 @@ static int align_level(const level_t *L, const oracle_params *P, const float *xy
         if (En.v[0] > E->v[0]) {
             p[0] = pn[0]; p[1] = pn[1]; p[2] = pn[2];
             *E = En;
-            lambda = fmax(lambda / 10.0, P->lambda_min);
+            lambda = fmax(lambda / P->lambda_down, P->lambda_min);
             if (small) { status = 0; break; }
         } else {
             if (small) { status = 0; break; }
-            lambda = lambda * 10.0;
+            lambda = lambda * P->lambda_up;
             if (lambda > P->lambda_max) { status = 2; break; }
         }
     }

@@ -24,7 +24,7 @@ extern "C" {
 /* SPEC.md section 1. Same field order as ndt2d_params in include/ndt2d.h. */
 typedef struct {
     double eig_ratio, eps_trans, eps_rot, max_step_trans, max_step_rot;
-    double lambda_init, lambda_min, lambda_max;
+    double lambda_init, lambda_min, lambda_max, lambda_up, lambda_down, lambda_fail_up;
     int32_t min_points, max_iterations, overlap, reserved;
 } oracle_params;
 

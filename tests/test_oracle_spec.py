@@ -54,7 +54,7 @@ def test_single_cell_closed_form():
 
 
 def test_min_points_and_degenerate_cells():
-    o = Oracle([1.0], min_points=3)
+    o = Oracle([1.0], min_points=3, eig_ratio=0.001)
     o.set_grid(0.0, 0.0, 4.0, 4.0)
     pts = np.array([[0.5, 0.5], [0.6, 0.6],                      # two points: below min_points
                     [2.5, 2.5], [2.5, 2.5], [2.5, 2.5],          # identical: l1 = 0 -> invalid
