@@ -191,10 +191,10 @@ int upload(ndt2d_matcher *m, DevBuf &b, const void *src, size_t bytes)
 // shared-memory slot capacity (points per warp) for the align kernel; 0 = read scans from global memory
 int align_cap_points(const ndt2d_matcher *m, int max_points)
 {
-    int cap = (max_points + 1) & ~1; // keep slots 16-byte aligned
-    if (cap < 2) cap = 2;
+    int cap = (max_points + 63) & ~63; // two NaN-padded planes per warp, 64 points per warp iteration
+    if (cap < 64) cap = 64;
     size_t bytes = (size_t)cap * sizeof(float2) * 8;
-    if (bytes > (size_t)m->cfg.max_smem_optin - 1024) return 0;
+    if (bytes > (size_t)m->cfg.max_smem_optin - 2048) return 0;
     return cap;
 }
 

@@ -187,12 +187,16 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_poses(const LevelDev L, c
                                                                int32_t *__restrict__ count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const float2 *pts = xy;
+    const int npad = (n + 63) & ~63;
+    float *xs = reinterpret_cast<float *>(smem_raw), *ys = xs + npad;
     if (STAGED) {
-        float2 *s = reinterpret_cast<float2 *>(smem_raw);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = __ldg(xy + i);
+        // two planes, NaN padded to a multiple of 64 points (NaN is outside every lattice)
+        for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+            float2 p = i < n ? __ldg(xy + i) : make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+            xs[i] = p.x;
+            ys[i] = p.y;
+        }
         __syncthreads();
-        pts = s;
     }
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * (EVAL_THREADS / 32);
@@ -207,7 +211,8 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_poses(const LevelDev L, c
         }
         Pose32 q = pose_to_f32(tx, ty, th);
         Eval E;
-        eval_warp<OV, FULL>(L, pts, n, q, lane, E);
+        if (STAGED) eval_warp2<OV, FULL>(L, xs, ys, npad, q, lane, E);
+        else eval_warp<OV, FULL>(L, xy, n, q, lane, E);
         if (lane == 0) {
             if (FULL) {
 #pragma unroll
@@ -225,17 +230,48 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_poses(const LevelDev L, c
 // ------------------------------------------------------------------------------------------------
 
 static constexpr int ALIGN_THREADS = 256;
+static constexpr int ALIGN_MIN_BLOCKS = 3; // 24 warps/SM: bounds registers at 85
 
 // SPEC 5, one pyramid level. Every lane carries the same f64 state (the butterfly reduction gives
 // all lanes identical sums), so the control flow is warp-uniform and needs no broadcast.
-template <int OV>
-__device__ __forceinline__ int align_level(const LevelDev &L, const ndt2d_params &P, const float2 *pts, int n, double p[3],
-                                           Eval &E, int &evals_total, int lane)
+// where a warp reads its scan from: two NaN-padded shared-memory planes (packed path) or global memory
+struct ScanView {
+    const float2 *pts;
+    const float *xs, *ys;
+    int n, npad;
+};
+
+template <int OV, bool STAGED>
+__device__ __forceinline__ void eval_scan(const LevelDev &L, const ScanView &v, const Pose32 &q, int lane, Eval &E)
 {
+    if (STAGED) eval_warp2<OV, true>(L, v.xs, v.ys, v.npad, q, lane, E);
+    else eval_warp<OV, true>(L, v.pts, v.n, q, lane, E);
+}
+
+// Per-warp LM state kept in shared memory between evaluations so that it does not occupy registers
+// while the point loop runs: the last accepted evaluation (SPEC 5's E).
+struct WarpState {
+    double v[10];
+    int count, pad;
+};
+
+template <int OV, bool STAGED>
+__device__ __forceinline__ int align_level(const LevelDev &L, const ndt2d_params &P, const ScanView &v, double p[3],
+                                           WarpState *ws, int &evals_total, int lane)
+{
+    const int n = v.n;
     double lambda = P.lambda_init;
-    eval_warp<OV, true>(L, pts, n, pose_to_f32(p[0], p[1], p[2]), lane, E);
+    {
+        Eval E;
+        eval_scan<OV, STAGED>(L, v, pose_to_f32(p[0], p[1], p[2]), lane, E);
+#pragma unroll
+        for (int t = 0; t < 10; ++t)
+            if (lane == t) ws->v[t] = E.v[t];
+        if (lane == 10) ws->count = E.count;
+        __syncwarp();
+    }
     int evals = 1, status = NDT2D_MAX_ITERATIONS;
-    if (n == 0 || E.count == 0) {
+    if (n == 0 || ws->count == 0) {
         evals_total += evals;
         return NDT2D_NO_OVERLAP;
     }
@@ -243,9 +279,13 @@ __device__ __forceinline__ int align_level(const LevelDev &L, const ndt2d_params
         if (evals >= P.max_iterations) break;
         double d[3];
         bool stalled = false;
-        while (!solve3(&E.v[1], &E.v[4], lambda, d)) {
-            lambda = lambda * P.lambda_fail_up;
-            if (lambda > P.lambda_max) { stalled = true; break; }
+        {
+            double g[3] = {ws->v[1], ws->v[2], ws->v[3]};
+            double H6[6] = {ws->v[4], ws->v[5], ws->v[6], ws->v[7], ws->v[8], ws->v[9]};
+            while (!solve3(g, H6, lambda, d)) {
+                lambda = lambda * P.lambda_fail_up;
+                if (lambda > P.lambda_max) { stalled = true; break; }
+            }
         }
         if (stalled) { status = NDT2D_STALLED; break; }
         double nt = sqrt(d[0] * d[0] + d[1] * d[1]);
@@ -260,11 +300,16 @@ __device__ __forceinline__ int align_level(const LevelDev &L, const ndt2d_params
         bool small = (nt < P.eps_trans) && (fabs(d[2]) < P.eps_rot);
         double pn0 = p[0] + d[0], pn1 = p[1] + d[1], pn2 = p[2] + d[2];
         Eval En;
-        eval_warp<OV, true>(L, pts, n, pose_to_f32(pn0, pn1, pn2), lane, En);
+        eval_scan<OV, STAGED>(L, v, pose_to_f32(pn0, pn1, pn2), lane, En);
         evals += 1;
-        if (En.v[0] > E.v[0]) {
+        if (En.v[0] > ws->v[0]) {
             p[0] = pn0; p[1] = pn1; p[2] = pn2;
-            E = En;
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 10; ++t)
+                if (lane == t) ws->v[t] = En.v[t];
+            if (lane == 10) ws->count = En.count;
+            __syncwarp();
             lambda = fmax(lambda / P.lambda_down, P.lambda_min);
             if (small) { status = NDT2D_CONVERGED; break; }
         } else {
@@ -282,18 +327,23 @@ __device__ __forceinline__ int align_level(const LevelDev &L, const ndt2d_params
 // every iteration (an align touches its points 10-30 times, its HBM bytes once).
 // RANGES: the scan arrives as LaserScan ranges and is converted in the staging step (SPEC 8).
 template <int OV, bool STAGED, bool RANGES>
-__global__ void __launch_bounds__(ALIGN_THREADS) k_align(const __grid_constant__ AlignArgs a)
+__global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_BLOCKS : 1) k_align(const __grid_constant__ AlignArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool SM = STAGED || RANGES;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2 *slot = reinterpret_cast<float2 *>(smem_raw) + (size_t)warp * a.cap_points;
+    // per-warp slot: xs[cap] then ys[cap], cap a multiple of 64 points
+    WarpState *ws = reinterpret_cast<WarpState *>(smem_raw) + warp;
+    float *xs = reinterpret_cast<float *>(smem_raw + (ALIGN_THREADS / 32) * sizeof(WarpState)) + (size_t)warp * 2 * a.cap_points;
+    float *ys = xs + a.cap_points;
+    const float qnan = __int_as_float(0x7fc00000);
     for (;;) {
         unsigned job = 0;
         if (lane == 0) job = atomicAdd(a.counter, 1u);
         job = __shfl_sync(FULL_MASK, job, 0);
         if (job >= (unsigned)a.nscans) break;
-        const float2 *pts;
-        int n;
+        ScanView v;
+        v.pts = nullptr; v.xs = xs; v.ys = ys; v.n = 0; v.npad = 0;
         if (RANGES) {
             // SPEC 8: keep beams with range_min <= rho <= range_max, in beam order
             int kept = 0;
@@ -315,33 +365,37 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(const __grid_constant__
                 unsigned m = __ballot_sync(FULL_MASK, ok);
                 if (ok) {
                     float2 bt = __ldg(a.beams + b);
-                    slot[kept + __popc(m & ((1u << lane) - 1u))] = make_float2(__fmul_rn(rho, bt.x), __fmul_rn(rho, bt.y));
+                    int dst = kept + __popc(m & ((1u << lane) - 1u));
+                    xs[dst] = __fmul_rn(rho, bt.x);
+                    ys[dst] = __fmul_rn(rho, bt.y);
                 }
                 kept += __popc(m);
             }
-            __syncwarp();
-            pts = slot;
-            n = kept;
+            v.n = kept;
         } else {
             int64_t o0 = __ldg(a.offsets + job), o1 = __ldg(a.offsets + job + 1);
-            n = (int)(o1 - o0);
+            v.n = (int)(o1 - o0);
             const float2 *src = a.xy + o0;
             if (STAGED) {
-                for (int i = lane; i < n; i += 32) slot[i] = __ldg(src + i);
-                __syncwarp();
-                pts = slot;
+                for (int i = lane; i < v.n; i += 32) {
+                    float2 p = __ldg(src + i);
+                    xs[i] = p.x;
+                    ys[i] = p.y;
+                }
             } else {
-                pts = src;
+                v.pts = src;
             }
         }
+        if (SM) {
+            v.npad = (v.n + 63) & ~63;
+            for (int i = v.n + lane; i < v.npad; i += 32) { xs[i] = qnan; ys[i] = qnan; }
+            __syncwarp();
+        }
         double p[3] = {__ldg(a.init + 3 * (size_t)job), __ldg(a.init + 3 * (size_t)job + 1), __ldg(a.init + 3 * (size_t)job + 2)};
-        Eval E;
-#pragma unroll
-        for (int t = 0; t < 10; ++t) E.v[t] = 0.0;
-        E.count = 0;
         int evals = 0, status = NDT2D_NO_OVERLAP;
-        for (int l = 0; l < a.nlevels; ++l) status = align_level<OV>(a.lv[l], a.prm, pts, n, p, E, evals, lane);
+        for (int l = 0; l < a.nlevels; ++l) status = align_level<OV, SM>(a.lv[l], a.prm, v, p, ws, evals, lane);
         if (lane == 0) {
+            WarpState E = *ws;
             ndt2d_result *r = a.res + job;
             const double TWO_PI = 6.283185307179586476925286766559;
             r->pose[0] = p[0];
@@ -485,7 +539,7 @@ template <int OV, bool FULL, bool F32POSE>
 static cudaError_t launch_eval_t(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const void *d_poses,
                                  int64_t npose, double *d_out, int out_stride, int32_t *d_count)
 {
-    size_t smem = (size_t)n * sizeof(float2);
+    size_t smem = (size_t)((n + 63) & ~63) * sizeof(float2);
     int grid = grid_for(npose, EVAL_THREADS / 32, c.sm_count, 4);
     if (smem <= (size_t)c.max_smem_optin - 1024) {
         auto kern = k_eval_poses<OV, FULL, F32POSE, true>;
@@ -523,9 +577,13 @@ template <int OV, bool STAGED, bool RANGES>
 static cudaError_t launch_align_t(const LaunchCfg &c, const AlignArgs &a)
 {
     auto kern = k_align<OV, STAGED, RANGES>;
-    size_t smem = (STAGED || RANGES) ? (size_t)a.cap_points * sizeof(float2) * (ALIGN_THREADS / 32) : 0;
+    size_t smem = ((STAGED || RANGES) ? (size_t)a.cap_points * sizeof(float2) : 0) * (ALIGN_THREADS / 32) + (ALIGN_THREADS / 32) * sizeof(WarpState);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    if (smem > 4096) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
     }
     int per_sm = 0;
