@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--scans", type=int, default=16384, help="scans per step per GPU (16384 x 1080 x 8 B = 141 MB > L2)")
+    ap.add_argument("--scans", type=int, default=65536, help="scans per step per GPU (65536 x 1080 x 8 B = 566 MB, far above the 126 MB L2)")
     ap.add_argument("--map-scans", type=int, default=2048, help="scans fused into the target map")
     ap.add_argument("--res", type=float, nargs="+", default=[0.25])
     ap.add_argument("--overlap", type=int, default=0)

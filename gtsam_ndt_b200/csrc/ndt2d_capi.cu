@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -73,6 +74,13 @@ struct ndt2d_matcher {
         b_counter, b_beams, b_ranges, b_box;
     double beams_amin = 0, beams_ainc = 0;
     int beams_n = 0;
+    // host-buffer batch calls are cut into chunks: chunk i+1 is copied on copy_stream while chunk i computes
+    static constexpr int MAX_CHUNKS = 16;
+    cudaStream_t copy_stream = nullptr;
+    cudaStream_t work_stream[2] = {nullptr, nullptr}; // chunk kernels alternate so one chunk's tail overlaps the next
+    cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
+    cudaEvent_t ev_begin = nullptr, ev_done[2] = {nullptr, nullptr};
+    int chunk_scans = 8192;
     int64_t launches = 0;
     std::string err;
 };
@@ -198,6 +206,23 @@ int align_cap_points(const ndt2d_matcher *m, int max_points)
     return cap;
 }
 
+// SPEC 8 beam table, computed on the host with libm in f64 and rounded once, then cached on the device
+int ensure_beams(ndt2d_matcher *m, int nbeams, double angle_min, double angle_inc)
+{
+    if (m->beams_n == nbeams && m->beams_amin == angle_min && m->beams_ainc == angle_inc) return NDT2D_OK;
+    std::vector<float> tab((size_t)nbeams * 2);
+    for (int i = 0; i < nbeams; ++i) {
+        double phi = angle_min + (double)i * angle_inc;
+        tab[2 * i] = (float)cos(phi);
+        tab[2 * i + 1] = (float)sin(phi);
+    }
+    int rc = upload(m, m->b_beams, tab.data(), tab.size() * 4);
+    if (rc) return rc;
+    CK(m, cudaStreamSynchronize(m->cfg.stream)); // tab goes out of scope
+    m->beams_n = nbeams; m->beams_amin = angle_min; m->beams_ainc = angle_inc;
+    return NDT2D_OK;
+}
+
 void fill_align_args(ndt2d_matcher *m, AlignArgs &a)
 {
     memset(&a, 0, sizeof(a));
@@ -205,6 +230,62 @@ void fill_align_args(ndt2d_matcher *m, AlignArgs &a)
     a.nlevels = m->nlevels;
     a.prm = m->prm;
     a.counter = m->b_counter.as<unsigned int>();
+}
+
+// Host-buffer batch driver shared by the xy and ranges entry points. The input is cut into chunks; chunk
+// copies run back to back on copy_stream, chunk kernels alternate between two work streams (so the tail
+// of one chunk overlaps the head of the next) and each chunk's results are copied back as it finishes.
+// The call returns after everything has completed (host-synchronous, like the rest of the host API).
+struct ChunkPlan {
+    int nchunks, per;
+};
+
+ChunkPlan plan_chunks(const ndt2d_matcher *m, int nscans)
+{
+    ChunkPlan p;
+    p.nchunks = (nscans + m->chunk_scans - 1) / m->chunk_scans;
+    if (p.nchunks > ndt2d_matcher::MAX_CHUNKS) p.nchunks = ndt2d_matcher::MAX_CHUNKS;
+    if (p.nchunks < 1) p.nchunks = 1;
+    p.per = (nscans + p.nchunks - 1) / p.nchunks;
+    return p;
+}
+
+template <typename CopyFn, typename LaunchFn>
+int run_pipeline(ndt2d_matcher *m, int nscans, ndt2d_result *res, CopyFn copy_chunk, LaunchFn launch_chunk)
+{
+    const ChunkPlan pl = plan_chunks(m, nscans);
+    CK(m, cudaEventRecord(m->ev_begin, m->cfg.stream)); // earlier work on the handle's stream comes first
+    CK(m, cudaStreamWaitEvent(m->copy_stream, m->ev_begin, 0));
+    for (int i = 0; i < 2; ++i) CK(m, cudaStreamWaitEvent(m->work_stream[i], m->ev_begin, 0));
+    for (int c = 0; c < pl.nchunks; ++c) {
+        int s0 = c * pl.per, s1 = s0 + pl.per < nscans ? s0 + pl.per : nscans;
+        if (s1 > s0) {
+            int rc = copy_chunk(s0, s1, m->copy_stream);
+            if (rc) return rc;
+        }
+        CK(m, cudaEventRecord(m->ev_chunk[c], m->copy_stream));
+    }
+    const cudaStream_t main_stream = m->cfg.stream;
+    int rc = NDT2D_OK;
+    for (int c = 0; c < pl.nchunks && rc == NDT2D_OK; ++c) {
+        int s0 = c * pl.per, s1 = s0 + pl.per < nscans ? s0 + pl.per : nscans;
+        if (s1 <= s0) break;
+        cudaStream_t ws = m->work_stream[c & 1];
+        CK(m, cudaStreamWaitEvent(ws, m->ev_chunk[c], 0));
+        m->cfg.stream = ws; // launches below go to the work stream
+        rc = launch_chunk(s0, s1, m->b_counter.as<unsigned int>() + 1 + c);
+        m->cfg.stream = main_stream;
+        if (rc) break;
+        cudaError_t e = cudaMemcpyAsync(res + s0, m->b_res.as<ndt2d_result>() + s0, (size_t)(s1 - s0) * sizeof(ndt2d_result),
+                                        cudaMemcpyDeviceToHost, ws);
+        if (e != cudaSuccess) rc = fail(m, NDT2D_ECUDA, "result copy: %s", cudaGetErrorString(e));
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaEventRecord(m->ev_done[i], m->work_stream[i]);
+        cudaStreamWaitEvent(main_stream, m->ev_done[i], 0);
+    }
+    int rs = ndt2d_synchronize(m);
+    return rc ? rc : rs;
 }
 
 } // namespace
@@ -255,7 +336,25 @@ int ndt2d_create_on_stream(int device, void *cuda_stream, ndt2d_matcher **out)
         m->cfg.stream = (cudaStream_t)cuda_stream;
     }
     ndt2d_default_params(&m->prm);
-    if (m->b_counter.ensure(16) != cudaSuccess || m->b_box.ensure(16) != cudaSuccess ||
+    {
+        bool ok = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&m->ev_begin, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 2 && ok; ++i) {
+            ok = cudaStreamCreateWithFlags(&m->work_stream[i], cudaStreamNonBlocking) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        for (int i = 0; i < ndt2d_matcher::MAX_CHUNKS && ok; ++i)
+            ok = cudaEventCreateWithFlags(&m->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            ndt2d_destroy(m);
+            return fail(nullptr, NDT2D_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if (const char *e = getenv("NDT2D_CHUNK_SCANS")) {
+            int v = atoi(e);
+            if (v > 0) m->chunk_scans = v;
+        }
+    }
+    if (m->b_counter.ensure(4 * (ndt2d_matcher::MAX_CHUNKS + 1)) != cudaSuccess || m->b_box.ensure(16) != cudaSuccess ||
         m->b_scratch.ensure(sizeof(unsigned long long) * (size_t)topk_scratch_words(m->cfg.sm_count)) != cudaSuccess) {
         ndt2d_destroy(m);
         return fail(nullptr, NDT2D_ENOMEM, "device allocation failed");
@@ -276,6 +375,20 @@ void ndt2d_destroy(ndt2d_matcher *m)
                       &m->b_hyp, &m->b_scores, &m->b_tki, &m->b_tkv, &m->b_scratch, &m->b_counter, &m->b_beams, &m->b_ranges,
                       &m->b_box};
     for (DevBuf *b : bufs) b->release();
+    if (m->copy_stream) {
+        cudaStreamSynchronize(m->copy_stream);
+        cudaStreamDestroy(m->copy_stream);
+    }
+    if (m->ev_begin) cudaEventDestroy(m->ev_begin);
+    for (int i = 0; i < 2; ++i) {
+        if (m->work_stream[i]) {
+            cudaStreamSynchronize(m->work_stream[i]);
+            cudaStreamDestroy(m->work_stream[i]);
+        }
+        if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
+    }
+    for (cudaEvent_t e : m->ev_chunk)
+        if (e) cudaEventDestroy(e);
     if (m->own_stream) cudaStreamDestroy(m->cfg.stream);
     delete m;
 }
@@ -527,8 +640,17 @@ int ndt2d_point_terms(ndt2d_matcher *m, int level, const float *xy, int n, const
     return ndt2d_synchronize(m);
 }
 
+static int align_batch_device_impl(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, int nscans, int max_points,
+                                   const double *d_init, ndt2d_result *d_res, unsigned int *counter);
+
 int ndt2d_align_batch_device(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, int nscans, int max_points,
                              const double *d_init, ndt2d_result *d_res)
+{
+    return align_batch_device_impl(m, d_xy, d_offsets, nscans, max_points, d_init, d_res, nullptr);
+}
+
+static int align_batch_device_impl(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, int nscans, int max_points,
+                                   const double *d_init, ndt2d_result *d_res, unsigned int *counter)
 {
     if (!m) return NDT2D_EINVAL;
     if (!m->has_target) return fail(m, NDT2D_ENOTARGET, "no target set");
@@ -545,6 +667,7 @@ int ndt2d_align_batch_device(ndt2d_matcher *m, const float *d_xy, const int64_t 
     a.res = d_res;
     a.nscans = nscans;
     a.cap_points = align_cap_points(m, max_points);
+    if (counter) a.counter = counter;
     CK(m, launch_align(m->cfg, a, &m->launches));
     return NDT2D_OK;
 }
@@ -566,15 +689,22 @@ int ndt2d_align_batch(ndt2d_matcher *m, const float *xy, const int64_t *offsets,
     if (offsets[0] < 0 || (total > 0 && !xy)) return fail(m, NDT2D_EINVAL, "bad offsets / xy");
     DeviceGuard g(m->device);
     int rc;
-    if ((rc = upload(m, m->b_xy, xy, (size_t)total * 8))) return rc;
+    CK(m, m->b_xy.ensure((size_t)(total ? total : 1) * 8));
+    CK(m, m->b_res.ensure((size_t)nscans * sizeof(ndt2d_result)));
     if ((rc = upload(m, m->b_off, offsets, (size_t)(nscans + 1) * 8))) return rc;
     if ((rc = upload(m, m->b_init, init, (size_t)nscans * 24))) return rc;
-    CK(m, m->b_res.ensure((size_t)nscans * sizeof(ndt2d_result)));
-    rc = ndt2d_align_batch_device(m, m->b_xy.as<float>(), m->b_off.as<int64_t>(), nscans, (int)maxn, m->b_init.as<double>(),
-                                  m->b_res.as<ndt2d_result>());
-    if (rc) return rc;
-    CK(m, cudaMemcpyAsync(res, m->b_res.p, (size_t)nscans * sizeof(ndt2d_result), cudaMemcpyDeviceToHost, m->cfg.stream));
-    return ndt2d_synchronize(m);
+    return run_pipeline(
+        m, nscans, res,
+        [&](int s0, int s1, cudaStream_t cs) -> int {
+            int64_t p0 = offsets[s0], p1 = offsets[s1];
+            if (p1 > p0)
+                CK(m, cudaMemcpyAsync(m->b_xy.as<float>() + 2 * p0, xy + 2 * p0, (size_t)(p1 - p0) * 8, cudaMemcpyHostToDevice, cs));
+            return NDT2D_OK;
+        },
+        [&](int s0, int s1, unsigned int *counter) -> int {
+            return align_batch_device_impl(m, m->b_xy.as<float>(), m->b_off.as<int64_t>() + s0, s1 - s0, (int)maxn,
+                                           m->b_init.as<double>() + 3 * (size_t)s0, m->b_res.as<ndt2d_result>() + s0, counter);
+        });
 }
 
 int ndt2d_align(ndt2d_matcher *m, const float *xy, int n, const double init[3], ndt2d_result *res)
@@ -584,9 +714,21 @@ int ndt2d_align(ndt2d_matcher *m, const float *xy, int n, const double init[3], 
     return ndt2d_align_batch(m, xy, off, 1, init, res);
 }
 
+static int align_ranges_device_impl(ndt2d_matcher *m, const void *d_ranges, int ranges_are_u16, int nscans, int nbeams,
+                                    double angle_min, double angle_inc, float range_scale, float range_min, float range_max,
+                                    const double *d_init, ndt2d_result *d_res, unsigned int *counter);
+
 int ndt2d_align_batch_ranges_device(ndt2d_matcher *m, const void *d_ranges, int ranges_are_u16, int nscans, int nbeams,
                                     double angle_min, double angle_inc, float range_scale, float range_min, float range_max,
                                     const double *d_init, ndt2d_result *d_res)
+{
+    return align_ranges_device_impl(m, d_ranges, ranges_are_u16, nscans, nbeams, angle_min, angle_inc, range_scale, range_min,
+                                    range_max, d_init, d_res, nullptr);
+}
+
+static int align_ranges_device_impl(ndt2d_matcher *m, const void *d_ranges, int ranges_are_u16, int nscans, int nbeams,
+                                    double angle_min, double angle_inc, float range_scale, float range_min, float range_max,
+                                    const double *d_init, ndt2d_result *d_res, unsigned int *counter)
 {
     if (!m) return NDT2D_EINVAL;
     if (!m->has_target) return fail(m, NDT2D_ENOTARGET, "no target set");
@@ -596,18 +738,9 @@ int ndt2d_align_batch_ranges_device(ndt2d_matcher *m, const void *d_ranges, int 
     DeviceGuard g(m->device);
     int cap = align_cap_points(m, nbeams);
     if (cap == 0) return fail(m, NDT2D_EINVAL, "nbeams %d exceeds the shared-memory staging limit", nbeams);
-    // SPEC 8 beam table, computed on the host with libm in f64 and rounded once, then cached
-    if (m->beams_n != nbeams || m->beams_amin != angle_min || m->beams_ainc != angle_inc) {
-        std::vector<float> tab((size_t)nbeams * 2);
-        for (int i = 0; i < nbeams; ++i) {
-            double phi = angle_min + (double)i * angle_inc;
-            tab[2 * i] = (float)cos(phi);
-            tab[2 * i + 1] = (float)sin(phi);
-        }
-        int rc = upload(m, m->b_beams, tab.data(), tab.size() * 4);
-        if (rc) return rc;
-        CK(m, cudaStreamSynchronize(m->cfg.stream)); // tab goes out of scope
-        m->beams_n = nbeams; m->beams_amin = angle_min; m->beams_ainc = angle_inc;
+    {
+        int rcb = ensure_beams(m, nbeams, angle_min, angle_inc);
+        if (rcb) return rcb;
     }
     AlignArgs a;
     fill_align_args(m, a);
@@ -621,6 +754,7 @@ int ndt2d_align_batch_ranges_device(ndt2d_matcher *m, const void *d_ranges, int 
     a.res = d_res;
     a.nscans = nscans;
     a.cap_points = cap;
+    if (counter) a.counter = counter;
     CK(m, launch_align(m->cfg, a, &m->launches));
     return NDT2D_OK;
 }
@@ -635,15 +769,24 @@ int ndt2d_align_batch_ranges(ndt2d_matcher *m, const void *ranges, int ranges_ar
     if (nscans == 0) return NDT2D_OK;
     DeviceGuard g(m->device);
     int rc;
-    size_t rbytes = (size_t)nscans * nbeams * (ranges_are_u16 ? 2 : 4);
-    if ((rc = upload(m, m->b_ranges, ranges, rbytes))) return rc;
-    if ((rc = upload(m, m->b_init, init, (size_t)nscans * 24))) return rc;
+    const size_t esz = ranges_are_u16 ? 2 : 4;
+    CK(m, m->b_ranges.ensure((size_t)nscans * nbeams * esz));
     CK(m, m->b_res.ensure((size_t)nscans * sizeof(ndt2d_result)));
-    rc = ndt2d_align_batch_ranges_device(m, m->b_ranges.p, ranges_are_u16, nscans, nbeams, angle_min, angle_inc, range_scale,
-                                         range_min, range_max, m->b_init.as<double>(), m->b_res.as<ndt2d_result>());
-    if (rc) return rc;
-    CK(m, cudaMemcpyAsync(res, m->b_res.p, (size_t)nscans * sizeof(ndt2d_result), cudaMemcpyDeviceToHost, m->cfg.stream));
-    return ndt2d_synchronize(m);
+    if ((rc = upload(m, m->b_init, init, (size_t)nscans * 24))) return rc;
+    if ((rc = ensure_beams(m, nbeams, angle_min, angle_inc))) return rc; // on the main stream, before the work streams fork
+    return run_pipeline(
+        m, nscans, res,
+        [&](int s0, int s1, cudaStream_t cs) -> int {
+            CK(m, cudaMemcpyAsync(m->b_ranges.as<unsigned char>() + (size_t)s0 * nbeams * esz,
+                                  reinterpret_cast<const unsigned char *>(ranges) + (size_t)s0 * nbeams * esz,
+                                  (size_t)(s1 - s0) * nbeams * esz, cudaMemcpyHostToDevice, cs));
+            return NDT2D_OK;
+        },
+        [&](int s0, int s1, unsigned int *counter) -> int {
+            return align_ranges_device_impl(m, m->b_ranges.as<unsigned char>() + (size_t)s0 * nbeams * esz, ranges_are_u16,
+                                            s1 - s0, nbeams, angle_min, angle_inc, range_scale, range_min, range_max,
+                                            m->b_init.as<double>() + 3 * (size_t)s0, m->b_res.as<ndt2d_result>() + s0, counter);
+        });
 }
 
 int ndt2d_sweep_device(ndt2d_matcher *m, int level, const float *d_xy, int n, const float *d_hyp, int64_t nhyp,

@@ -22,9 +22,15 @@
 
 typedef struct { double x0, y0, x1, y1; } box_t;
 
+#define GRID_N 20          /* broad phase: 20 x 20 buckets of 10 m over [-100, 100]^2 */
+#define GRID_CELL 10.0
+#define GRID_MAX 64
+
 typedef struct {
     int nboxes;
     box_t box[SYNTH_MAX_BOXES];
+    int bucket_n[GRID_N][GRID_N];
+    short bucket[GRID_N][GRID_N][GRID_MAX];
 } world_t;
 
 static uint64_t splitmix64(uint64_t *s)
@@ -50,6 +56,15 @@ static void build_world(world_t *w, uint64_t seed, int ncand)
         if (b.x0 < -WALL + 0.5 || b.x1 > WALL - 0.5 || b.y0 < -WALL + 0.5 || b.y1 > WALL - 0.5) continue;
         w->box[w->nboxes++] = b;
     }
+    for (int gy = 0; gy < GRID_N; ++gy) for (int gx = 0; gx < GRID_N; ++gx) w->bucket_n[gy][gx] = 0;
+    for (int i = 0; i < w->nboxes; ++i) {
+        const box_t *b = &w->box[i];
+        int x0 = (int)floor((b->x0 + 100.0) / GRID_CELL), x1 = (int)floor((b->x1 + 100.0) / GRID_CELL);
+        int y0 = (int)floor((b->y0 + 100.0) / GRID_CELL), y1 = (int)floor((b->y1 + 100.0) / GRID_CELL);
+        for (int gy = y0; gy <= y1; ++gy) for (int gx = x0; gx <= x1; ++gx)
+            if (gx >= 0 && gx < GRID_N && gy >= 0 && gy < GRID_N && w->bucket_n[gy][gx] < GRID_MAX)
+                w->bucket[gy][gx][w->bucket_n[gy][gx]++] = (short)i;
+    }
 }
 
 /* distance along (dx,dy) from (px,py) to the first surface */
@@ -60,14 +75,28 @@ static double cast(const world_t *w, double px, double py, double dx, double dy)
     double tx = ((dx > 0 ? WALL : -WALL) - px) * idx;
     double ty = ((dy > 0 ? WALL : -WALL) - py) * idy;
     double best = fmin(dx != 0 ? tx : INFINITY, dy != 0 ? ty : INFINITY);
-    for (int i = 0; i < w->nboxes; ++i) {
-        const box_t *b = &w->box[i];
-        double t0x = (b->x0 - px) * idx, t1x = (b->x1 - px) * idx;
-        double t0y = (b->y0 - py) * idy, t1y = (b->y1 - py) * idy;
-        double tnx = fmin(t0x, t1x), tfx = fmax(t0x, t1x);
-        double tny = fmin(t0y, t1y), tfy = fmax(t0y, t1y);
-        double tn = fmax(tnx, tny), tf = fmin(tfx, tfy);
-        if (tn <= tf && tn > 0.0 && tn < best) best = tn;
+    /* walk the buckets along the ray (DDA); the first bucket whose nearest hit lies inside it ends the walk.
+       The result is the minimum over all boxes, exactly as a brute-force loop would give. */
+    int gx = (int)floor((px + 100.0) / GRID_CELL), gy = (int)floor((py + 100.0) / GRID_CELL);
+    int sx = dx > 0 ? 1 : -1, sy = dy > 0 ? 1 : -1;
+    double tmx = dx != 0 ? (((gx + (dx > 0)) * GRID_CELL - 100.0) - px) * idx : INFINITY;
+    double tmy = dy != 0 ? (((gy + (dy > 0)) * GRID_CELL - 100.0) - py) * idy : INFINITY;
+    double tdx = dx != 0 ? GRID_CELL * fabs(idx) : INFINITY, tdy = dy != 0 ? GRID_CELL * fabs(idy) : INFINITY;
+    double tenter = 0.0;
+    while (gx >= 0 && gx < GRID_N && gy >= 0 && gy < GRID_N && tenter < best) {
+        double texit = fmin(tmx, tmy);
+        for (int k = 0; k < w->bucket_n[gy][gx]; ++k) {
+            const box_t *b = &w->box[w->bucket[gy][gx][k]];
+            double t0x = (b->x0 - px) * idx, t1x = (b->x1 - px) * idx;
+            double t0y = (b->y0 - py) * idy, t1y = (b->y1 - py) * idy;
+            double tnx = fmin(t0x, t1x), tfx = fmax(t0x, t1x);
+            double tny = fmin(t0y, t1y), tfy = fmax(t0y, t1y);
+            double tn = fmax(tnx, tny), tf = fmin(tfx, tfy);
+            if (tn <= tf && tn > 0.0 && tn < best) best = tn;
+        }
+        if (best <= texit) break; /* the nearest hit so far is inside the buckets already visited */
+        tenter = texit;
+        if (tmx < tmy) { gx += sx; tmx += tdx; } else { gy += sy; tmy += tdy; }
     }
     return best;
 }
