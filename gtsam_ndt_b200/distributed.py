@@ -1,0 +1,75 @@
+"""Multi-GPU host logic for the batched paths: one process per GPU, torch.distributed
+for the plumbing. Scans and hypotheses are independent, so they are sharded by contiguous ranges with no
+data-path collective; the sweep's only exchange is the best-hypothesis combine (16 B per rank and per k).
+
+Nothing here computes NDT: scoring is done by the caller's matcher (libndt2d.so on that rank's GPU).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """Contiguous, near-equal [lo, hi) slice of n items for `rank` of `world` (first n % world ranks get one more)."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _device_for_backend():
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def combine_topk(local_idx, local_score, k):
+    """Merge per-rank top-k lists (global indices, scores) into the global top-k ordered by (-score, index).
+
+    Every rank passes arrays of length k (pad with index -1); every rank gets the same answer.
+    Ties go to the smaller global index, so the result equals the unsharded sweep's (SPEC.md section 6)."""
+    local_idx = np.asarray(local_idx, np.int64).reshape(-1)
+    local_score = np.asarray(local_score, np.float64).reshape(-1)
+    assert len(local_idx) == k and len(local_score) == k
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        all_idx, all_score = local_idx, local_score
+    else:
+        dev = _device_for_backend()
+        world = dist.get_world_size()
+        ti = torch.from_numpy(local_idx).to(dev)
+        ts = torch.from_numpy(local_score).to(dev)
+        gi = [torch.empty_like(ti) for _ in range(world)]
+        gs = [torch.empty_like(ts) for _ in range(world)]
+        dist.all_gather(gi, ti)
+        dist.all_gather(gs, ts)
+        all_idx = torch.cat(gi).cpu().numpy()
+        all_score = torch.cat(gs).cpu().numpy()
+    keep = all_idx >= 0
+    all_idx, all_score = all_idx[keep], all_score[keep]
+    order = np.lexsort((all_idx, -all_score))[:k]
+    out_i = np.full(k, -1, np.int64)
+    out_s = np.zeros(k, np.float64)
+    out_i[: len(order)] = all_idx[order]
+    out_s[: len(order)] = all_score[order]
+    return out_i, out_s
+
+
+def sweep_sharded(score_shard, nhyp, k=1):
+    """Relocalisation sweep over `nhyp` hypotheses sharded across the ranks of the default process group.
+
+    score_shard(lo, hi, k) -> (idx[k] relative to lo or -1, score[k]) scores hypotheses [lo, hi) on this rank
+    (e.g. lambda lo, hi, k: matcher.sweep(xy, hyp[lo:hi], k, want_scores=False)[1:]).
+    Returns the global (idx[k], score[k])."""
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    lo, hi = shard_range(nhyp, rank, world)
+    idx, score = score_shard(lo, hi, k)
+    idx = np.asarray(idx, np.int64).copy()
+    idx[idx >= 0] += lo
+    return combine_topk(idx, score, k)
+
+
+def align_sharded_counts(nscans):
+    """[lo, hi) of this rank's scans for a batched align; results stay on the rank that computed them."""
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    return shard_range(nscans, rank, world)

@@ -1,0 +1,160 @@
+// ndt2d.hpp — header-only C++ host mirror of the matcher interface, over the C ABI in ndt2d.h.
+//
+// This is the class a GTSAM-NDT style C++ front end holds in place of its CPU matcher: set the target map or
+// scan, set the cell resolution, align(scan, initial pose) -> pose, score, Hessian (BASELINE.json north_star).
+// Reference class/signature replaced: none citable — the reference mount is /root/reference/README.md:1 only
+// (SURVEY.md 8b), so the method names follow the north_star's wording. INTEGRATION.md shows the GTSAM glue.
+//
+// Error behaviour: every failure of the C ABI becomes a std::runtime_error carrying ndt2d_last_error().
+// There is no CPU fallback: constructing a Matcher without a B200-class CUDA device throws.
+#ifndef NDT2D_HPP
+#define NDT2D_HPP
+
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "ndt2d.h"
+
+namespace ndt2d {
+
+struct Point2f {
+    float x, y;
+};
+
+struct Pose2d {
+    double x = 0, y = 0, theta = 0;
+};
+
+using Result = ndt2d_result;   // pose[3], score, grad[3], hessian[9] (row-major), iterations, status, count
+using Params = ndt2d_params;
+
+class Matcher {
+  public:
+    explicit Matcher(int device = 0, void *cuda_stream = reinterpret_cast<void *>(-1))
+    {
+        int rc = cuda_stream == reinterpret_cast<void *>(-1) ? ndt2d_create(device, &h_)
+                                                             : ndt2d_create_on_stream(device, cuda_stream, &h_);
+        if (rc != NDT2D_OK) throw std::runtime_error(std::string("ndt2d_create: ") + ndt2d_last_error(nullptr));
+    }
+    ~Matcher() { ndt2d_destroy(h_); }
+    Matcher(const Matcher &) = delete;
+    Matcher &operator=(const Matcher &) = delete;
+    Matcher(Matcher &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    Matcher &operator=(Matcher &&o) noexcept
+    {
+        if (this != &o) {
+            ndt2d_destroy(h_);
+            h_ = o.h_;
+            o.h_ = nullptr;
+        }
+        return *this;
+    }
+
+    // ---- configuration ------------------------------------------------------------------------
+    Params params() const
+    {
+        Params p;
+        ck(ndt2d_get_params(h_, &p));
+        return p;
+    }
+    void setParams(const Params &p) { ck(ndt2d_set_params(h_, &p)); }
+    void setResolution(float res) { ck(ndt2d_set_resolution(h_, res)); }
+    void setResolutions(const std::vector<float> &coarse_to_fine)
+    {
+        ck(ndt2d_set_resolutions(h_, coarse_to_fine.data(), static_cast<int>(coarse_to_fine.size())));
+    }
+    void setGrid(float ox, float oy, float extent_x, float extent_y) { ck(ndt2d_set_grid(h_, ox, oy, extent_x, extent_y)); }
+
+    // ---- target: a previous scan (scan-to-scan) or a map point cloud (scan-to-map) ---------------
+    void setTarget(const Point2f *pts, std::int64_t n) { ck(ndt2d_set_target(h_, reinterpret_cast<const float *>(pts), n)); }
+    void setTarget(const std::vector<Point2f> &pts) { setTarget(pts.data(), static_cast<std::int64_t>(pts.size())); }
+    void addToTarget(const Point2f *pts, std::int64_t n) { ck(ndt2d_add_target(h_, reinterpret_cast<const float *>(pts), n)); }
+    void addToTarget(const std::vector<Point2f> &pts) { addToTarget(pts.data(), static_cast<std::int64_t>(pts.size())); }
+
+    // ---- align(scan, initial pose) -> pose, score, Hessian -----------------------------------------
+    Result align(const Point2f *scan, int n, const Pose2d &init)
+    {
+        const double p[3] = {init.x, init.y, init.theta};
+        Result r;
+        ck(ndt2d_align(h_, reinterpret_cast<const float *>(scan), n, p, &r));
+        return r;
+    }
+    Result align(const std::vector<Point2f> &scan, const Pose2d &init) { return align(scan.data(), static_cast<int>(scan.size()), init); }
+
+    // independent scans in one launch; scan b is points [offsets[b], offsets[b+1]) of `points`
+    std::vector<Result> alignBatch(const std::vector<Point2f> &points, const std::vector<std::int64_t> &offsets,
+                                   const std::vector<Pose2d> &init)
+    {
+        const int nb = static_cast<int>(init.size());
+        if (offsets.size() != init.size() + 1) throw std::invalid_argument("alignBatch: offsets.size() must be init.size() + 1");
+        std::vector<Result> out(init.size());
+        static_assert(sizeof(Pose2d) == 3 * sizeof(double), "Pose2d must be three packed doubles");
+        ck(ndt2d_align_batch(h_, reinterpret_cast<const float *>(points.data()), offsets.data(), nb,
+                             reinterpret_cast<const double *>(init.data()), out.data()));
+        return out;
+    }
+
+    // LaserScan input: ranges[nscans * nbeams] in metres, beam i at angle_min + i * angle_inc
+    std::vector<Result> alignBatchRanges(const std::vector<float> &ranges, int nbeams, double angle_min, double angle_inc,
+                                         float range_min, float range_max, const std::vector<Pose2d> &init)
+    {
+        std::vector<Result> out(init.size());
+        ck(ndt2d_align_batch_ranges(h_, ranges.data(), 0, static_cast<int>(init.size()), nbeams, angle_min, angle_inc, 1.0f,
+                                    range_min, range_max, reinterpret_cast<const double *>(init.data()), out.data()));
+        return out;
+    }
+
+    // ---- multi-hypothesis search (relocalisation, loop-closure candidates) --------------------------
+    // hypotheses: (x, y, theta) float triples. Returns the k best (index, score), best first.
+    std::vector<std::pair<std::int64_t, double>> sweep(const std::vector<Point2f> &scan, const std::vector<float> &hyp_xyt, int k,
+                                                       int level = 0, std::vector<double> *scores = nullptr)
+    {
+        const std::int64_t m = static_cast<std::int64_t>(hyp_xyt.size() / 3);
+        std::vector<std::int64_t> idx(static_cast<size_t>(k), -1);
+        std::vector<double> val(static_cast<size_t>(k), 0.0);
+        if (scores) scores->assign(static_cast<size_t>(m), 0.0);
+        ck(ndt2d_sweep(h_, level, reinterpret_cast<const float *>(scan.data()), static_cast<int>(scan.size()), hyp_xyt.data(), m,
+                       scores ? scores->data() : nullptr, k, idx.data(), val.data()));
+        std::vector<std::pair<std::int64_t, double>> out;
+        for (int i = 0; i < k && idx[static_cast<size_t>(i)] >= 0; ++i) out.emplace_back(idx[static_cast<size_t>(i)], val[static_cast<size_t>(i)]);
+        return out;
+    }
+    // sweep, then a full align from each of the k best
+    std::vector<Result> relocalize(const std::vector<Point2f> &scan, const std::vector<float> &hyp_xyt, int k, int level = 0)
+    {
+        std::vector<std::int64_t> idx(static_cast<size_t>(k), -1);
+        std::vector<Result> res(static_cast<size_t>(k));
+        ck(ndt2d_relocalize(h_, level, reinterpret_cast<const float *>(scan.data()), static_cast<int>(scan.size()), hyp_xyt.data(),
+                            static_cast<std::int64_t>(hyp_xyt.size() / 3), k, idx.data(), res.data()));
+        return res;
+    }
+
+    // ---- evaluation at fixed poses: {S, g0,g1,g2, H00,H01,H02,H11,H12,H22} ---------------------------
+    std::array<double, 10> evaluate(const std::vector<Point2f> &scan, const Pose2d &pose, int level = 0, int *count = nullptr)
+    {
+        const double p[3] = {pose.x, pose.y, pose.theta};
+        std::array<double, 10> out{};
+        std::int32_t c = 0;
+        ck(ndt2d_evaluate(h_, level, reinterpret_cast<const float *>(scan.data()), static_cast<int>(scan.size()), p, 1, out.data(), &c));
+        if (count) *count = c;
+        return out;
+    }
+
+    ndt2d_matcher *handle() const { return h_; }
+    void synchronize() { ck(ndt2d_synchronize(h_)); }
+
+  private:
+    void ck(int rc) const
+    {
+        if (rc != NDT2D_OK) throw std::runtime_error(std::string("libndt2d (") + std::to_string(rc) + "): " + ndt2d_last_error(h_));
+    }
+    ndt2d_matcher *h_ = nullptr;
+};
+
+} // namespace ndt2d
+
+#endif // NDT2D_HPP
