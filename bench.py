@@ -41,16 +41,25 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--scans", type=int, default=65536, help="scans per step per GPU (65536 x 1080 x 8 B = 566 MB, far above the 126 MB L2)")
+    ap.add_argument("--workload", default="scan2map", choices=["scan2map", "pyramid", "sweep"],
+                    help="scan2map: BASELINE configs[1] (default, the metric's config); pyramid: configs[2] (2.0/1.0/0.5 m, "
+                         "10k scans, 0.2 m / 3 deg prior error); sweep: configs[3] (1M hypotheses x one 1080-pt scan)")
+    ap.add_argument("--hyps", type=int, default=1000000, help="sweep: total hypotheses (sharded across GPUs)")
+    ap.add_argument("--scans", type=int, default=None, help="scans per step per GPU (65536 x 1080 x 8 B = 566 MB, far above the 126 MB L2)")
     ap.add_argument("--map-scans", type=int, default=2048, help="scans fused into the target map")
-    ap.add_argument("--res", type=float, nargs="+", default=[0.25])
+    ap.add_argument("--res", type=float, nargs="+", default=None)
     ap.add_argument("--overlap", type=int, default=0)
-    ap.add_argument("--perturb", type=float, nargs=2, default=[0.03, 0.3], help="initial guess error: metres, degrees")
+    ap.add_argument("--perturb", type=float, nargs=2, default=None, help="initial guess error: metres, degrees")
     ap.add_argument("--input", default="xy", choices=["xy", "ranges_f32", "ranges_u16"], help="e2e input format")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scans in the cpu_baseline sample (0: auto, about 10-20 s)")
     ap.add_argument("--ref-scans", type=int, default=0, help="scans per step of the reference arm (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    dflt = {"scan2map": (65536, [0.25], [0.03, 0.3]), "pyramid": (10000, [2.0, 1.0, 0.5], [0.2, 3.0]), "sweep": (1, [0.25], [0.0, 0.0])}[a.workload]
+    a.scans = a.scans or dflt[0]
+    a.res = a.res or dflt[1]
+    a.perturb = a.perturb or dflt[2]
+    return a
 
 
 def peaks():
@@ -169,8 +178,10 @@ def run_reference(args):
 
 def workload_config(args, scans, extra=None):
     K = 4 if args.overlap else 1
-    c = {"workload": "configs[1]: scan-to-map NDT align, 1080-beam scans vs 200x200 m map at %s m cells (K=%d), batch of %d scans per GPU per step"
-         % ("/".join(str(r) for r in args.res), K, scans),
+    name = {"scan2map": "configs[1]: scan-to-map NDT align", "pyramid": "configs[2]: multi-resolution NDT align (pyramid)",
+            "sweep": "configs[3]"}[args.workload]
+    c = {"workload": "%s, 1080-beam scans vs 200x200 m map at %s m cells (K=%d), batch of %d scans per GPU per step"
+         % (name, "/".join(str(r) for r in args.res), K, scans),
          "scans_per_step_per_gpu": scans, "points_per_scan": 1080, "cell_res_m": list(args.res), "K": K,
          "map_points": args.map_scans * 1080, "init_error": {"trans_m": args.perturb[0], "rot_deg": args.perturb[1]},
          "l2": "per-step scan input %.0f MB > 126 MB L2 (no flush needed); the 200x200 m cell table is L2-resident by design"
@@ -327,6 +338,107 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+def run_sweep(args):
+    """BASELINE configs[3]: relocalisation, `--hyps` pose hypotheses x one 1080-pt scan vs the global map, hypotheses
+    sharded across the GPUs, best-hypothesis combine as the only collective. One step = one full sweep + combine."""
+    import torch
+    import torch.distributed as dist
+    import gtsam_ndt_b200 as g
+    from gtsam_ndt_b200 import synth, distributed as D
+
+    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the NDT path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    K = 4 if args.overlap else 1
+    sc = synth.SCAN_1080
+    map_xy = synth.make_map(args.map_scans, traj_len=args.map_scans, **sc)
+    ranges, poses = synth.scans(1, traj_len=1000, first=137, **sc)
+    xy = synth.polar_to_points(ranges[0], sc["angle_min"], sc["angle_inc"])
+    # SURVEY 8(d): regular lattice, 0.2 m in x and y, 3 deg in theta, truncated to --hyps
+    nth = 120
+    side = int(math.ceil(math.sqrt(args.hyps / nth)))
+    gx = (np.arange(side) - side // 2) * 0.2
+    lat = np.stack(np.meshgrid(gx, gx, np.radians(np.arange(nth) * 3.0 - 180.0), indexing="ij"), -1).reshape(-1, 3)[: args.hyps]
+    hyp = (poses[0] + lat).astype(np.float32)
+    lo, hi = D.shard_range(len(hyp), rank, world)
+    stream = torch.cuda.current_stream()
+    m = g.NdtMatcher2D(args.res, device=local, stream=stream.cuda_stream, overlap=args.overlap)
+    m.set_grid(-100.0, -100.0, 200.0, 200.0)
+    m.set_target(map_xy)
+    d_xy = torch.from_numpy(xy).to(dev)
+    d_hyp = torch.from_numpy(hyp[lo:hi].copy()).to(dev)
+    d_scores = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
+    d_bi = torch.zeros(1, dtype=torch.int64, device=dev); d_bs = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def step():
+        m.sweep_device(d_xy, len(xy), d_hyp, hi - lo, d_scores, 1, d_bi, d_bs)
+        if world > 1:   # best-hypothesis combine: 16 B per rank
+            pair = torch.stack([d_bs, (d_bi + lo).to(torch.float64)]).reshape(1, 2)
+            out = [torch.empty_like(pair) for _ in range(world)]
+            dist.all_gather(out, pair)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = m.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = m.kernel_launches - l0
+    # e2e: host hypotheses in, best pose out, through the host-buffer call + the gloo/nccl combine
+    h_hyp = torch.from_numpy(hyp[lo:hi].copy()).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        gi, gs = D.sweep_sharded(lambda a, b, k: m.sweep(xy, h_hyp.numpy(), k=k, want_scores=False)[1:], len(hyp), k=1) if world == 1 else \
+            D.combine_topk(*(lambda r: (r[1] + lo, r[2]))(m.sweep(xy, h_hyp.numpy(), k=1, want_scores=False)), 1)
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        hbm, peak_src = peaks()
+        per_hyp = len(xy) * (8 + 32 * K) + 12 + 8
+        kernel_ms = ms / args.steps
+        achieved = (hi - lo) * per_hyp / (kernel_ms / 1e3) / 1e9
+        truth_err = float(np.abs(hyp[int(gi[0])] - poses[0]).max())
+        line = {"metric": "NDT pose hypotheses/sec (1080-pt scan vs global map)", "value": len(hyp) * args.steps / (ms / 1e3),
+                "unit": "hypotheses/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 per point, f64 sums", "data": "synthetic",
+                "config": {"workload": "configs[3]: relocalisation, %d pose hypotheses (0.2 m x 0.2 m x 3 deg lattice) x one %d-pt scan vs 200x200 m map at %s m cells (K=%d), hypotheses sharded over %d GPU(s)"
+                                       % (len(hyp), len(xy), args.res[0], K, world),
+                           "l2": "hypotheses %.0f MB + scores per step; scan and cell table are cache-resident by design" % (len(hyp) * 12 / 1e6),
+                           "parallelism": "hypotheses sharded per GPU; all-gather of one (score, index) pair per rank"},
+                "e2e": {"value": len(hyp) * args.steps / (e2e_ms / 1e3), "unit": "hypotheses/s", "h2d_bytes_per_step": int((hi - lo) * 12 + len(xy) * 8),
+                        "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / args.steps, "api": "ndt2d_sweep + combine_topk"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                             "kernel": "k_eval_poses (score only)", "peak_source": peak_src, "bytes_per_hypothesis": per_hyp,
+                             "convention": "gather traffic (see DESIGN.md section 4); scan and cells are cache-resident"},
+                "best_hypothesis_abs_err_vs_truth": truth_err, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def cpu_baseline(args, xy, offsets, init, map_xy, res_gpu):
     """The CPU spec oracle on a bounded sample of the same workload, all host threads (reported, not the target)."""
     import oracle
@@ -357,5 +469,7 @@ if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "sweep":
+        run_sweep(a)
     else:
         run_native(a)
