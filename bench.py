@@ -140,6 +140,13 @@ def to_points(ranges):
     return xy.reshape(-1, 2), offsets
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def eval_bytes(npts, K):
     return npts * (8 + 32 * K) + 12 + 80
 
@@ -153,16 +160,16 @@ def run_reference(args):
     from gtsam_ndt_b200 import synth
     o = oracle.Oracle(args.res, overlap=args.overlap)
     o.set_grid(-100.0, -100.0, 200.0, 200.0)
-    cores = o.num_threads()
+    cores = host_cores()      # torchrun exports OMP_NUM_THREADS=1; the arm uses every core the process may run on
     nref = args.ref_scans or max(64, min(args.scans, 16 * cores))
     ranges, poses, init, map_xy = make_workload(args, 0, count=nref)
     o.set_target(map_xy)
     xy, off = to_points(ranges)
     for _ in range(max(1, min(args.warmup, 1))):
-        o.align_batch(xy, off, init)
+        o.align_batch(xy, off, init, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = o.align_batch(xy, off, init)
+        res = o.align_batch(xy, off, init, nthreads=cores)
     dt = time.perf_counter() - t0
     v = nref * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -445,16 +452,16 @@ def cpu_baseline(args, xy, offsets, init, map_xy, res_gpu):
     o = oracle.Oracle(args.res, overlap=args.overlap)
     o.set_grid(-100.0, -100.0, 200.0, 200.0)
     o.set_target(map_xy)
-    cores = o.num_threads()
+    cores = host_cores()
     probe = min(len(offsets) - 1, 8 * cores)
     t0 = time.perf_counter()
-    o.align_batch(xy, offsets[: probe + 1], init[:probe])
+    o.align_batch(xy, offsets[: probe + 1], init[:probe], nthreads=cores)
     rate = probe / (time.perf_counter() - t0)
     n = args.cpu_sample or int(min(len(offsets) - 1, max(probe, rate * 12.0)))
     t0 = time.perf_counter()
     reps = 0
     while True:
-        r = o.align_batch(xy, offsets[: n + 1], init[:n])
+        r = o.align_batch(xy, offsets[: n + 1], init[:n], nthreads=cores)
         reps += 1
         dt = time.perf_counter() - t0
         if dt >= 10.0 or reps >= 64:

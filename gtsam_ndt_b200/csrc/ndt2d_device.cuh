@@ -1,7 +1,14 @@
 // Device-side building blocks of the 2D NDT path: lattice index (SPEC 2), per-pair terms (SPEC 4),
-// expneg (SPEC 4.1), warp evaluation with f64 shuffle reduction, and the damped 3x3 solve (SPEC 5).
-// Compiled with -fmad=false: only the explicit fmaf()/fma() calls below fuse, exactly as SPEC.md
-// writes them. Reference file:line: none exists (/root/reference/README.md:1 is the whole mount).
+// expneg (SPEC 4.1), the warp evaluation with SPEC 4's fixed summation order, and the damped 3x3 solve
+// (SPEC 5). Compiled with -fmad=false: only the explicit fma calls below fuse, exactly as SPEC.md writes them.
+// Reference file:line: none exists (/root/reference/README.md:1 is the whole mount).
+//
+// The evaluation is written for Blackwell's packed f32x2 instructions (FFMA2 / FMUL2 / FADD2): SPEC.md v2
+// arranges every per-point quantity as a pair — (rx,ry), (jx,jy), (X,Y), (qx,qy), (ux,uy), (vx,vy), the record
+// pairs (mux,muy) (B00,B01) (B01,B11) — so one packed instruction does both components with the scalar of
+// the other operand broadcast, and the scalar chains (exp, dot-product sums) of the two points a lane owns
+// are packed across the points. Each packed op is the IEEE round-to-nearest op on both halves: results are
+// bit-identical to the scalar oracle.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -10,9 +17,27 @@
 
 namespace ndt2d {
 
-__device__ __forceinline__ float ld_f(const float *p) { return __ldg(p); }
+typedef unsigned long long u64;
 
-// SPEC 2: lattice index. Returns false when outside (also for NaN).
+// ---- packed f32x2 helpers --------------------------------------------------------------------------
+__device__ __forceinline__ u64 pk(float lo, float hi)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ float lo32(u64 v) { float a, b; upk(v, a, b); return a; }
+__device__ __forceinline__ float hi32(u64 v) { float a, b; upk(v, a, b); return b; }
+__device__ __forceinline__ u64 bc(float c) { return pk(c, c); } // broadcast; ptxas folds it into an .F32 operand
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// lo + hi of a packed product pair: the "a*b + c*d" of SPEC 4 (two rounded products, one add)
+__device__ __forceinline__ float hsum(u64 v) { float a, b; upk(v, a, b); return __fadd_rn(a, b); }
+
+// ---- SPEC 2: lattice index (scalar form, used by the small kernels) -----------------------------------
 __device__ __forceinline__ bool lattice(const LevelDev &L, float X, float Y, int &hx, int &hy)
 {
     float fx = __fmul_rn(__fsub_rn(X, L.ox), L.inv_st);
@@ -23,11 +48,10 @@ __device__ __forceinline__ bool lattice(const LevelDev &L, float X, float Y, int
     return inside;
 }
 
-// SPEC 4.1: exp(-h), bit-exact sequence of f32 operations.
+// ---- SPEC 4.1: exp(-h), bit-exact sequence of f32 operations -----------------------------------------
 __device__ __forceinline__ float expneg(float h)
 {
-    float z = __fmul_rn(h, 1.44269502f);
-    float t = __fadd_rn(z, 12582912.0f);
+    float t = __fmaf_rn(h, 1.44269502f, 12582912.0f);
     float nf = __fsub_rn(t, 12582912.0f);
     int ni = __float_as_int(t) - 0x4B400000;
     float r = __fmaf_rn(nf, -0.693145752f, h);
@@ -43,11 +67,35 @@ __device__ __forceinline__ float expneg(float h)
     return __fmul_rn(p, __int_as_float(0x3F800000 - ni * 0x800000));
 }
 
+// The same on two values; nh = -h. Uses fma(h,L,M) == fma(-h,-L,M) and fma(n,-C,h) == -fma(n,C,-h), both exact
+// under round-to-nearest-even, so both halves equal expneg(h) bit for bit.
+// NOTE (ptxas 12.9): mul.rn.f32x2 followed by add/sub.rn.f32x2 is contracted into FFMA2 even with -fmad=false
+// and explicit .rn, unlike the scalar forms. SPEC.md v2 is written so that every packed multiply that feeds a
+// packed add IS an fma; never write mul2 -> add2/sub2 in this file.
+__device__ __forceinline__ u64 expneg2(u64 nh)
+{
+    const u64 MAGIC = bc(12582912.0f);
+    u64 t = fma2(nh, bc(-1.44269502f), MAGIC);
+    u64 nf = sub2(t, MAGIC);
+    float t0, t1;
+    upk(t, t0, t1);
+    int n0 = __float_as_int(t0) - 0x4B400000, n1 = __float_as_int(t1) - 0x4B400000;
+    u64 y = fma2(nf, bc(0.693145752f), nh);
+    y = fma2(nf, bc(1.42860677e-6f), y);
+    u64 p = fma2(bc(1.38888889e-3f), y, bc(8.33333333e-3f));
+    p = fma2(p, y, bc(4.16666667e-2f));
+    p = fma2(p, y, bc(1.66666667e-1f));
+    p = fma2(p, y, bc(0.5f));
+    p = fma2(p, y, bc(1.0f));
+    p = fma2(p, y, bc(1.0f));
+    return mul2(p, pk(__int_as_float(0x3F800000 - n0 * 0x800000), __int_as_float(0x3F800000 - n1 * 0x800000)));
+}
+
+// ---- SPEC 4: pose and point -----------------------------------------------------------------------------
 struct Pose32 {
     float c, s, tx, ty;
 };
 
-// SPEC 4: pose to f32 (f64 sincos, one rounding each)
 __device__ __forceinline__ Pose32 pose_to_f32(double tx, double ty, double th)
 {
     double sn, cs;
@@ -60,55 +108,79 @@ __device__ __forceinline__ Pose32 pose_to_f32(double tx, double ty, double th)
     return q;
 }
 
-// One cell record = two 16-byte halves {mux, muy, B00, B01 | B11, det, n, valid}
-struct CellRec {
-    float4 a, b;
-};
-
-__device__ __forceinline__ CellRec load_cell(const float4 *__restrict__ cells, size_t idx)
+// SPEC 4: a point that cannot lie in any lattice becomes the finite far-away point (1e18, 1e18)
+__device__ __forceinline__ float2 sanitize(float2 p)
 {
-    CellRec r;
-    r.a = __ldg(cells + 2 * idx);
-    r.b = __ldg(cells + 2 * idx + 1);
+    bool bad = !(fabsf(p.x) <= 1e18f) || !(fabsf(p.y) <= 1e18f); // also true for NaN
+    return bad ? make_float2(1e18f, 1e18f) : p;
+}
+
+struct PosePk {
+    u64 cs, nsc, ncns, t; // (c,s) (-s,c) (-c,-s) (tx,ty)
+};
+__device__ __forceinline__ PosePk pose_pack(const Pose32 &q)
+{
+    PosePk P;
+    P.cs = pk(q.c, q.s);
+    P.nsc = pk(-q.s, q.c);
+    P.ncns = pk(-q.c, -q.s);
+    P.t = pk(q.tx, q.ty);
+    return P;
+}
+
+struct PointPk {
+    u64 r, j, XY; // (rx,ry) (jx,jy) (X,Y)
+};
+__device__ __forceinline__ PointPk transform_point(const PosePk &P, float x, float y)
+{
+    PointPk p;
+    p.r = fma2(P.cs, bc(x), mul2(P.nsc, bc(y)));   // rx = fma(c,x,ns*y), ry = fma(s,x,c*y)
+    p.j = fma2(P.nsc, bc(x), mul2(P.ncns, bc(y))); // jx = fma(ns,x,nc*y), jy = fma(c,x,ns*y)
+    p.XY = add2(p.r, P.t);
+    return p;
+}
+
+// ---- cell record: four f32 pairs in one 256-bit load ------------------------------------------------------
+struct Cell4 {
+    u64 mu, B0, B1, nv; // (mux,muy) (B00,B01) (B01,B11) (n,valid)
+};
+__device__ __forceinline__ Cell4 load_cell(const float4 *__restrict__ cells, unsigned idx)
+{
+    Cell4 r;
+    const float4 *p = cells + 2 * (size_t)idx;
+    asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.mu), "=l"(r.B0), "=l"(r.B1), "=l"(r.nv) : "l"(p));
     return r;
 }
 
-// SPEC 4: the ten f32 terms of one (point, cell) pair. Returns false when the pair is skipped.
-template <bool FULL>
-__device__ __forceinline__ bool pair_terms(const CellRec &rec, float rx, float ry, float X, float Y, float T[10])
+// ---- SPEC 4 per-pair terms, scalar form (diagnostic kernel k_point_terms) --------------------------------
+__device__ __forceinline__ bool pair_terms_scalar(const Cell4 &c, const PointPk &p, float T[10])
 {
-    if (rec.b.w == 0.0f) return false;
-    const float B00 = rec.a.z, B01 = rec.a.w, B11 = rec.b.x;
-    float qx = __fsub_rn(X, rec.a.x), qy = __fsub_rn(Y, rec.a.y);
-    float ux = __fmaf_rn(B00, qx, __fmul_rn(B01, qy));
-    float uy = __fmaf_rn(B01, qx, __fmul_rn(B11, qy));
-    float mm = __fmaf_rn(qx, ux, __fmul_rn(qy, uy));
+    float mux, muy, B00, B01, B01b, B11, nn, valid, rx, ry, jx, jy, X, Y;
+    upk(c.mu, mux, muy); upk(c.B0, B00, B01); upk(c.B1, B01b, B11); upk(c.nv, nn, valid);
+    upk(p.r, rx, ry); upk(p.j, jx, jy); upk(p.XY, X, Y);
+    if (valid == 0.0f) return false;
+    float qx = __fsub_rn(X, mux), qy = __fsub_rn(Y, muy);
+    float ux = __fmaf_rn(B00, qx, __fmul_rn(B01, qy)), uy = __fmaf_rn(B01, qx, __fmul_rn(B11, qy));
+    float mm = __fadd_rn(__fmul_rn(qx, ux), __fmul_rn(qy, uy));
     float h = __fmul_rn(0.5f, mm);
     if (!(h < 30.0f)) return false;
     float e = expneg(h);
-    T[0] = e;
-    if (FULL) {
-        float a2 = __fmaf_rn(uy, rx, -__fmul_rn(ux, ry));
-        float vx = __fmaf_rn(B01, rx, -__fmul_rn(B00, ry));
-        float vy = __fmaf_rn(B11, rx, -__fmul_rn(B01, ry));
-        float w = __fmaf_rn(ux, rx, __fmul_rn(uy, ry));
-        float k = __fmaf_rn(rx, vy, -__fmul_rn(ry, vx));
-        k = __fsub_rn(k, w);
-        k = __fmaf_rn(-a2, a2, k);
-        T[1] = __fmul_rn(e, ux);
-        T[2] = __fmul_rn(e, uy);
-        T[3] = __fmul_rn(e, a2);
-        T[4] = __fmul_rn(e, __fmaf_rn(-ux, ux, B00));
-        T[5] = __fmul_rn(e, __fmaf_rn(-ux, uy, B01));
-        T[6] = __fmul_rn(e, __fmaf_rn(-ux, a2, vx));
-        T[7] = __fmul_rn(e, __fmaf_rn(-uy, uy, B11));
-        T[8] = __fmul_rn(e, __fmaf_rn(-uy, a2, vy));
-        T[9] = __fmul_rn(e, k);
-    }
+    float a2 = __fadd_rn(__fmul_rn(ux, jx), __fmul_rn(uy, jy));
+    float vx = __fmaf_rn(B00, jx, __fmul_rn(B01, jy)), vy = __fmaf_rn(B01, jx, __fmul_rn(B11, jy));
+    float w = __fadd_rn(__fmul_rn(ux, rx), __fmul_rn(uy, ry));
+    float k = __fadd_rn(__fmul_rn(jx, vx), __fmul_rn(jy, vy));
+    k = __fsub_rn(k, w);
+    k = __fmaf_rn(-a2, a2, k);
+    T[0] = e; // the factors (e, c1..c9) that SPEC 4 accumulates with acc_t = fma(e, c_t, acc_t)
+    T[1] = ux; T[2] = uy; T[3] = a2;
+    T[4] = __fmaf_rn(-ux, ux, B00); T[5] = __fmaf_rn(-ux, uy, B01); T[6] = __fmaf_rn(-a2, ux, vx);
+    T[7] = __fmaf_rn(-uy, uy, B11); T[8] = __fmaf_rn(-a2, uy, vy);
+    T[9] = k;
     return true;
 }
 
-// Result of one evaluation held redundantly by every lane of the warp.
+// ---- SPEC 4 evaluation for one warp -------------------------------------------------------------------------
+// Result of one evaluation, held redundantly by every lane.
 struct Eval {
     double v[10];
     int count;
@@ -118,253 +190,138 @@ __device__ __forceinline__ double warp_sum(double x)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    return x; // xor butterfly: every lane ends with the same bits
+    return x; // SPEC 4's butterfly: D[l] + D[l xor o] is commutative, every lane ends with the same bits
 }
 
-// SPEC 4 for one warp: lanes stride over the scan (shared or global memory), f32 terms are widened
-// and summed in f64 per lane, then a fixed xor-butterfly combines the lanes (deterministic).
-template <int OV, bool FULL>
-__device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane,
-                                          Eval &E)
-{
-    constexpr int NT = FULL ? 10 : 1;
-    double acc[NT];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) acc[t] = 0.0;
-    int cnt = 0;
-    const float4 *__restrict__ cells = L.cells;
-#pragma unroll 2
-    for (int i = lane; i < n; i += 32) {
-        float2 p = pts[i];
-        float rx = __fmaf_rn(q.c, p.x, -__fmul_rn(q.s, p.y));
-        float ry = __fmaf_rn(q.s, p.x, __fmul_rn(q.c, p.y));
-        float X = __fadd_rn(rx, q.tx), Y = __fadd_rn(ry, q.ty);
-        int hx, hy;
-        if (!lattice(L, X, Y, hx, hy)) continue;
-        size_t base = (size_t)hy * (size_t)L.njx + (size_t)hx;
-        if (OV == 0) {
-            CellRec rec = load_cell(cells, base);
-            float T[10];
-            if (pair_terms<FULL>(rec, rx, ry, X, Y, T)) {
-#pragma unroll
-                for (int t = 0; t < NT; ++t) acc[t] += (double)T[t];
-                cnt += 1;
-            }
-        } else {
-            CellRec rec[4];
-            rec[0] = load_cell(cells, base);
-            rec[1] = load_cell(cells, base + 1);
-            rec[2] = load_cell(cells, base + L.njx);
-            rec[3] = load_cell(cells, base + L.njx + 1);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float T[10];
-                if (pair_terms<FULL>(rec[k], rx, ry, X, Y, T)) {
-#pragma unroll
-                    for (int t = 0; t < NT; ++t) acc[t] += (double)T[t];
-                    cnt += 1;
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < NT; ++t) E.v[t] = warp_sum(acc[t]);
-    if (!FULL) {
-#pragma unroll
-        for (int t = 1; t < 10; ++t) E.v[t] = 0.0;
-    }
-    E.count = __reduce_add_sync(0xffffffffu, cnt);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Packed path: Blackwell's f32x2 instructions (FFMA2 / FMUL2 / FADD2) carry two points per issue slot.
-// Every packed operation is the IEEE round-to-nearest operation of SPEC 4 applied to both halves, so
-// the terms are bit-identical to the scalar path above; negations are sign-bit flips (exact).
-// Identities used to place the negations (all exact under round-to-nearest-even):
-//   -(a*b) == (-a)*b,   fma(n,-C,h) == -fma(n,C,-h),   z + M == M - (-z).
-// ------------------------------------------------------------------------------------------------
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 pk(float lo, float hi)
-{
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 pk1(float c) { return pk(c, c); }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ u64 neg2(u64 a) { return a ^ 0x8000000080000000ull; }
-
-// 32-byte cell record in one 256-bit load (LDG.E.256 on sm_100a)
-struct Cell8 {
-    float mux, muy, B00, B01, B11, det, n, valid;
+// f32 partial sums of one lane = SPEC 4's partials p = 2*lane (point A) and 2*lane + 1 (point B)
+struct Partials {
+    u64 s12[2], s45[2], s68[2]; // per point: (T1,T2) (T4,T5) (T6,T8)
+    u64 s0, s3, s7, s9;         // (A,B): T0 T3 T7 T9
 };
-__device__ __forceinline__ Cell8 load_cell256(const float4 *__restrict__ cells, unsigned idx)
-{
-    Cell8 r;
-    const float4 *p = cells + 2 * (size_t)idx;
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(r.mux), "=f"(r.muy), "=f"(r.B00), "=f"(r.B01), "=f"(r.B11), "=f"(r.det), "=f"(r.n), "=f"(r.valid)
-        : "l"(p));
-    return r;
-}
 
-// pose constants replicated into both halves, built once per evaluation
-struct Pose2 {
-    u64 c, s, ns, tx, ty;
-};
-__device__ __forceinline__ Pose2 pose_pack(const Pose32 &q)
-{
-    Pose2 P;
-    P.c = pk1(q.c); P.s = pk1(q.s); P.ns = pk1(-q.s); P.tx = pk1(q.tx); P.ty = pk1(q.ty);
-    return P;
-}
-
-// SPEC 4.1 on two values; nh = -h. Returns exp(-h) in both halves.
-__device__ __forceinline__ u64 expneg2(u64 nh)
-{
-    const u64 MAGIC = pk1(12582912.0f);
-    u64 nz = mul2(nh, pk1(1.44269502f));
-    u64 t = sub2(MAGIC, nz);
-    u64 nf = sub2(t, MAGIC);
-    float t0, t1;
-    upk(t, t0, t1);
-    int n0 = __float_as_int(t0) - 0x4B400000, n1 = __float_as_int(t1) - 0x4B400000;
-    u64 y = fma2(nf, pk1(0.693145752f), nh);
-    y = fma2(nf, pk1(1.42860677e-6f), y);
-    u64 p = fma2(pk1(1.38888889e-3f), y, pk1(8.33333333e-3f));
-    p = fma2(p, y, pk1(4.16666667e-2f));
-    p = fma2(p, y, pk1(1.66666667e-1f));
-    p = fma2(p, y, pk1(0.5f));
-    p = fma2(p, y, pk1(1.0f));
-    p = fma2(p, y, pk1(1.0f));
-    return mul2(p, pk(__int_as_float(0x3F800000 - n0 * 0x800000), __int_as_float(0x3F800000 - n1 * 0x800000)));
-}
-
-// SPEC 4 for two (point, cell) pairs at once. ok0/ok1 say which halves contribute (already false for
-// points outside the lattice); they are cleared for invalid cells and for h >= 30.
+// one cell for the lane's two points
 template <bool FULL>
-__device__ __forceinline__ void pair_terms2(const Cell8 &r0, const Cell8 &r1, u64 rx, u64 ry, u64 nry, u64 X, u64 Y,
-                                            bool &ok0, bool &ok1, u64 T[10])
+__device__ __forceinline__ void accumulate_cell(const Cell4 &cA, const Cell4 &cB, const PointPk &A, const PointPk &B, bool inA,
+                                                bool inB, Partials &S, int &cnt)
 {
-    ok0 = ok0 && (r0.valid != 0.0f);
-    ok1 = ok1 && (r1.valid != 0.0f);
-    const u64 B00 = pk(r0.B00, r1.B00), B01 = pk(r0.B01, r1.B01), B11 = pk(r0.B11, r1.B11);
-    u64 qx = sub2(X, pk(r0.mux, r1.mux)), qy = sub2(Y, pk(r0.muy, r1.muy));
-    u64 ux = fma2(B00, qx, mul2(B01, qy));
-    u64 uy = fma2(B01, qx, mul2(B11, qy));
-    u64 mm = fma2(qx, ux, mul2(qy, uy));
-    u64 nh = mul2(pk1(-0.5f), mm);
-    float nh0, nh1;
-    upk(nh, nh0, nh1);
-    ok0 = ok0 && (nh0 > -30.0f);
-    ok1 = ok1 && (nh1 > -30.0f);
+    // q = XY - mu ; u = B q ; m = q.u ; nh = -0.5 m
+    u64 qA = sub2(A.XY, cA.mu), qB = sub2(B.XY, cB.mu);
+    u64 uA = fma2(cA.B0, bc(lo32(qA)), mul2(cA.B1, bc(hi32(qA))));
+    u64 uB = fma2(cB.B0, bc(lo32(qB)), mul2(cB.B1, bc(hi32(qB))));
+    u64 nh = mul2(bc(-0.5f), pk(hsum(mul2(qA, uA)), hsum(mul2(qB, uB))));
+    bool okA = inA && (hi32(cA.nv) != 0.0f) && (lo32(nh) > -30.0f);
+    bool okB = inB && (hi32(cB.nv) != 0.0f) && (hi32(nh) > -30.0f);
     u64 e = expneg2(nh);
-    T[0] = e;
+    // skipped pairs get e = 0: fma(0, c, acc) == acc bit for bit (every c is finite, see sanitize())
+    e = pk(okA ? lo32(e) : 0.0f, okB ? hi32(e) : 0.0f);
+    cnt += (okA ? 1 : 0) + (okB ? 1 : 0);
+    S.s0 = add2(S.s0, e);
     if (FULL) {
-        u64 nux = neg2(ux), nuy = neg2(uy);
-        u64 a2 = fma2(uy, rx, mul2(ux, nry));
-        u64 vx = fma2(B01, rx, mul2(B00, nry));
-        u64 vy = fma2(B11, rx, mul2(B01, nry));
-        u64 w = fma2(ux, rx, mul2(uy, ry));
-        u64 k = fma2(rx, vy, mul2(nry, vx));
-        k = sub2(k, w);
-        k = fma2(neg2(a2), a2, k);
-        T[1] = mul2(e, ux);
-        T[2] = mul2(e, uy);
-        T[3] = mul2(e, a2);
-        T[4] = mul2(e, fma2(nux, ux, B00));
-        T[5] = mul2(e, fma2(nux, uy, B01));
-        T[6] = mul2(e, fma2(nux, a2, vx));
-        T[7] = mul2(e, fma2(nuy, uy, B11));
-        T[8] = mul2(e, fma2(nuy, a2, vy));
-        T[9] = mul2(e, k);
+        const float eA = lo32(e), eB = hi32(e);
+        float a2A = hsum(mul2(uA, A.j)), a2B = hsum(mul2(uB, B.j));
+        u64 vA = fma2(cA.B0, bc(lo32(A.j)), mul2(cA.B1, bc(hi32(A.j))));
+        u64 vB = fma2(cB.B0, bc(lo32(B.j)), mul2(cB.B1, bc(hi32(B.j))));
+        float wA = hsum(mul2(uA, A.r)), wB = hsum(mul2(uB, B.r));
+        u64 k = sub2(pk(hsum(mul2(A.j, vA)), hsum(mul2(B.j, vB))), pk(wA, wB));
+        u64 a2 = pk(a2A, a2B);
+        k = fma2(pk(-a2A, -a2B), a2, k);
+        // acc_t = fma(e, c_t, acc_t): per point pairs (c1,c2) (c4,c5) (c6,c8) ...
+        S.s12[0] = fma2(bc(eA), uA, S.s12[0]);
+        S.s12[1] = fma2(bc(eB), uB, S.s12[1]);
+        S.s45[0] = fma2(bc(eA), fma2(bc(-lo32(uA)), uA, cA.B0), S.s45[0]);
+        S.s45[1] = fma2(bc(eB), fma2(bc(-lo32(uB)), uB, cB.B0), S.s45[1]);
+        S.s68[0] = fma2(bc(eA), fma2(bc(-a2A), uA, vA), S.s68[0]);
+        S.s68[1] = fma2(bc(eB), fma2(bc(-a2B), uB, vB), S.s68[1]);
+        // ... and c3, c7, c9 across the two points
+        u64 uy = pk(hi32(uA), hi32(uB));
+        u64 c7 = fma2(pk(-hi32(uA), -hi32(uB)), uy, pk(hi32(cA.B1), hi32(cB.B1)));
+        S.s3 = fma2(e, a2, S.s3);
+        S.s7 = fma2(e, c7, S.s7);
+        S.s9 = fma2(e, k, S.s9);
     }
 }
 
-// SPEC 4 for one warp, packed: the scan lives in shared memory as two planes xs[], ys[] padded with NaN
-// to a multiple of 64 points; lane l takes points (64 j + 2 l, 64 j + 2 l + 1). Cell records arrive through
-// one 256-bit load each; points outside the lattice read record 0 and are masked.
-template <int OV, bool FULL>
-__device__ __forceinline__ void eval_warp2(const LevelDev &L, const float *xs, const float *ys, int npad, const Pose32 &q,
-                                           int lane, Eval &E)
+// Where the warp's points come from: AoS float2 in shared memory, sanitised and padded with the far-away
+// point to a multiple of 64 (SMEM), or global memory with bounds checks (scans too long for the slot).
+template <bool SMEM>
+__device__ __forceinline__ void load_two(const float2 *pts, int n, int i, float2 &a, float2 &b)
 {
-    constexpr int NT = FULL ? 10 : 1;
-    double acc[NT];
+    if (SMEM) {
+        float4 v = *reinterpret_cast<const float4 *>(pts + i);
+        a = make_float2(v.x, v.y);
+        b = make_float2(v.z, v.w);
+    } else {
+        const float2 far = make_float2(1e18f, 1e18f);
+        a = i < n ? sanitize(__ldg(pts + i)) : far;
+        b = i + 1 < n ? sanitize(__ldg(pts + i + 1)) : far;
+    }
+}
+
+// SPEC 4 for one warp. Lane l owns points 64 j + 2 l (A) and 64 j + 2 l + 1 (B), i.e. partials 2l and 2l+1.
+template <int OV, bool FULL, bool SMEM>
+__device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E)
+{
+    Partials S;
+    S.s0 = S.s3 = S.s7 = S.s9 = 0ull;
 #pragma unroll
-    for (int t = 0; t < NT; ++t) acc[t] = 0.0;
+    for (int k = 0; k < 2; ++k) S.s12[k] = S.s45[k] = S.s68[k] = 0ull;
     int cnt = 0;
     const float4 *__restrict__ cells = L.cells;
-    const Pose2 P = pose_pack(q);
-    const u64 ox = pk1(L.ox), oy = pk1(L.oy), inv = pk1(L.inv_st);
+    const PosePk P = pose_pack(q);
+    const u64 org = pk(L.ox, L.oy), inv = bc(L.inv_st);
     const float nhxf = L.nhxf, nhyf = L.nhyf;
     const unsigned njx = (unsigned)L.njx;
+    const int npad = (n + 63) & ~63;
 #pragma unroll 1
     for (int i = 2 * lane; i < npad; i += 64) {
-        u64 x = *reinterpret_cast<const u64 *>(xs + i), y = *reinterpret_cast<const u64 *>(ys + i);
-        u64 rx = fma2(P.c, x, mul2(P.ns, y));
-        u64 ry = fma2(P.s, x, mul2(P.c, y));
-        u64 X = add2(rx, P.tx), Y = add2(ry, P.ty);
-        u64 fx = mul2(sub2(X, ox), inv), fy = mul2(sub2(Y, oy), inv);
-        float fx0, fx1, fy0, fy1;
-        upk(fx, fx0, fx1);
-        upk(fy, fy0, fy1);
-        bool in0 = (fx0 >= 0.0f) && (fx0 < nhxf) && (fy0 >= 0.0f) && (fy0 < nhyf);
-        bool in1 = (fx1 >= 0.0f) && (fx1 < nhxf) && (fy1 >= 0.0f) && (fy1 < nhyf);
-        unsigned b0 = in0 ? (unsigned)(int)fy0 * njx + (unsigned)(int)fx0 : 0u;
-        unsigned b1 = in1 ? (unsigned)(int)fy1 * njx + (unsigned)(int)fx1 : 0u;
-        u64 nry = neg2(ry);
-        // K = 1: one record per point. K = 4: two rows of two adjacent records (64 contiguous bytes per row);
-        // rows are processed one after the other to bound the registers held by in-flight loads.
+        float2 a, b;
+        load_two<SMEM>(pts, n, i, a, b);
+        const PointPk A = transform_point(P, a.x, a.y), B = transform_point(P, b.x, b.y);
+        u64 fA = mul2(sub2(A.XY, org), inv), fB = mul2(sub2(B.XY, org), inv);
+        float fxA, fyA, fxB, fyB;
+        upk(fA, fxA, fyA);
+        upk(fB, fxB, fyB);
+        const bool inA = (fxA >= 0.0f) && (fxA < nhxf) && (fyA >= 0.0f) && (fyA < nhyf);
+        const bool inB = (fxB >= 0.0f) && (fxB < nhxf) && (fyB >= 0.0f) && (fyB < nhyf);
+        const unsigned bA = (unsigned)(int)fyA * njx + (unsigned)(int)fxA;
+        const unsigned bB = (unsigned)(int)fyB * njx + (unsigned)(int)fxB;
+        // K = 1: one record per point. K = 4: two rows of two adjacent records (64 contiguous bytes per row),
+        // processed row by row to bound the registers held by loads in flight.
         constexpr int ROWS = OV ? 2 : 1, COLS = OV ? 2 : 1;
 #pragma unroll
-        for (int b = 0; b < ROWS; ++b) {
-            Cell8 r0[COLS], r1[COLS];
+        for (int rb = 0; rb < ROWS; ++rb) {
+            Cell4 cA[COLS], cB[COLS];
 #pragma unroll
-            for (int a = 0; a < COLS; ++a) {
-                r0[a] = load_cell256(cells, b0 + a + b * njx);
-                r1[a] = load_cell256(cells, b1 + a + b * njx);
+            for (int ca = 0; ca < COLS; ++ca) {
+                cA[ca].mu = cA[ca].B0 = cA[ca].B1 = cA[ca].nv = 0ull; // outside the lattice: an all-zero (invalid) record
+                cB[ca].mu = cB[ca].B0 = cB[ca].B1 = cB[ca].nv = 0ull;
+                if (inA) cA[ca] = load_cell(cells, bA + ca + rb * njx);
+                if (inB) cB[ca] = load_cell(cells, bB + ca + rb * njx);
             }
 #pragma unroll
-            for (int a = 0; a < COLS; ++a) {
-                bool ok0 = in0, ok1 = in1;
-                u64 T[10];
-                pair_terms2<FULL>(r0[a], r1[a], rx, ry, nry, X, Y, ok0, ok1, T);
-                if (ok0) {
-#pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        float lo, hi;
-                        upk(T[t], lo, hi);
-                        acc[t] += (double)lo;
-                    }
-                    cnt += 1;
-                }
-                if (ok1) {
-#pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        float lo, hi;
-                        upk(T[t], lo, hi);
-                        acc[t] += (double)hi;
-                    }
-                    cnt += 1;
-                }
-            }
+            for (int ca = 0; ca < COLS; ++ca) accumulate_cell<FULL>(cA[ca], cB[ca], A, B, inA, inB, S, cnt);
         }
     }
-#pragma unroll
-    for (int t = 0; t < NT; ++t) E.v[t] = warp_sum(acc[t]);
-    if (!FULL) {
+    // SPEC 4: D[l] = (double)P[2l] + (double)P[2l+1], then the butterfly
+    E.v[0] = warp_sum((double)lo32(S.s0) + (double)hi32(S.s0));
+    if (FULL) {
+        E.v[1] = warp_sum((double)lo32(S.s12[0]) + (double)lo32(S.s12[1]));
+        E.v[2] = warp_sum((double)hi32(S.s12[0]) + (double)hi32(S.s12[1]));
+        E.v[3] = warp_sum((double)lo32(S.s3) + (double)hi32(S.s3));
+        E.v[4] = warp_sum((double)lo32(S.s45[0]) + (double)lo32(S.s45[1]));
+        E.v[5] = warp_sum((double)hi32(S.s45[0]) + (double)hi32(S.s45[1]));
+        E.v[6] = warp_sum((double)lo32(S.s68[0]) + (double)lo32(S.s68[1]));
+        E.v[7] = warp_sum((double)lo32(S.s7) + (double)hi32(S.s7));
+        E.v[8] = warp_sum((double)hi32(S.s68[0]) + (double)hi32(S.s68[1]));
+        E.v[9] = warp_sum((double)lo32(S.s9) + (double)hi32(S.s9));
+    } else {
 #pragma unroll
         for (int t = 1; t < 10; ++t) E.v[t] = 0.0;
     }
     E.count = __reduce_add_sync(0xffffffffu, cnt);
 }
 
-// SPEC 5: damped Cholesky solve in f64, no contraction. g = v[1..3], H6 = v[4..9].
+// ---- SPEC 5: damped Cholesky solve in f64, no contraction. g = v[1..3], H6 = v[4..9] -------------------
 __device__ __forceinline__ bool solve3(const double *g, const double *H6, double lambda, double d[3])
 {
     double A00 = H6[0] + lambda * fmax(fabs(H6[0]), 1e-9);

@@ -116,8 +116,9 @@ __global__ void __launch_bounds__(256) k_finalize(const LevelDev L, float4 *__re
                 int jx = (int)(c % L.njx), jy = (int)(c / L.njx);
                 double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
                 double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
-                ra = make_float4((float)(cx + mx), (float)(cy + my), (float)(cyy / det), (float)(-(cxy / det)));
-                rb = make_float4((float)(cxx / det), (float)det, (float)n, 1.0f);
+                const float b01 = (float)(-(cxy / det));
+                ra = make_float4((float)(cx + mx), (float)(cy + my), (float)(cyy / det), b01);
+                rb = make_float4(b01, (float)(cxx / det), (float)n, 1.0f);
             }
         }
         cells[2 * c] = ra;
@@ -138,10 +139,9 @@ __global__ void k_cell_index(const LevelDev L, const float2 *__restrict__ xy, in
     float X = p.x, Y = p.y;
     if (pose) {
         Pose32 q = pose_to_f32(pose[0], pose[1], pose[2]);
-        float rx = __fmaf_rn(q.c, p.x, -__fmul_rn(q.s, p.y));
-        float ry = __fmaf_rn(q.s, p.x, __fmul_rn(q.c, p.y));
-        X = __fadd_rn(rx, q.tx);
-        Y = __fadd_rn(ry, q.ty);
+        float2 ps = sanitize(p);
+        PointPk t = transform_point(pose_pack(q), ps.x, ps.y);
+        upk(t.XY, X, Y);
     }
     int hx, hy;
     idx[i] = lattice(L, X, Y, hx, hy) ? hy * L.nhx + hx : -1;
@@ -155,19 +155,19 @@ __global__ void k_point_terms(const LevelDev L, const float2 *__restrict__ xy, i
     if (i >= n) return;
     constexpr int K = OV ? 4 : 1;
     Pose32 q = pose_to_f32(pose[0], pose[1], pose[2]);
-    float2 p = xy[i];
-    float rx = __fmaf_rn(q.c, p.x, -__fmul_rn(q.s, p.y));
-    float ry = __fmaf_rn(q.s, p.x, __fmul_rn(q.c, p.y));
-    float X = __fadd_rn(rx, q.tx), Y = __fadd_rn(ry, q.ty);
+    float2 p = sanitize(xy[i]);
+    PointPk pt = transform_point(pose_pack(q), p.x, p.y);
+    float X, Y;
+    upk(pt.XY, X, Y);
     float *out = terms + (size_t)i * K * 10;
     for (int t = 0; t < K * 10; ++t) out[t] = 0.0f;
     int hx, hy;
     if (!lattice(L, X, Y, hx, hy)) return;
     for (int k = 0; k < K; ++k) {
-        size_t cidx = (size_t)(hy + (k >> 1)) * L.njx + (size_t)(hx + (k & 1));
-        CellRec rec = load_cell(L.cells, cidx);
+        unsigned cidx = (unsigned)(hy + (k >> 1)) * (unsigned)L.njx + (unsigned)(hx + (k & 1));
+        Cell4 rec = load_cell(L.cells, cidx);
         float T[10];
-        if (pair_terms<true>(rec, rx, ry, X, Y, T))
+        if (pair_terms_scalar(rec, pt, T))
             for (int t = 0; t < 10; ++t) out[k * 10 + t] = T[t];
     }
 }
@@ -188,14 +188,10 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_poses(const LevelDev L, c
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int npad = (n + 63) & ~63;
-    float *xs = reinterpret_cast<float *>(smem_raw), *ys = xs + npad;
+    float2 *sp = reinterpret_cast<float2 *>(smem_raw);
     if (STAGED) {
-        // two planes, NaN padded to a multiple of 64 points (NaN is outside every lattice)
-        for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-            float2 p = i < n ? __ldg(xy + i) : make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
-            xs[i] = p.x;
-            ys[i] = p.y;
-        }
+        // sanitised points, padded with the far-away point to a multiple of 64 (SPEC 4)
+        for (int i = threadIdx.x; i < npad; i += blockDim.x) sp[i] = i < n ? sanitize(__ldg(xy + i)) : make_float2(1e18f, 1e18f);
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
@@ -211,8 +207,8 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_poses(const LevelDev L, c
         }
         Pose32 q = pose_to_f32(tx, ty, th);
         Eval E;
-        if (STAGED) eval_warp2<OV, FULL>(L, xs, ys, npad, q, lane, E);
-        else eval_warp<OV, FULL>(L, xy, n, q, lane, E);
+        if (STAGED) eval_warp<OV, FULL, true>(L, sp, n, q, lane, E);
+        else eval_warp<OV, FULL, false>(L, xy, n, q, lane, E);
         if (lane == 0) {
             if (FULL) {
 #pragma unroll
@@ -234,18 +230,16 @@ static constexpr int ALIGN_MIN_BLOCKS = 3; // 24 warps/SM: bounds registers at 8
 
 // SPEC 5, one pyramid level. Every lane carries the same f64 state (the butterfly reduction gives
 // all lanes identical sums), so the control flow is warp-uniform and needs no broadcast.
-// where a warp reads its scan from: two NaN-padded shared-memory planes (packed path) or global memory
+// where a warp reads its scan from: its padded shared-memory slot or global memory
 struct ScanView {
     const float2 *pts;
-    const float *xs, *ys;
-    int n, npad;
+    int n;
 };
 
 template <int OV, bool STAGED>
 __device__ __forceinline__ void eval_scan(const LevelDev &L, const ScanView &v, const Pose32 &q, int lane, Eval &E)
 {
-    if (STAGED) eval_warp2<OV, true>(L, v.xs, v.ys, v.npad, q, lane, E);
-    else eval_warp<OV, true>(L, v.pts, v.n, q, lane, E);
+    eval_warp<OV, true, STAGED>(L, v.pts, v.n, q, lane, E);
 }
 
 // Per-warp LM state kept in shared memory between evaluations so that it does not occupy registers
@@ -332,18 +326,17 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool SM = STAGED || RANGES;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per-warp slot: xs[cap] then ys[cap], cap a multiple of 64 points
+    // per-warp slot of cap points (a multiple of 64), after the warp states
     WarpState *ws = reinterpret_cast<WarpState *>(smem_raw) + warp;
-    float *xs = reinterpret_cast<float *>(smem_raw + (ALIGN_THREADS / 32) * sizeof(WarpState)) + (size_t)warp * 2 * a.cap_points;
-    float *ys = xs + a.cap_points;
-    const float qnan = __int_as_float(0x7fc00000);
+    float2 *slot = reinterpret_cast<float2 *>(smem_raw + (ALIGN_THREADS / 32) * sizeof(WarpState)) + (size_t)warp * a.cap_points;
+    const float2 far = make_float2(1e18f, 1e18f);
     for (;;) {
         unsigned job = 0;
         if (lane == 0) job = atomicAdd(a.counter, 1u);
         job = __shfl_sync(FULL_MASK, job, 0);
         if (job >= (unsigned)a.nscans) break;
         ScanView v;
-        v.pts = nullptr; v.xs = xs; v.ys = ys; v.n = 0; v.npad = 0;
+        v.pts = slot; v.n = 0;
         if (RANGES) {
             // SPEC 8: keep beams with range_min <= rho <= range_max, in beam order
             int kept = 0;
@@ -366,8 +359,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
                 if (ok) {
                     float2 bt = __ldg(a.beams + b);
                     int dst = kept + __popc(m & ((1u << lane) - 1u));
-                    xs[dst] = __fmul_rn(rho, bt.x);
-                    ys[dst] = __fmul_rn(rho, bt.y);
+                    slot[dst] = sanitize(make_float2(__fmul_rn(rho, bt.x), __fmul_rn(rho, bt.y)));
                 }
                 kept += __popc(m);
             }
@@ -377,18 +369,14 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
             v.n = (int)(o1 - o0);
             const float2 *src = a.xy + o0;
             if (STAGED) {
-                for (int i = lane; i < v.n; i += 32) {
-                    float2 p = __ldg(src + i);
-                    xs[i] = p.x;
-                    ys[i] = p.y;
-                }
+                for (int i = lane; i < v.n; i += 32) slot[i] = sanitize(__ldg(src + i));
             } else {
                 v.pts = src;
             }
         }
         if (SM) {
-            v.npad = (v.n + 63) & ~63;
-            for (int i = v.n + lane; i < v.npad; i += 32) { xs[i] = qnan; ys[i] = qnan; }
+            const int npad = (v.n + 63) & ~63;
+            for (int i = v.n + lane; i < npad; i += 32) slot[i] = far;
             __syncwarp();
         }
         double p[3] = {__ldg(a.init + 3 * (size_t)job), __ldg(a.init + 3 * (size_t)job + 1), __ldg(a.init + 3 * (size_t)job + 2)};

@@ -119,7 +119,7 @@ int ndt2d_add_target(ndt2d_matcher *m, const float *xy, int64_t n);
 int ndt2d_add_target_device(ndt2d_matcher *m, const float *d_xy, int64_t n);
 /* geom = {res, st, inv_st, ox, oy}; dims = {nhx, nhy, njx, njy} */
 int ndt2d_level_geometry(const ndt2d_matcher *m, int level, float geom[5], int32_t dims[4]);
-/* cell table: njx*njy records of 8 floats {mux, muy, B00, B01, B11, det, n, valid} */
+/* cell table: njx*njy records of 8 floats {mux, muy, B00, B01, B01, B11, n, valid} */
 int ndt2d_get_cells(ndt2d_matcher *m, int level, float *cells);
 /* raw accumulators: n[njx*njy] and sums[njx*njy*5] = {sx, sy, sxx, sxy, syy} in 2^-20 m units */
 int ndt2d_get_sums(ndt2d_matcher *m, int level, uint32_t *n, int64_t *sums);
@@ -136,7 +136,7 @@ int ndt2d_evaluate(ndt2d_matcher *m, int level, const float *xy, int n, const do
                    double *out, int32_t *count);
 int ndt2d_evaluate_device(ndt2d_matcher *m, int level, const float *d_xy, int n, const double *d_poses,
                           int npose, double *d_out, int32_t *d_count);
-/* the ten f32 terms of every (point, cell) pair: terms[n*K*10], zeros where skipped (tests) */
+/* the ten f32 factors (e, c1..c9; SPEC 4) of every (point, cell) pair: terms[n*K*10], zeros where skipped (tests) */
 int ndt2d_point_terms(ndt2d_matcher *m, int level, const float *xy, int n, const double *pose, float *terms);
 
 /* ---- align (north_star: "align(scan, initial pose) returning pose, score and Hessian", SPEC 5) - */

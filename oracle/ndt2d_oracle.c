@@ -207,8 +207,9 @@ static void finalize(level_t *L, const oracle_params *P)
         double cx = (double)L->ox + ((double)(jx - L->ov)) * (double)L->st + 0.5 * (double)L->res;
         double cy = (double)L->oy + ((double)(jy - L->ov)) * (double)L->st + 0.5 * (double)L->res;
         rec[0] = (float)(cx + mx); rec[1] = (float)(cy + my);
-        rec[2] = (float)(cyy / det); rec[3] = (float)(-(cxy / det)); rec[4] = (float)(cxx / det);
-        rec[5] = (float)det; rec[6] = (float)n; rec[7] = 1.0f;
+        rec[2] = (float)(cyy / det); rec[3] = (float)(-(cxy / det));
+        rec[4] = rec[3]; rec[5] = (float)(cxx / det);
+        rec[6] = (float)n; rec[7] = 1.0f;
     }
 }
 
@@ -279,6 +280,21 @@ static pose32 pose_to_f32(const double p[3])
     return q;
 }
 
+/* SPEC 4: the per-point quantities shared by its K cells */
+typedef struct { float rx, ry, jx, jy, X, Y; } point_t;
+
+static point_t transform_point(const pose32 *q, float x, float y)
+{
+    /* SPEC 4: points that cannot lie in any lattice are replaced by a finite far-away point */
+    if (!isfinite(x) || !isfinite(y) || fabsf(x) > 1e18f || fabsf(y) > 1e18f) { x = 1e18f; y = 1e18f; }
+    const float nc = -q->c, ns = -q->s;
+    point_t p;
+    p.rx = fmaf(q->c, x, ns * y); p.ry = fmaf(q->s, x, q->c * y);
+    p.jx = fmaf(ns, x, nc * y);   p.jy = fmaf(q->c, x, ns * y);
+    p.X = p.rx + q->tx; p.Y = p.ry + q->ty;
+    return p;
+}
+
 int oracle_cell_index(const oracle_matcher *m, int level, const float *xy, int n,
                       const double *pose, int32_t *idx)
 {
@@ -289,8 +305,8 @@ int oracle_cell_index(const oracle_matcher *m, int level, const float *xy, int n
     for (int i = 0; i < n; ++i) {
         float x = xy[2 * i], y = xy[2 * i + 1], X = x, Y = y;
         if (pose) {
-            float rx = fmaf(q.c, x, -(q.s * y)), ry = fmaf(q.s, x, q.c * y);
-            X = rx + q.tx; Y = ry + q.ty;
+            point_t p = transform_point(&q, x, y);
+            X = p.X; Y = p.Y;
         }
         int hx, hy;
         idx[i] = lattice(L, X, Y, &hx, &hy) ? hy * L->nhx + hx : -1;
@@ -301,8 +317,7 @@ int oracle_cell_index(const oracle_matcher *m, int level, const float *xy, int n
 /* SPEC 4.1 */
 float oracle_expneg(float h)
 {
-    float z = h * 1.44269502f;
-    float t = z + 12582912.0f;
+    float t = fmaf(h, 1.44269502f, 12582912.0f);
     float nf = t - 12582912.0f;
     int32_t ni = (int32_t)(f2u(t) - 0x4B400000u);
     float r = fmaf(nf, -0.693145752f, h);
@@ -318,54 +333,69 @@ float oracle_expneg(float h)
     return p * u2f((uint32_t)(0x3F800000 - ni * 0x800000));
 }
 
-/* SPEC 4: the ten f32 terms of one (point, cell) pair; returns 0 when skipped */
-static int pair_terms(const float *rec, float rx, float ry, float X, float Y, float T[10])
+/* SPEC 4: the ten f32 factors (e, c1..c9) of one (point, cell) pair; returns 0 when skipped */
+static int pair_terms(const float *rec, const point_t *p, float T[10])
 {
     if (rec[7] == 0.0f) return 0;
-    float mux = rec[0], muy = rec[1], B00 = rec[2], B01 = rec[3], B11 = rec[4];
-    float qx = X - mux, qy = Y - muy;
+    float mux = rec[0], muy = rec[1], B00 = rec[2], B01 = rec[3], B11 = rec[5];
+    float qx = p->X - mux, qy = p->Y - muy;
     float ux = fmaf(B00, qx, B01 * qy), uy = fmaf(B01, qx, B11 * qy);
-    float mm = fmaf(qx, ux, qy * uy), h = 0.5f * mm;
+    float m1 = qx * ux, m2 = qy * uy;
+    float mm = m1 + m2, h = 0.5f * mm;
     if (!(h < 30.0f)) return 0;
     float e = oracle_expneg(h);
-    float a2 = fmaf(uy, rx, -(ux * ry));
-    float vx = fmaf(B01, rx, -(B00 * ry)), vy = fmaf(B11, rx, -(B01 * ry));
-    float w = fmaf(ux, rx, uy * ry);
-    float k = fmaf(rx, vy, -(ry * vx));
+    float a1 = ux * p->jx, a1b = uy * p->jy;
+    float a2 = a1 + a1b;
+    float vx = fmaf(B00, p->jx, B01 * p->jy), vy = fmaf(B01, p->jx, B11 * p->jy);
+    float w1 = ux * p->rx, w2 = uy * p->ry;
+    float w = w1 + w2;
+    float k1 = p->jx * vx, k2 = p->jy * vy;
+    float k = k1 + k2;
     k = k - w;
     k = fmaf(-a2, a2, k);
+    /* T = (e, c1..c9): the factors SPEC 4 accumulates with acc0 += e, acc_t = fma(e, c_t, acc_t) */
     T[0] = e;
-    T[1] = e * ux; T[2] = e * uy; T[3] = e * a2;
-    T[4] = e * fmaf(-ux, ux, B00); T[5] = e * fmaf(-ux, uy, B01); T[6] = e * fmaf(-ux, a2, vx);
-    T[7] = e * fmaf(-uy, uy, B11); T[8] = e * fmaf(-uy, a2, vy); T[9] = e * k;
+    T[1] = ux; T[2] = uy; T[3] = a2;
+    T[4] = fmaf(-ux, ux, B00); T[5] = fmaf(-ux, uy, B01); T[6] = fmaf(-a2, ux, vx);
+    T[7] = fmaf(-uy, uy, B11); T[8] = fmaf(-a2, uy, vy); T[9] = k;
     return 1;
 }
 
-/* SPEC 4: evaluate; terms_out (optional) gets n*K*10 f32 */
+/* SPEC 4: evaluate with the fixed summation order (64 f32 partials, f64 butterfly); terms_out (optional)
+ * gets n*K*10 f32 */
 static void evaluate_level(const level_t *L, const float *xy, int n, const double pose[3],
                            double out[10], int32_t *count, float *terms_out)
 {
     pose32 q = pose_to_f32(pose);
     const int K = L->ov ? 2 : 1;
-    double acc[10] = {0};
+    float part[64][10];
+    memset(part, 0, sizeof(part));
     int32_t cnt = 0;
     if (terms_out) memset(terms_out, 0, (size_t)n * K * K * 10 * sizeof(float));
     for (int i = 0; i < n; ++i) {
-        float x = xy[2 * i], y = xy[2 * i + 1];
-        float rx = fmaf(q.c, x, -(q.s * y)), ry = fmaf(q.s, x, q.c * y);
-        float X = rx + q.tx, Y = ry + q.ty;
+        point_t p = transform_point(&q, xy[2 * i], xy[2 * i + 1]);
         int hx, hy;
-        if (!lattice(L, X, Y, &hx, &hy)) continue;
+        if (!lattice(L, p.X, p.Y, &hx, &hy)) continue;
+        float *acc = part[i & 63];
         for (int b = 0; b < K; ++b) for (int a = 0; a < K; ++a) {
             const float *rec = L->cells + 8 * ((size_t)(hy + b) * L->njx + (size_t)(hx + a));
             float T[10];
-            if (!pair_terms(rec, rx, ry, X, Y, T)) continue;
-            for (int t = 0; t < 10; ++t) acc[t] += (double)T[t];
+            if (!pair_terms(rec, &p, T)) continue;
+            acc[0] = acc[0] + T[0];
+            for (int t = 1; t < 10; ++t) acc[t] = fmaf(T[0], T[t], acc[t]);
             if (terms_out) memcpy(terms_out + ((size_t)i * K * K + (size_t)(b * K + a)) * 10, T, sizeof(T));
             cnt += 1;
         }
     }
-    memcpy(out, acc, sizeof(acc));
+    for (int t = 0; t < 10; ++t) {
+        double D[32], E[32];
+        for (int l = 0; l < 32; ++l) D[l] = (double)part[2 * l][t] + (double)part[2 * l + 1][t];
+        for (int o = 16; o > 0; o >>= 1) {
+            for (int l = 0; l < 32; ++l) E[l] = D[l] + D[l ^ o];
+            memcpy(D, E, sizeof(D));
+        }
+        out[t] = D[0];
+    }
     *count = cnt;
 }
 

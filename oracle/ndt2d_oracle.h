@@ -53,7 +53,7 @@ int oracle_add_target(oracle_matcher *m, const float *xy, int n);
 
 /* geometry of a level: out = {res, st, inv_st, ox, oy}, dims = {nhx, nhy, njx, njy} */
 int oracle_level_geometry(const oracle_matcher *m, int level, float out[5], int32_t dims[4]);
-/* cell records (njx*njy*8 floats) and raw integer sums (n: u32, sums: 5 x i64 per cell) */
+/* cell records (njx*njy*8 floats: mux muy | B00 B01 | B01 B11 | n valid) and raw integer sums (n: u32, sums: 5 x i64 per cell) */
 int oracle_get_cells(const oracle_matcher *m, int level, float *cells);
 int oracle_get_sums(const oracle_matcher *m, int level, uint32_t *n, int64_t *sums);
 /* SPEC 2: lattice index of points transformed by pose (pose == NULL: identity, no transform) */
@@ -62,7 +62,7 @@ int oracle_cell_index(const oracle_matcher *m, int level, const float *xy, int n
 /* SPEC 4: out10 = {S, g0,g1,g2, H00,H01,H02,H11,H12,H22} */
 int oracle_evaluate(const oracle_matcher *m, int level, const float *xy, int n,
                     const double pose[3], double out10[10], int32_t *count);
-/* SPEC 4 per-term dump for bit-exact checks: terms[n*K*10] f32 (zeros where skipped) */
+/* SPEC 4 per-pair factors (e, c1..c9) for bit-exact checks: terms[n*K*10] f32 (zeros where skipped) */
 int oracle_point_terms(const oracle_matcher *m, int level, const float *xy, int n,
                        const double pose[3], float *terms);
 /* SPEC 5 */

@@ -59,7 +59,7 @@ def gather(cells, geom, xy, pose, overlap=0):
                 rec = cells[hy[i] + b, hx[i] + a].astype(np.float64)
                 if rec[7] == 0:
                     continue
-                pts.append(x64[i]); mus.append(rec[0:2]); Bs.append([[rec[2], rec[3]], [rec[3], rec[4]]])
+                pts.append(x64[i]); mus.append(rec[0:2]); Bs.append([[rec[2], rec[3]], [rec[4], rec[5]]])
     if not pts:
         return np.zeros((0, 2)), np.zeros((0, 2)), np.zeros((0, 2, 2)), edge
     return np.array(pts), np.array(mus), np.array(Bs), edge

@@ -1,8 +1,9 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU spec oracle on the same seeded inputs.
 
 Bars (BASELINE.json north_star): cell assignment and point-to-cell indexing bit-exact; final pose within
-1e-5 m / 1e-6 rad; score and Hessian within 1e-6 relative. Because SPEC.md fixes every f32 operation, the
-per-pair terms are compared bit for bit and the f64 sums to 1e-12.
+1e-5 m / 1e-6 rad; score and Hessian within 1e-6 relative. Because SPEC.md fixes every f32 operation AND the
+summation order, the per-pair factors and the ten sums are compared bit for bit; only the pose's sin/cos
+(CUDA libm vs glibc, both < 1 ulp in f64, rounded to f32) can differ, in about 1 evaluation in 2^29.
 PARITY UNPINNED: the oracle restates SPEC.md, not upstream GTSAM-NDT (no source in /root/reference)."""
 import math
 
@@ -112,9 +113,8 @@ def test_point_terms_bit_exact_and_sums(mods, small_world, overlap):
         tg, to = m.point_terms(xy, pose), o.point_terms(xy, pose)
         assert tg.tobytes() == to.tobytes()
         eg, cg = m.evaluate(xy, pose); eo, co = o.evaluate(xy, pose)
-        assert cg == co
-        scale = np.abs(to.astype(np.float64)).sum((0, 1))
-        assert np.all(np.abs(eg - eo) <= 1e-12 * scale + 1e-300)
+        assert cg == co and np.count_nonzero(to[..., 0]) == co
+        assert np.array_equal(eg, eo)            # fixed summation order: the sums are bit-identical
 
 
 def test_evaluate_many_poses(mods, small_world):
@@ -127,7 +127,7 @@ def test_evaluate_many_poses(mods, small_world):
         ref = [o.evaluate(xy, p, level=lv) for p in poses]
         eo = np.array([r[0] for r in ref]); co = np.array([r[1] for r in ref])
         assert np.array_equal(cg, co)
-        assert np.allclose(eg, eo, rtol=1e-11, atol=1e-9 * np.abs(eo).max())
+        assert np.array_equal(eg, eo)
 
 
 @pytest.mark.parametrize("cfg", [dict(res=[0.5], overlap=0), dict(res=[0.5], overlap=1), dict(res=[2.0, 1.0, 0.5], overlap=0),
@@ -140,6 +140,7 @@ def test_align_batch_matches_oracle(mods, small_world, cfg):
     rg = m.align_batch(xy, off, small_world["init"])
     ro = o.align_batch(xy, off, small_world["init"])
     assert_results_match(rg, ro)
+    assert sum(rg[i].tobytes() == ro[i].tobytes() for i in range(len(rg))) >= len(rg) - 1   # bit-identical results
     assert np.all(rg["status"] <= 1) and (rg["status"] == 0).mean() > 0.8
     err = rg["pose"] - small_world["poses"]
     err[:, 2] = (err[:, 2] + np.pi) % (2 * np.pi) - np.pi
@@ -199,6 +200,25 @@ def test_align_edge_cases(mods, small_world):
     assert m.align_batch(np.zeros((0, 2), np.float32), [0], np.zeros((0, 3))).shape == (0,)
 
 
+def test_unusable_points_are_ignored(mods, small_world):
+    """SPEC 4: NaN / Inf / huge scan points are replaced by a far-away point; nothing becomes NaN."""
+    from gtsam_ndt_b200 import synth
+    m, o = make_pair(mods, [1.0, 0.5], None, overlap=1)
+    m.set_target(small_world["map_xy"]); o.set_target(small_world["map_xy"])
+    bad = np.array([[np.nan, 1.0], [1.0, np.inf], [-np.inf, np.nan], [1e30, 0.0], [3e38, -3e38]], np.float32)
+    xy = np.concatenate([small_world["scans"][0][:500], bad, small_world["scans"][0][500:]])
+    pose = small_world["init"][0]
+    eg, cg = m.evaluate(xy, pose, level=1); eo, co = o.evaluate(xy, pose, level=1)
+    assert cg == co and np.array_equal(eg, eo) and np.all(np.isfinite(eg))
+    assert np.array_equal(m.cell_index(bad, pose), o.cell_index(bad, pose))
+    rg, ro = m.align(xy, pose), o.align(xy, pose)
+    assert_results_match(np.array([rg]), np.array([ro]))
+    assert np.all(np.isfinite(rg["hessian"])) and rg["status"] == 0
+    allbad = np.tile(bad, (30, 1))
+    rg = m.align(allbad, pose)
+    assert rg["status"] == 3 and rg["count"] == 0
+
+
 def test_align_permutation_invariant_and_idempotent(mods, small_world):
     from gtsam_ndt_b200 import synth
     m, _ = make_pair(mods, [1.0, 0.5])
@@ -248,7 +268,7 @@ def test_sweep_matches_oracle(mods, small_world, overlap):
     hyp = np.concatenate([hyp, hyp[:200]])                        # duplicates: ties go to the smaller index
     sg, bi, bs = m.sweep(xy, hyp, k=8)
     so, oi, os_ = o.sweep(xy, hyp)
-    assert np.allclose(sg, so, rtol=1e-12, atol=1e-12)
+    assert np.array_equal(sg, so)
     assert bi[0] == oi and bs[0] == sg[oi]
     order = np.lexsort((np.arange(len(sg)), -sg))[:8]
     assert np.array_equal(bi, order) and np.array_equal(bs, sg[order])
