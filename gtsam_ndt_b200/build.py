@@ -43,7 +43,8 @@ def build_cuda(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; libndt2d.so must be prebuilt")
-    cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-o", LIB_CUDA] + srcs + ["-lcudart"]
+    extra = os.environ.get("NDT2D_NVCC_EXTRA", "").split()   # kernel tuning experiments, e.g. -DNDT2D_PIPE=0
+    cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + extra + ["-I", INCLUDE, "-I", CSRC, "-o", LIB_CUDA] + srcs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(HERE, "build_cuda.log"), "w") as f:

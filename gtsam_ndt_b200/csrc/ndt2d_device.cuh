@@ -15,7 +15,16 @@
 
 #include "ndt2d_internal.h"
 
+#ifndef NDT2D_UNROLL
+#define NDT2D_UNROLL 1
+#endif
+#ifndef NDT2D_LDMODE
+#define NDT2D_LDMODE 0 // cell gather instruction variant (tuning experiments; 0 = ld.global.nc 256-bit)
+#endif
+
 namespace ndt2d {
+
+static constexpr int kUnroll = NDT2D_UNROLL; // point-loop unroll of the non-pipelined evaluation
 
 typedef unsigned long long u64;
 
@@ -148,7 +157,18 @@ __device__ __forceinline__ Cell4 load_cell(const float4 *__restrict__ cells, uns
 {
     Cell4 r;
     const float4 *p = cells + 2 * (size_t)idx;
+#if NDT2D_LDMODE == 0
     asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.mu), "=l"(r.B0), "=l"(r.B1), "=l"(r.nv) : "l"(p));
+#elif NDT2D_LDMODE == 1
+    asm("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.mu), "=l"(r.B0), "=l"(r.B1), "=l"(r.nv) : "l"(p));
+#elif NDT2D_LDMODE == 2
+    asm("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(r.mu), "=l"(r.B0) : "l"(p));
+    asm("ld.global.nc.v2.b64 {%0,%1}, [%2+16];" : "=l"(r.B1), "=l"(r.nv) : "l"(p));
+#elif NDT2D_LDMODE == 3
+    asm("ld.global.nc.L1::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.mu), "=l"(r.B0), "=l"(r.B1), "=l"(r.nv) : "l"(p));
+#elif NDT2D_LDMODE == 4
+    asm("ld.global.nc.L1::no_allocate.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.mu), "=l"(r.B0), "=l"(r.B1), "=l"(r.nv) : "l"(p));
+#endif
     return r;
 }
 
@@ -193,7 +213,7 @@ __device__ __forceinline__ double warp_sum(double x)
     return x; // SPEC 4's butterfly: D[l] + D[l xor o] is commutative, every lane ends with the same bits
 }
 
-// f32 partial sums of one lane = SPEC 4's partials p = 2*lane (point A) and 2*lane + 1 (point B)
+// f32 partial sums of one lane = SPEC 4's partials p = lane (point A) and lane + 32 (point B)
 struct Partials {
     u64 s12[2], s45[2], s68[2]; // per point: (T1,T2) (T4,T5) (T6,T8)
     u64 s0, s3, s7, s9;         // (A,B): T0 T3 T7 T9
@@ -247,18 +267,63 @@ template <bool SMEM>
 __device__ __forceinline__ void load_two(const float2 *pts, int n, int i, float2 &a, float2 &b)
 {
     if (SMEM) {
-        float4 v = *reinterpret_cast<const float4 *>(pts + i);
-        a = make_float2(v.x, v.y);
-        b = make_float2(v.z, v.w);
+        a = pts[i];
+        b = pts[i + 32];
     } else {
         const float2 far = make_float2(1e18f, 1e18f);
         a = i < n ? sanitize(__ldg(pts + i)) : far;
-        b = i + 1 < n ? sanitize(__ldg(pts + i + 1)) : far;
+        b = i + 32 < n ? sanitize(__ldg(pts + i + 32)) : far;
     }
 }
 
-// SPEC 4 for one warp. Lane l owns points 64 j + 2 l (A) and 64 j + 2 l + 1 (B), i.e. partials 2l and 2l+1.
-template <int OV, bool FULL, bool SMEM>
+// One iteration's worth of fetched state for a lane: its two transformed points, whether they are inside the
+// lattice, and the K cell records of each (loads may still be in flight when the struct is handed on).
+template <int OV>
+struct Fetched {
+    static constexpr int NC = OV ? 4 : 1;
+    PointPk A, B;
+    bool inA, inB;
+    Cell4 cA[NC], cB[NC];
+};
+
+struct LatticePk {
+    u64 org, inv;
+    float nhxf, nhyf;
+    unsigned njx;
+};
+
+template <int OV, bool SMEM>
+__device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const LatticePk &G, const PosePk &P, const float2 *pts,
+                                      int n, int i, Fetched<OV> &F)
+{
+    float2 a, b;
+    load_two<SMEM>(pts, n, i, a, b);
+    F.A = transform_point(P, a.x, a.y);
+    F.B = transform_point(P, b.x, b.y);
+    u64 fA = mul2(sub2(F.A.XY, G.org), G.inv), fB = mul2(sub2(F.B.XY, G.org), G.inv);
+    float fxA, fyA, fxB, fyB;
+    upk(fA, fxA, fyA);
+    upk(fB, fxB, fyB);
+    F.inA = (fxA >= 0.0f) && (fxA < G.nhxf) && (fyA >= 0.0f) && (fyA < G.nhyf);
+    F.inB = (fxB >= 0.0f) && (fxB < G.nhxf) && (fyB >= 0.0f) && (fyB < G.nhyf);
+    const unsigned bA = (unsigned)(int)fyA * G.njx + (unsigned)(int)fxA;
+    const unsigned bB = (unsigned)(int)fyB * G.njx + (unsigned)(int)fxB;
+    // K = 1: one record per point. K = 4: two rows of two adjacent records (64 contiguous bytes per row).
+#pragma unroll
+    for (int k = 0; k < Fetched<OV>::NC; ++k) {
+        F.cA[k].mu = F.cA[k].B0 = F.cA[k].B1 = F.cA[k].nv = 0ull; // outside the lattice: an all-zero (invalid) record
+        F.cB[k].mu = F.cB[k].B0 = F.cB[k].B1 = F.cB[k].nv = 0ull;
+        const unsigned o = (k & 1) + (k >> 1) * G.njx;
+        if (F.inA) F.cA[k] = load_cell(cells, bA + o);
+        if (F.inB) F.cB[k] = load_cell(cells, bB + o);
+    }
+}
+
+// SPEC 4 for one warp. Lane l owns points 64 j + l (A) and 64 j + 32 + l (B), i.e. partials l and l + 32: each of the
+// two gather requests of an iteration then covers 32 consecutive beams (few distinct cache lines per request).
+// PIPE: software pipelining, the records of iteration j+1 are requested before iteration j is computed, so the
+// L2 round trip of the gathers overlaps this warp's own arithmetic (costs ~28 registers).
+template <int OV, bool FULL, bool SMEM, bool PIPE>
 __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E)
 {
     Partials S;
@@ -268,41 +333,31 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
     int cnt = 0;
     const float4 *__restrict__ cells = L.cells;
     const PosePk P = pose_pack(q);
-    const u64 org = pk(L.ox, L.oy), inv = bc(L.inv_st);
-    const float nhxf = L.nhxf, nhyf = L.nhyf;
-    const unsigned njx = (unsigned)L.njx;
+    LatticePk G;
+    G.org = pk(L.ox, L.oy); G.inv = bc(L.inv_st); G.nhxf = L.nhxf; G.nhyf = L.nhyf; G.njx = (unsigned)L.njx;
     const int npad = (n + 63) & ~63;
+    if (PIPE) {
+        Fetched<OV> cur;
+        if (lane < npad) fetch<OV, SMEM>(cells, G, P, pts, n, lane, cur);
 #pragma unroll 1
-    for (int i = 2 * lane; i < npad; i += 64) {
-        float2 a, b;
-        load_two<SMEM>(pts, n, i, a, b);
-        const PointPk A = transform_point(P, a.x, a.y), B = transform_point(P, b.x, b.y);
-        u64 fA = mul2(sub2(A.XY, org), inv), fB = mul2(sub2(B.XY, org), inv);
-        float fxA, fyA, fxB, fyB;
-        upk(fA, fxA, fyA);
-        upk(fB, fxB, fyB);
-        const bool inA = (fxA >= 0.0f) && (fxA < nhxf) && (fyA >= 0.0f) && (fyA < nhyf);
-        const bool inB = (fxB >= 0.0f) && (fxB < nhxf) && (fyB >= 0.0f) && (fyB < nhyf);
-        const unsigned bA = (unsigned)(int)fyA * njx + (unsigned)(int)fxA;
-        const unsigned bB = (unsigned)(int)fyB * njx + (unsigned)(int)fxB;
-        // K = 1: one record per point. K = 4: two rows of two adjacent records (64 contiguous bytes per row),
-        // processed row by row to bound the registers held by loads in flight.
-        constexpr int ROWS = OV ? 2 : 1, COLS = OV ? 2 : 1;
+        for (int i = lane; i < npad; i += 64) {
+            Fetched<OV> nxt;
+            const bool more = i + 64 < npad;
+            if (more) fetch<OV, SMEM>(cells, G, P, pts, n, i + 64, nxt);
 #pragma unroll
-        for (int rb = 0; rb < ROWS; ++rb) {
-            Cell4 cA[COLS], cB[COLS];
+            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(cur.cA[k], cur.cB[k], cur.A, cur.B, cur.inA, cur.inB, S, cnt);
+            if (more) cur = nxt;
+        }
+    } else {
+#pragma unroll kUnroll
+        for (int i = lane; i < npad; i += 64) {
+            Fetched<OV> cur;
+            fetch<OV, SMEM>(cells, G, P, pts, n, i, cur);
 #pragma unroll
-            for (int ca = 0; ca < COLS; ++ca) {
-                cA[ca].mu = cA[ca].B0 = cA[ca].B1 = cA[ca].nv = 0ull; // outside the lattice: an all-zero (invalid) record
-                cB[ca].mu = cB[ca].B0 = cB[ca].B1 = cB[ca].nv = 0ull;
-                if (inA) cA[ca] = load_cell(cells, bA + ca + rb * njx);
-                if (inB) cB[ca] = load_cell(cells, bB + ca + rb * njx);
-            }
-#pragma unroll
-            for (int ca = 0; ca < COLS; ++ca) accumulate_cell<FULL>(cA[ca], cB[ca], A, B, inA, inB, S, cnt);
+            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(cur.cA[k], cur.cB[k], cur.A, cur.B, cur.inA, cur.inB, S, cnt);
         }
     }
-    // SPEC 4: D[l] = (double)P[2l] + (double)P[2l+1], then the butterfly
+    // SPEC 4: D[l] = (double)P[l] + (double)P[l+32], then the butterfly
     E.v[0] = warp_sum((double)lo32(S.s0) + (double)hi32(S.s0));
     if (FULL) {
         E.v[1] = warp_sum((double)lo32(S.s12[0]) + (double)lo32(S.s12[1]));

@@ -177,6 +177,10 @@ __global__ void k_point_terms(const LevelDev L, const float2 *__restrict__ xy, i
 // ------------------------------------------------------------------------------------------------
 
 static constexpr int EVAL_THREADS = 256;
+#ifndef NDT2D_PIPE
+#define NDT2D_PIPE 0
+#endif
+static constexpr bool EVAL_PIPE = NDT2D_PIPE != 0;
 
 // Block stages the scan in shared memory once (coalesced float2 loads), then each warp takes poses
 // from a grid-stride loop. FULL: ten f64 sums per pose; otherwise the score only (sweep).
@@ -207,8 +211,8 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_poses(const LevelDev L, c
         }
         Pose32 q = pose_to_f32(tx, ty, th);
         Eval E;
-        if (STAGED) eval_warp<OV, FULL, true>(L, sp, n, q, lane, E);
-        else eval_warp<OV, FULL, false>(L, xy, n, q, lane, E);
+        if (STAGED) eval_warp<OV, FULL, true, EVAL_PIPE && OV == 0>(L, sp, n, q, lane, E);
+        else eval_warp<OV, FULL, false, false>(L, xy, n, q, lane, E);
         if (lane == 0) {
             if (FULL) {
 #pragma unroll
@@ -226,7 +230,10 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_poses(const LevelDev L, c
 // ------------------------------------------------------------------------------------------------
 
 static constexpr int ALIGN_THREADS = 256;
-static constexpr int ALIGN_MIN_BLOCKS = 3; // 24 warps/SM: bounds registers at 85
+#ifndef NDT2D_ALIGN_MIN_BLOCKS
+#define NDT2D_ALIGN_MIN_BLOCKS 3
+#endif
+static constexpr int ALIGN_MIN_BLOCKS = NDT2D_ALIGN_MIN_BLOCKS; // 3: 24 warps/SM at 80 registers (2: 16 warps at 128; measured equal)
 
 // SPEC 5, one pyramid level. Every lane carries the same f64 state (the butterfly reduction gives
 // all lanes identical sums), so the control flow is warp-uniform and needs no broadcast.
@@ -236,34 +243,38 @@ struct ScanView {
     int n;
 };
 
-template <int OV, bool STAGED>
-__device__ __forceinline__ void eval_scan(const LevelDev &L, const ScanView &v, const Pose32 &q, int lane, Eval &E)
-{
-    eval_warp<OV, true, STAGED>(L, v.pts, v.n, q, lane, E);
-}
-
-// Per-warp LM state kept in shared memory between evaluations so that it does not occupy registers
-// while the point loop runs: the last accepted evaluation (SPEC 5's E).
+// Per-warp LM state kept in shared memory so that it does not occupy registers while the point loop runs.
 struct WarpState {
-    double v[10];
+    double v[10];   // the last accepted evaluation (SPEC 5's E)
     int count, pad;
+    double t[10];   // the trial evaluation
+    int tcount, tpad;
 };
 
+// One SPEC 4 evaluation written to shared memory (lane t stores sum t). Deliberately not inlined: the point
+// loop gets its own register allocation, independent of the f64 solver state of the caller.
 template <int OV, bool STAGED>
-__device__ __forceinline__ int align_level(const LevelDev &L, const ndt2d_params &P, const ScanView &v, double p[3],
-                                           WarpState *ws, int &evals_total, int lane)
+__device__ __noinline__ void eval_to_smem(const LevelDev *L, const float2 *pts, int n, double px, double py, double pth,
+                                          double *out, int *out_count)
+{
+    const int lane = threadIdx.x & 31;
+    Eval E;
+    eval_warp<OV, true, STAGED, STAGED && (NDT2D_PIPE != 0) && OV == 0>(*L, pts, n, pose_to_f32(px, py, pth), lane, E);
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 10; ++t)
+        if (lane == t) out[t] = E.v[t];
+    if (lane == 10) *out_count = E.count;
+    __syncwarp();
+}
+
+template <int OV, bool STAGED>
+__device__ __forceinline__ int align_level(const LevelDev *L, const ndt2d_params &P, const ScanView &v, double p[3],
+                                           WarpState *ws, int &evals_total)
 {
     const int n = v.n;
     double lambda = P.lambda_init;
-    {
-        Eval E;
-        eval_scan<OV, STAGED>(L, v, pose_to_f32(p[0], p[1], p[2]), lane, E);
-#pragma unroll
-        for (int t = 0; t < 10; ++t)
-            if (lane == t) ws->v[t] = E.v[t];
-        if (lane == 10) ws->count = E.count;
-        __syncwarp();
-    }
+    eval_to_smem<OV, STAGED>(L, v.pts, n, p[0], p[1], p[2], ws->v, &ws->count);
     int evals = 1, status = NDT2D_MAX_ITERATIONS;
     if (n == 0 || ws->count == 0) {
         evals_total += evals;
@@ -293,16 +304,14 @@ __device__ __forceinline__ int align_level(const LevelDev &L, const ndt2d_params
         }
         bool small = (nt < P.eps_trans) && (fabs(d[2]) < P.eps_rot);
         double pn0 = p[0] + d[0], pn1 = p[1] + d[1], pn2 = p[2] + d[2];
-        Eval En;
-        eval_scan<OV, STAGED>(L, v, pose_to_f32(pn0, pn1, pn2), lane, En);
+        eval_to_smem<OV, STAGED>(L, v.pts, n, pn0, pn1, pn2, ws->t, &ws->tcount);
         evals += 1;
-        if (En.v[0] > ws->v[0]) {
+        if (ws->t[0] > ws->v[0]) {
             p[0] = pn0; p[1] = pn1; p[2] = pn2;
             __syncwarp();
-#pragma unroll
-            for (int t = 0; t < 10; ++t)
-                if (lane == t) ws->v[t] = En.v[t];
-            if (lane == 10) ws->count = En.count;
+            const int lane = threadIdx.x & 31;
+            if (lane < 10) ws->v[lane] = ws->t[lane];
+            if (lane == 10) ws->count = ws->tcount;
             __syncwarp();
             lambda = fmax(lambda / P.lambda_down, P.lambda_min);
             if (small) { status = NDT2D_CONVERGED; break; }
@@ -381,9 +390,9 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
         }
         double p[3] = {__ldg(a.init + 3 * (size_t)job), __ldg(a.init + 3 * (size_t)job + 1), __ldg(a.init + 3 * (size_t)job + 2)};
         int evals = 0, status = NDT2D_NO_OVERLAP;
-        for (int l = 0; l < a.nlevels; ++l) status = align_level<OV, SM>(a.lv[l], a.prm, v, p, ws, evals, lane);
+        for (int l = 0; l < a.nlevels; ++l) status = align_level<OV, SM>(&a.lv[l], a.prm, v, p, ws, evals);
         if (lane == 0) {
-            WarpState E = *ws;
+            const WarpState &E = *ws;
             ndt2d_result *r = a.res + job;
             const double TWO_PI = 6.283185307179586476925286766559;
             r->pose[0] = p[0];
@@ -578,6 +587,9 @@ static cudaError_t launch_align_t(const LaunchCfg &c, const AlignArgs &a)
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ALIGN_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+#ifdef NDT2D_MAX_BLOCKS_PER_SM
+    if (per_sm > NDT2D_MAX_BLOCKS_PER_SM) per_sm = NDT2D_MAX_BLOCKS_PER_SM;
+#endif
     int grid = grid_for(a.nscans, ALIGN_THREADS / 32, c.sm_count, per_sm);
     kern<<<grid, ALIGN_THREADS, smem, c.stream>>>(a);
     return cudaGetLastError();

@@ -389,7 +389,7 @@ static void evaluate_level(const level_t *L, const float *xy, int n, const doubl
     }
     for (int t = 0; t < 10; ++t) {
         double D[32], E[32];
-        for (int l = 0; l < 32; ++l) D[l] = (double)part[2 * l][t] + (double)part[2 * l + 1][t];
+        for (int l = 0; l < 32; ++l) D[l] = (double)part[l][t] + (double)part[l + 32][t];
         for (int o = 16; o > 0; o >>= 1) {
             for (int l = 0; l < 32; ++l) E[l] = D[l] + D[l ^ o];
             memcpy(D, E, sizeof(D));

@@ -210,7 +210,7 @@ def test_point_terms_sum_to_evaluate(small_world):
                 acc[0] = acc[0] + T[i, k, 0]
                 for t in range(1, 10):
                     acc[t] = f32_fma(T[i, k, 0], T[i, k, t], acc[t])
-    D = part[0::2].astype(np.float64) + part[1::2].astype(np.float64)
+    D = part[:32].astype(np.float64) + part[32:].astype(np.float64)
     for o_ in (16, 8, 4, 2, 1):
         D = D + D[np.arange(32) ^ o_]
     assert np.array_equal(D[0], out)
