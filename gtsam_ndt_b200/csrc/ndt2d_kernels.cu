@@ -180,6 +180,9 @@ static constexpr int EVAL_THREADS = 256;
 #ifndef NDT2D_PIPE
 #define NDT2D_PIPE 0
 #endif
+#ifndef NDT2D_QUEUE
+#define NDT2D_QUEUE 0 // 0: one global atomic work queue; 1: contiguous per-block ranges (tuning experiment)
+#endif
 static constexpr bool EVAL_PIPE = NDT2D_PIPE != 0;
 
 // Block stages the scan in shared memory once (coalesced float2 loads), then each warp takes poses
@@ -339,11 +342,26 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
     WarpState *ws = reinterpret_cast<WarpState *>(smem_raw) + warp;
     float2 *slot = reinterpret_cast<float2 *>(smem_raw + (ALIGN_THREADS / 32) * sizeof(WarpState)) + (size_t)warp * a.cap_points;
     const float2 far = make_float2(1e18f, 1e18f);
+#if NDT2D_QUEUE == 1
+    // locality-preserving queue: each block owns a contiguous range of scans and its warps pull from a
+    // block-local counter, so the 8 warps of a block work on neighbouring scans (which gather the same cells)
+    __shared__ unsigned s_next;
+    const unsigned q_lo = (unsigned)(((unsigned long long)blockIdx.x * (unsigned)a.nscans) / gridDim.x);
+    const unsigned q_hi = (unsigned)(((unsigned long long)(blockIdx.x + 1) * (unsigned)a.nscans) / gridDim.x);
+    if (threadIdx.x == 0) s_next = q_lo;
+    __syncthreads();
+#endif
     for (;;) {
         unsigned job = 0;
+#if NDT2D_QUEUE == 1
+        if (lane == 0) job = atomicAdd(&s_next, 1u);
+        job = __shfl_sync(FULL_MASK, job, 0);
+        if (job >= q_hi) break;
+#else
         if (lane == 0) job = atomicAdd(a.counter, 1u);
         job = __shfl_sync(FULL_MASK, job, 0);
         if (job >= (unsigned)a.nscans) break;
+#endif
         ScanView v;
         v.pts = slot; v.n = 0;
         if (RANGES) {
