@@ -395,14 +395,15 @@ def run_sweep(args):
     d_xy = torch.from_numpy(xy).to(dev)
     d_hyp = torch.from_numpy(hyp[lo:hi].copy()).to(dev)
     d_scores = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
-    d_bi = torch.zeros(1, dtype=torch.int64, device=dev); d_bs = torch.zeros(1, dtype=torch.float64, device=dev)
+    # the library writes (local best index, best score bits) straight into one 16-byte buffer, which is what is
+    # all-gathered: no arithmetic kernels between the sweep and the collective (the shard offset is added on the host)
+    pair = torch.zeros(2, dtype=torch.int64, device=dev)
+    gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
 
     def step():
-        m.sweep_device(d_xy, len(xy), d_hyp, hi - lo, d_scores, 1, d_bi, d_bs)
+        m.sweep_device(d_xy, len(xy), d_hyp, hi - lo, d_scores, 1, pair.data_ptr(), pair.data_ptr() + 8)
         if world > 1:   # best-hypothesis combine: 16 B per rank
-            pair = torch.stack([d_bs, (d_bi + lo).to(torch.float64)]).reshape(1, 2)
-            out = [torch.empty_like(pair) for _ in range(world)]
-            dist.all_gather(out, pair)
+            dist.all_gather_into_tensor(gathered, pair)
 
     def sync_all():
         torch.cuda.synchronize()

@@ -337,16 +337,23 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
     G.org = pk(L.ox, L.oy); G.inv = bc(L.inv_st); G.nhxf = L.nhxf; G.nhyf = L.nhyf; G.njx = (unsigned)L.njx;
     const int npad = (n + 63) & ~63;
     if (PIPE) {
-        Fetched<OV> cur;
-        if (lane < npad) fetch<OV, SMEM>(cells, G, P, pts, n, lane, cur);
+        // ping-pong: the records of step j+1 are requested before step j is computed; no register copies
+        Fetched<OV> F0, F1;
+        int i = lane;
+        if (i < npad) fetch<OV, SMEM>(cells, G, P, pts, n, i, F0);
 #pragma unroll 1
-        for (int i = lane; i < npad; i += 64) {
-            Fetched<OV> nxt;
-            const bool more = i + 64 < npad;
-            if (more) fetch<OV, SMEM>(cells, G, P, pts, n, i + 64, nxt);
+        while (i < npad) {
+            const bool m1 = i + 64 < npad;
+            if (m1) fetch<OV, SMEM>(cells, G, P, pts, n, i + 64, F1);
 #pragma unroll
-            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(cur.cA[k], cur.cB[k], cur.A, cur.B, cur.inA, cur.inB, S, cnt);
-            if (more) cur = nxt;
+            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(F0.cA[k], F0.cB[k], F0.A, F0.B, F0.inA, F0.inB, S, cnt);
+            if (!m1) break;
+            const bool m2 = i + 128 < npad;
+            if (m2) fetch<OV, SMEM>(cells, G, P, pts, n, i + 128, F0);
+#pragma unroll
+            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(F1.cA[k], F1.cB[k], F1.A, F1.B, F1.inA, F1.inB, S, cnt);
+            i += 128;
+            if (!m2) break;
         }
     } else {
 #pragma unroll kUnroll
