@@ -353,6 +353,16 @@ def run_native(args):
             "mean_iterations": float(iters.mean()), "status_counts": np.bincount(res["status"], minlength=4).tolist(),
             "map_build_ms": build_ms, "clocks": clocks,
         }
+        # single-scan latency (configs[0]/[1] at batch 1): one warp runs the whole LM loop, so this is a latency
+        # figure, not a throughput or roofline figure (hard part 4)
+        lat = []
+        one = np.ascontiguousarray(xy[:npts])
+        for i in range(60):
+            t0 = time.perf_counter()
+            r1 = m.align(one, init[0])
+            lat.append((time.perf_counter() - t0) * 1e6)
+        line["single_align_latency_us"] = {"median": float(np.median(lat[10:])), "min": float(np.min(lat[10:])),
+                                           "iterations": int(r1["iterations"]), "api": "ndt2d_align (host buffers, synchronous)"}
         if not args.no_cpu_baseline and world >= 1:
             line["cpu_baseline"] = cpu_baseline(args, xy, offsets, init, map_xy, res)
         print(json.dumps(line), flush=True)

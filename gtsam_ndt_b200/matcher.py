@@ -133,6 +133,27 @@ class NdtMatcher2D:
     def cells_device(self, level=0):
         return self._L.ndt2d_cells_device(self._h, level)
 
+    def save_map(self, path):
+        """Persist the target (geometry, parameters that shape the cells, every level's cell table) as .npz."""
+        g0 = self.geometry(0)
+        levels = [self.cells(l) for l in range(self.nlevels)]
+        res = np.array([self.geometry(l)["res"] for l in range(self.nlevels)], np.float32)
+        ext = np.array([g0["ox"], g0["oy"], g0["nhx"] * g0["st"], g0["nhy"] * g0["st"]], np.float32)
+        np.savez_compressed(path, format=np.int32(2), res=res, grid=ext, overlap=np.int32(self.params.overlap),
+                            min_points=np.int32(self.params.min_points), eig_ratio=np.float64(self.params.eig_ratio),
+                            **{f"cells{l}": c for l, c in enumerate(levels)})
+
+    def load_map(self, path):
+        """Inverse of save_map: restores the grid and cell tables (no point sums, so add_target is unavailable)."""
+        z = np.load(path)
+        if int(z["format"]) != 2:
+            raise NdtError("unknown map file format")
+        self.set_params(overlap=int(z["overlap"]), min_points=int(z["min_points"]), eig_ratio=float(z["eig_ratio"]))
+        self.set_resolutions(z["res"])
+        self.set_grid(*[float(v) for v in z["grid"]])
+        for l in range(self.nlevels):
+            self.set_cells(z[f"cells{l}"], level=l)
+
     # -- evaluation ------------------------------------------------------------------------------
     def cell_index(self, xy, pose=None, level=0):
         xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)

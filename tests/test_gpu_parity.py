@@ -305,6 +305,24 @@ def test_set_cells_roundtrip(mods, small_world):
     assert m2.align(small_world["scans"][1], small_world["init"][1]).tobytes() == r1.tobytes()
 
 
+def test_save_and_load_map(mods, small_world, tmp_path):
+    g, _ = mods
+    m = g.NdtMatcher2D([2.0, 0.5], overlap=1)
+    m.set_grid(-100.0, -100.0, 200.0, 200.0)
+    m.set_target(small_world["map_xy"])
+    path = str(tmp_path / "map.npz")
+    m.save_map(path)
+    m2 = g.NdtMatcher2D([1.0])
+    m2.load_map(path)
+    assert m2.nlevels == 2 and m2.geometry(1) == m.geometry(1)
+    assert m2.cells(0).tobytes() == m.cells(0).tobytes() and m2.cells(1).tobytes() == m.cells(1).tobytes()
+    a = m.align(small_world["scans"][3], small_world["init"][3])
+    b = m2.align(small_world["scans"][3], small_world["init"][3])
+    assert a.tobytes() == b.tobytes()
+    with pytest.raises(g.NdtError, match="no sums"):
+        m2.add_target(small_world["map_xy"][:10])
+
+
 def test_errors_are_reported(mods):
     g, _ = mods
     m = g.NdtMatcher2D([0.5])
