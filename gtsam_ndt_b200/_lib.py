@@ -69,7 +69,7 @@ def load():
     """Load libndt2d.so (built in-tree by gtsam_ndt_b200.build). Raises if it is missing: no fallback."""
     global _lib
     if _lib is None:
-        so = _build.LIB_CUDA
+        so = os.environ.get("NDT2D_LIB") or _build.LIB_CUDA  # NDT2D_LIB: a tuning-experiment build of the same sources
         if not os.path.exists(so):
             raise ImportError(f"{so} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(needs nvcc). There is no CPU fallback for the NDT path.")

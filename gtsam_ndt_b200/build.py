@@ -56,6 +56,22 @@ def build_cuda(force=False, verbose=False):
     return LIB_CUDA
 
 
+def build_variant(name, extra_flags):
+    """Kernel tuning experiments: the same sources with extra -D knobs -> build/variants/libndt2d_<name>.so
+    (git-ignored, travels to the GPU box). Select it at run time with NDT2D_LIB=<path>."""
+    out_dir = os.path.join(os.path.dirname(HERE), "build", "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libndt2d_{name}.so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + list(extra_flags) + ["-I", INCLUDE, "-I", CSRC, "-o", out] + cuda_sources() + ["-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    with open(out + ".log", "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + (r.stdout + r.stderr)[-6000:])
+    return out
+
+
 def build_synth(force=False):
     src = os.path.join(CSRC, "synth.c")
     if not force and not _stale(LIB_SYNTH, [src]):

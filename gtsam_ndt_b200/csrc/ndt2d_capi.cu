@@ -160,10 +160,11 @@ int setup_level(ndt2d_matcher *m, int l, const float bbox[4])
     if (nc >= (int64_t)1 << 31) return fail(m, NDT2D_EINVAL, "level %d: %lld cells exceed 2^31", l, (long long)nc);
     LevelMem &M = m->mem[l];
     M.release();
-    CK(m, cudaMalloc(&M.cells, (size_t)nc * 32));
+    // one extra all-zero record after the table: the gather target of points outside the lattice (never written again)
+    CK(m, cudaMalloc(&M.cells, (size_t)(nc + 1) * 32));
     CK(m, cudaMalloc(&M.cnt, (size_t)nc * 4));
     CK(m, cudaMalloc(&M.sums, (size_t)nc * 40));
-    CK(m, cudaMemsetAsync(M.cells, 0, (size_t)nc * 32, m->cfg.stream));
+    CK(m, cudaMemsetAsync(M.cells, 0, (size_t)(nc + 1) * 32, m->cfg.stream));
     CK(m, cudaMemsetAsync(M.cnt, 0, (size_t)nc * 4, m->cfg.stream));
     CK(m, cudaMemsetAsync(M.sums, 0, (size_t)nc * 40, m->cfg.stream));
     L.cells = M.cells;
@@ -201,8 +202,7 @@ int align_cap_points(const ndt2d_matcher *m, int max_points)
 {
     int cap = (max_points + 63) & ~63; // two NaN-padded planes per warp, 64 points per warp iteration
     if (cap < 64) cap = 64;
-    size_t bytes = (size_t)cap * sizeof(float2) * 8;
-    if (bytes > (size_t)m->cfg.max_smem_optin - 2048) return 0;
+    if (align_smem_bytes(cap) > (size_t)m->cfg.max_smem_optin) return 0;
     return cap;
 }
 

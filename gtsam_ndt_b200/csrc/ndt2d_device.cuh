@@ -57,6 +57,40 @@ __device__ __forceinline__ bool lattice(const LevelDev &L, float X, float Y, int
     return inside;
 }
 
+// ---- SPEC 3: finalisation of one cell from its integer sums; f64, operations in the order the spec lists ----
+__device__ __forceinline__ void finalize_record(unsigned n, long long s0, long long s1, long long s2, long long s3, long long s4,
+                                                int jx, int jy, float ox, float oy, float st, float res, int ov, int min_points,
+                                                double eig_ratio, float4 &ra, float4 &rb)
+{
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = ra;
+    if (n < (unsigned)min_points) return;
+    const double U = 1.0 / 1048576.0;
+    double N = (double)n;
+    double mx = (double)s0 / N, my = (double)s1 / N;
+    double cxx = ((double)s2 - (double)s0 * mx) / (N - 1.0);
+    double cxy = ((double)s3 - (double)s0 * my) / (N - 1.0);
+    double cyy = ((double)s4 - (double)s1 * my) / (N - 1.0);
+    mx *= U; my *= U; cxx *= U * U; cxy *= U * U; cyy *= U * U;
+    double tr = cxx + cyy, hd = 0.5 * (cxx - cyy), rad = sqrt(hd * hd + cxy * cxy);
+    double l1 = 0.5 * tr + rad, l2 = 0.5 * tr - rad;
+    if (!(l1 > 1e-10)) return;
+    if (l2 < eig_ratio * l1) {
+        double l2n = eig_ratio * l1, vx, vy;
+        if (hd >= 0.0) { vx = hd + rad; vy = cxy; } else { vx = cxy; vy = rad - hd; }
+        double nn = vx * vx + vy * vy, dl = l1 - l2n;
+        cxx = l2n + dl * (vx * vx) / nn;
+        cxy = dl * (vx * vy) / nn;
+        cyy = l2n + dl * (vy * vy) / nn;
+    }
+    double det = cxx * cyy - cxy * cxy;
+    double cx = (double)ox + ((double)(jx - ov)) * (double)st + 0.5 * (double)res;
+    double cy = (double)oy + ((double)(jy - ov)) * (double)st + 0.5 * (double)res;
+    const float b01 = (float)(-(cxy / det));
+    ra = make_float4((float)(cx + mx), (float)(cy + my), (float)(cyy / det), b01);
+    rb = make_float4(b01, (float)(cxx / det), (float)n, 1.0f);
+}
+
 // ---- SPEC 4.1: exp(-h), bit-exact sequence of f32 operations -----------------------------------------
 __device__ __forceinline__ float expneg(float h)
 {
@@ -172,6 +206,26 @@ __device__ __forceinline__ Cell4 load_cell(const float4 *__restrict__ cells, uns
     return r;
 }
 
+// ---- asynchronous gather: the 32 B record goes global -> shared memory without passing through registers ----
+#ifndef NDT2D_ASYNC_CG
+#define NDT2D_ASYNC_CG 0 // 1: cp.async.cg (bypass L1)
+#endif
+__device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src)
+{
+#if NDT2D_ASYNC_CG
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void lds_pair(unsigned addr, u64 &a, u64 &b)
+{
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
+}
+
 // ---- SPEC 4 per-pair terms, scalar form (diagnostic kernel k_point_terms) --------------------------------
 __device__ __forceinline__ bool pair_terms_scalar(const Cell4 &c, const PointPk &p, float T[10])
 {
@@ -216,48 +270,73 @@ __device__ __forceinline__ double warp_sum(double x)
 // f32 partial sums of one lane = SPEC 4's partials p = lane (point A) and lane + 32 (point B)
 struct Partials {
     u64 s12[2], s45[2], s68[2]; // per point: (T1,T2) (T4,T5) (T6,T8)
-    u64 s0, s3, s7, s9;         // (A,B): T0 T3 T7 T9
+    u64 s0, s3, s9;             // (A,B): T0 T3 T9
+    float s7[2];                // T7 per point (scalar: its operands (uy, B11) sit in the high halves of two pairs)
 };
 
-// one cell for the lane's two points
+// The SPEC 4 factors of one cell for the lane's two points A and B. Skipped pairs have e = 0.
+struct Factors {
+    u64 e;                 // (eA, eB)
+    u64 c12[2], c45[2], c68[2]; // per point: (c1,c2) (c4,c5) (c6,c8)
+    u64 c3, c9;            // (A,B)
+    float c7[2];           // per point
+};
+
+// A point outside the lattice was given the all-zero sentinel record (fetch()), so `valid` covers both tests of SPEC 4.
 template <bool FULL>
-__device__ __forceinline__ void accumulate_cell(const Cell4 &cA, const Cell4 &cB, const PointPk &A, const PointPk &B, bool inA,
-                                                bool inB, Partials &S, int &cnt)
+__device__ __forceinline__ void cell_factors(const Cell4 &cA, const Cell4 &cB, const PointPk &A, const PointPk &B, Factors &F,
+                                             int &cnt)
 {
     // q = XY - mu ; u = B q ; m = q.u ; nh = -0.5 m
     u64 qA = sub2(A.XY, cA.mu), qB = sub2(B.XY, cB.mu);
     u64 uA = fma2(cA.B0, bc(lo32(qA)), mul2(cA.B1, bc(hi32(qA))));
     u64 uB = fma2(cB.B0, bc(lo32(qB)), mul2(cB.B1, bc(hi32(qB))));
     u64 nh = mul2(bc(-0.5f), pk(hsum(mul2(qA, uA)), hsum(mul2(qB, uB))));
-    bool okA = inA && (hi32(cA.nv) != 0.0f) && (lo32(nh) > -30.0f);
-    bool okB = inB && (hi32(cB.nv) != 0.0f) && (hi32(nh) > -30.0f);
+    bool okA = (hi32(cA.nv) != 0.0f) && (lo32(nh) > -30.0f);
+    bool okB = (hi32(cB.nv) != 0.0f) && (hi32(nh) > -30.0f);
     u64 e = expneg2(nh);
     // skipped pairs get e = 0: fma(0, c, acc) == acc bit for bit (every c is finite, see sanitize())
-    e = pk(okA ? lo32(e) : 0.0f, okB ? hi32(e) : 0.0f);
+    F.e = pk(okA ? lo32(e) : 0.0f, okB ? hi32(e) : 0.0f);
     cnt += (okA ? 1 : 0) + (okB ? 1 : 0);
-    S.s0 = add2(S.s0, e);
     if (FULL) {
-        const float eA = lo32(e), eB = hi32(e);
         float a2A = hsum(mul2(uA, A.j)), a2B = hsum(mul2(uB, B.j));
         u64 vA = fma2(cA.B0, bc(lo32(A.j)), mul2(cA.B1, bc(hi32(A.j))));
         u64 vB = fma2(cB.B0, bc(lo32(B.j)), mul2(cB.B1, bc(hi32(B.j))));
         float wA = hsum(mul2(uA, A.r)), wB = hsum(mul2(uB, B.r));
         u64 k = sub2(pk(hsum(mul2(A.j, vA)), hsum(mul2(B.j, vB))), pk(wA, wB));
-        u64 a2 = pk(a2A, a2B);
-        k = fma2(pk(-a2A, -a2B), a2, k);
-        // acc_t = fma(e, c_t, acc_t): per point pairs (c1,c2) (c4,c5) (c6,c8) ...
-        S.s12[0] = fma2(bc(eA), uA, S.s12[0]);
-        S.s12[1] = fma2(bc(eB), uB, S.s12[1]);
-        S.s45[0] = fma2(bc(eA), fma2(bc(-lo32(uA)), uA, cA.B0), S.s45[0]);
-        S.s45[1] = fma2(bc(eB), fma2(bc(-lo32(uB)), uB, cB.B0), S.s45[1]);
-        S.s68[0] = fma2(bc(eA), fma2(bc(-a2A), uA, vA), S.s68[0]);
-        S.s68[1] = fma2(bc(eB), fma2(bc(-a2B), uB, vB), S.s68[1]);
-        // ... and c3, c7, c9 across the two points
-        u64 uy = pk(hi32(uA), hi32(uB));
-        u64 c7 = fma2(pk(-hi32(uA), -hi32(uB)), uy, pk(hi32(cA.B1), hi32(cB.B1)));
-        S.s3 = fma2(e, a2, S.s3);
-        S.s7 = fma2(e, c7, S.s7);
-        S.s9 = fma2(e, k, S.s9);
+        F.c3 = pk(a2A, a2B);
+        F.c9 = fma2(pk(-a2A, -a2B), F.c3, k);
+        F.c12[0] = uA;
+        F.c12[1] = uB;
+        F.c45[0] = fma2(bc(-lo32(uA)), uA, cA.B0);
+        F.c45[1] = fma2(bc(-lo32(uB)), uB, cB.B0);
+        F.c68[0] = fma2(bc(-a2A), uA, vA);
+        F.c68[1] = fma2(bc(-a2B), uB, vB);
+        F.c7[0] = __fmaf_rn(-hi32(uA), hi32(uA), hi32(cA.B1));
+        F.c7[1] = __fmaf_rn(-hi32(uB), hi32(uB), hi32(cB.B1));
+    }
+}
+
+// one cell for the lane's two points, accumulated into the lane's partials: acc_t = fma(e, c_t, acc_t)
+template <bool FULL>
+__device__ __forceinline__ void accumulate_cell(const Cell4 &cA, const Cell4 &cB, const PointPk &A, const PointPk &B, Partials &S,
+                                                int &cnt)
+{
+    Factors F;
+    cell_factors<FULL>(cA, cB, A, B, F, cnt);
+    S.s0 = add2(S.s0, F.e);
+    if (FULL) {
+        const float eA = lo32(F.e), eB = hi32(F.e);
+        S.s12[0] = fma2(bc(eA), F.c12[0], S.s12[0]);
+        S.s12[1] = fma2(bc(eB), F.c12[1], S.s12[1]);
+        S.s45[0] = fma2(bc(eA), F.c45[0], S.s45[0]);
+        S.s45[1] = fma2(bc(eB), F.c45[1], S.s45[1]);
+        S.s68[0] = fma2(bc(eA), F.c68[0], S.s68[0]);
+        S.s68[1] = fma2(bc(eB), F.c68[1], S.s68[1]);
+        S.s3 = fma2(F.e, F.c3, S.s3);
+        S.s7[0] = __fmaf_rn(eA, F.c7[0], S.s7[0]);
+        S.s7[1] = __fmaf_rn(eB, F.c7[1], S.s7[1]);
+        S.s9 = fma2(F.e, F.c9, S.s9);
     }
 }
 
@@ -276,21 +355,32 @@ __device__ __forceinline__ void load_two(const float2 *pts, int n, int i, float2
     }
 }
 
-// One iteration's worth of fetched state for a lane: its two transformed points, whether they are inside the
-// lattice, and the K cell records of each (loads may still be in flight when the struct is handed on).
+// One iteration's worth of fetched state for a lane: its two transformed points and the K cell records of each
+// (loads may still be in flight when the struct is handed on).
 template <int OV>
 struct Fetched {
     static constexpr int NC = OV ? 4 : 1;
     PointPk A, B;
-    bool inA, inB;
     Cell4 cA[NC], cB[NC];
 };
 
 struct LatticePk {
     u64 org, inv;
-    float nhxf, nhyf;
-    unsigned njx;
+    unsigned nhx, nhy, njx;
+    unsigned sentinel; // index of the all-zero record that follows the njx*njy cells of the table
 };
+
+// SPEC 2 in integers: for a finite f, (f >= 0 && f < (float)nh) == ((unsigned)floor_to_int(f) < nh), because the
+// conversion saturates (huge -> INT_MAX, very negative -> INT_MIN) and rounds (-1, 0) down to -1; inside the
+// lattice floor and SPEC 2's truncation agree. Points are sanitised, so f is never NaN here.
+__device__ __forceinline__ bool cell_base(const LatticePk &G, u64 f, unsigned &base)
+{
+    float fx, fy;
+    upk(f, fx, fy);
+    const unsigned ix = (unsigned)__float2int_rd(fx), iy = (unsigned)__float2int_rd(fy);
+    base = iy * G.njx + ix;
+    return (ix < G.nhx) && (iy < G.nhy);
+}
 
 template <int OV, bool SMEM>
 __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const LatticePk &G, const PosePk &P, const float2 *pts,
@@ -300,22 +390,16 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
     load_two<SMEM>(pts, n, i, a, b);
     F.A = transform_point(P, a.x, a.y);
     F.B = transform_point(P, b.x, b.y);
-    u64 fA = mul2(sub2(F.A.XY, G.org), G.inv), fB = mul2(sub2(F.B.XY, G.org), G.inv);
-    float fxA, fyA, fxB, fyB;
-    upk(fA, fxA, fyA);
-    upk(fB, fxB, fyB);
-    F.inA = (fxA >= 0.0f) && (fxA < G.nhxf) && (fyA >= 0.0f) && (fyA < G.nhyf);
-    F.inB = (fxB >= 0.0f) && (fxB < G.nhxf) && (fyB >= 0.0f) && (fyB < G.nhyf);
-    const unsigned bA = (unsigned)(int)fyA * G.njx + (unsigned)(int)fxA;
-    const unsigned bB = (unsigned)(int)fyB * G.njx + (unsigned)(int)fxB;
+    unsigned bA, bB;
+    const bool inA = cell_base(G, mul2(sub2(F.A.XY, G.org), G.inv), bA);
+    const bool inB = cell_base(G, mul2(sub2(F.B.XY, G.org), G.inv), bB);
     // K = 1: one record per point. K = 4: two rows of two adjacent records (64 contiguous bytes per row).
+    // Outside the lattice: the sentinel record (all zero = invalid), so the gather needs no predicate.
 #pragma unroll
     for (int k = 0; k < Fetched<OV>::NC; ++k) {
-        F.cA[k].mu = F.cA[k].B0 = F.cA[k].B1 = F.cA[k].nv = 0ull; // outside the lattice: an all-zero (invalid) record
-        F.cB[k].mu = F.cB[k].B0 = F.cB[k].B1 = F.cB[k].nv = 0ull;
         const unsigned o = (k & 1) + (k >> 1) * G.njx;
-        if (F.inA) F.cA[k] = load_cell(cells, bA + o);
-        if (F.inB) F.cB[k] = load_cell(cells, bB + o);
+        F.cA[k] = load_cell(cells, inA ? bA + o : G.sentinel);
+        F.cB[k] = load_cell(cells, inB ? bB + o : G.sentinel);
     }
 }
 
@@ -323,20 +407,74 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
 // two gather requests of an iteration then covers 32 consecutive beams (few distinct cache lines per request).
 // PIPE: software pipelining, the records of iteration j+1 are requested before iteration j is computed, so the
 // L2 round trip of the gathers overlaps this warp's own arithmetic (costs ~28 registers).
-template <int OV, bool FULL, bool SMEM, bool PIPE>
-__device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E)
+// PIPE == 2 (K = 1 only): the records of step j+1 are copied asynchronously (cp.async) into this warp's staging
+// buffer at shared address `stage` (two buffers of 64 records) while step j is computed; no registers are held
+// by loads in flight. Stage layout: [first halves of the 64 records][second halves], 16 B per lane and half.
+static constexpr int kStageBytes = 64 * 32;
+
+template <int OV, bool FULL, bool SMEM, int PIPE>
+__device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E,
+                                          unsigned stage = 0)
 {
     Partials S;
-    S.s0 = S.s3 = S.s7 = S.s9 = 0ull;
+    S.s0 = S.s3 = S.s9 = 0ull;
+    S.s7[0] = S.s7[1] = 0.0f;
 #pragma unroll
     for (int k = 0; k < 2; ++k) S.s12[k] = S.s45[k] = S.s68[k] = 0ull;
     int cnt = 0;
     const float4 *__restrict__ cells = L.cells;
     const PosePk P = pose_pack(q);
     LatticePk G;
-    G.org = pk(L.ox, L.oy); G.inv = bc(L.inv_st); G.nhxf = L.nhxf; G.nhyf = L.nhyf; G.njx = (unsigned)L.njx;
+    G.org = pk(L.ox, L.oy); G.inv = bc(L.inv_st); G.nhx = (unsigned)L.nhx; G.nhy = (unsigned)L.nhy; G.njx = (unsigned)L.njx;
+    G.sentinel = (unsigned)L.njx * (unsigned)L.njy;
     const int npad = (n + 63) & ~63;
-    if (PIPE) {
+    if (PIPE == 2 && OV == 0) {
+        const int steps = npad >> 6;
+        const unsigned st0 = stage + 16u * (unsigned)lane, st1 = st0 + kStageBytes;
+        auto issue = [&](int it, unsigned sb, PointPk &A, PointPk &B) {
+            float2 a, b;
+            load_two<SMEM>(pts, n, (it << 6) + lane, a, b);
+            A = transform_point(P, a.x, a.y);
+            B = transform_point(P, b.x, b.y);
+            unsigned bA, bB;
+            const bool inA = cell_base(G, mul2(sub2(A.XY, G.org), G.inv), bA);
+            const bool inB = cell_base(G, mul2(sub2(B.XY, G.org), G.inv), bB);
+            const float4 *pa = cells + 2 * (size_t)(inA ? bA : G.sentinel);
+            const float4 *pb = cells + 2 * (size_t)(inB ? bB : G.sentinel);
+            cp_async16(sb, pa);
+            cp_async16(sb + 1024u, pa + 1);
+            cp_async16(sb + 512u, pb);
+            cp_async16(sb + 1536u, pb + 1);
+            cp_async_commit();
+        };
+        auto consume = [&](unsigned sb, const PointPk &A, const PointPk &B) {
+            Cell4 cA, cB;
+            lds_pair(sb, cA.mu, cA.B0);
+            lds_pair(sb + 1024u, cA.B1, cA.nv);
+            lds_pair(sb + 512u, cB.mu, cB.B0);
+            lds_pair(sb + 1536u, cB.B1, cB.nv);
+            accumulate_cell<FULL>(cA, cB, A, B, S, cnt);
+        };
+        PointPk A0, B0, A1, B1;
+        if (steps > 0) {
+            issue(0, st0, A0, B0);
+            int it = 0;
+#pragma unroll 1
+            for (;;) {
+                const bool m1 = it + 1 < steps;
+                if (m1) issue(it + 1, st1, A1, B1); else cp_async_commit();
+                cp_async_wait<1>();
+                consume(st0, A0, B0);
+                if (!m1) break;
+                const bool m2 = it + 2 < steps;
+                if (m2) issue(it + 2, st0, A0, B0); else cp_async_commit();
+                cp_async_wait<1>();
+                consume(st1, A1, B1);
+                if (!m2) break;
+                it += 2;
+            }
+        }
+    } else if (PIPE == 1) {
         // ping-pong: the records of step j+1 are requested before step j is computed; no register copies
         Fetched<OV> F0, F1;
         int i = lane;
@@ -346,12 +484,12 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
             const bool m1 = i + 64 < npad;
             if (m1) fetch<OV, SMEM>(cells, G, P, pts, n, i + 64, F1);
 #pragma unroll
-            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(F0.cA[k], F0.cB[k], F0.A, F0.B, F0.inA, F0.inB, S, cnt);
+            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(F0.cA[k], F0.cB[k], F0.A, F0.B, S, cnt);
             if (!m1) break;
             const bool m2 = i + 128 < npad;
             if (m2) fetch<OV, SMEM>(cells, G, P, pts, n, i + 128, F0);
 #pragma unroll
-            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(F1.cA[k], F1.cB[k], F1.A, F1.B, F1.inA, F1.inB, S, cnt);
+            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(F1.cA[k], F1.cB[k], F1.A, F1.B, S, cnt);
             i += 128;
             if (!m2) break;
         }
@@ -361,7 +499,7 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
             Fetched<OV> cur;
             fetch<OV, SMEM>(cells, G, P, pts, n, i, cur);
 #pragma unroll
-            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(cur.cA[k], cur.cB[k], cur.A, cur.B, cur.inA, cur.inB, S, cnt);
+            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(cur.cA[k], cur.cB[k], cur.A, cur.B, S, cnt);
         }
     }
     // SPEC 4: D[l] = (double)P[l] + (double)P[l+32], then the butterfly
@@ -373,7 +511,7 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
         E.v[4] = warp_sum((double)lo32(S.s45[0]) + (double)lo32(S.s45[1]));
         E.v[5] = warp_sum((double)hi32(S.s45[0]) + (double)hi32(S.s45[1]));
         E.v[6] = warp_sum((double)lo32(S.s68[0]) + (double)lo32(S.s68[1]));
-        E.v[7] = warp_sum((double)lo32(S.s7) + (double)hi32(S.s7));
+        E.v[7] = warp_sum((double)S.s7[0] + (double)S.s7[1]);
         E.v[8] = warp_sum((double)hi32(S.s68[0]) + (double)hi32(S.s68[1]));
         E.v[9] = warp_sum((double)lo32(S.s9) + (double)hi32(S.s9));
     } else {

@@ -9,7 +9,7 @@ namespace ndt2d {
 
 // One pyramid level as the kernels see it (SPEC 2). Passed by value in kernel parameters.
 struct LevelDev {
-    const float4 *cells;      // njx*njy records, two float4 each
+    const float4 *cells;      // njx*njy records, two float4 each, followed by one all-zero sentinel record
     uint32_t *cnt;            // njx*njy
     unsigned long long *sums; // njx*njy*5, two's-complement i64
     float res, st, inv_st, ox, oy;
@@ -53,6 +53,7 @@ cudaError_t launch_eval_poses(const LaunchCfg &c, const LevelDev &L, const float
                               int poses_f32, int64_t npose, int full, double *d_out, int out_stride, int32_t *d_count,
                               int64_t *launches);
 cudaError_t launch_align(const LaunchCfg &c, const AlignArgs &a, int64_t *launches);
+size_t align_smem_bytes(int cap_points); // dynamic shared memory per k_align block
 // top-k of scores by (-score, index); k small. d_work: nhyp bytes of scratch (mask).
 cudaError_t launch_topk(const LaunchCfg &c, const double *d_scores, int64_t nhyp, int k, int64_t *d_idx, double *d_val,
                         unsigned long long *d_scratch, int64_t *launches);

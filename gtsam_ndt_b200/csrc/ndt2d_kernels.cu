@@ -84,43 +84,15 @@ __global__ void __launch_bounds__(256) k_accumulate(const LevelDev L, const floa
     }
 }
 
-// SPEC 3 finalisation: one thread per cell, f64, operations in the order the spec lists them.
+// SPEC 3 finalisation: one thread per cell (the arithmetic is finalize_record() in ndt2d_device.cuh).
 __global__ void __launch_bounds__(256) k_finalize(const LevelDev L, float4 *__restrict__ cells, int min_points, double eig_ratio)
 {
     const int64_t nc = (int64_t)L.njx * L.njy;
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
-        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
-        unsigned n = L.cnt[c];
-        if (n >= (unsigned)min_points) {
-            const long long *s = reinterpret_cast<const long long *>(L.sums) + 5 * c;
-            const double U = 1.0 / 1048576.0;
-            double N = (double)n;
-            long long s0 = s[0], s1 = s[1];
-            double mx = (double)s0 / N, my = (double)s1 / N;
-            double cxx = ((double)s[2] - (double)s0 * mx) / (N - 1.0);
-            double cxy = ((double)s[3] - (double)s0 * my) / (N - 1.0);
-            double cyy = ((double)s[4] - (double)s1 * my) / (N - 1.0);
-            mx *= U; my *= U; cxx *= U * U; cxy *= U * U; cyy *= U * U;
-            double tr = cxx + cyy, hd = 0.5 * (cxx - cyy), rad = sqrt(hd * hd + cxy * cxy);
-            double l1 = 0.5 * tr + rad, l2 = 0.5 * tr - rad;
-            if (l1 > 1e-10) {
-                if (l2 < eig_ratio * l1) {
-                    double l2n = eig_ratio * l1, vx, vy;
-                    if (hd >= 0.0) { vx = hd + rad; vy = cxy; } else { vx = cxy; vy = rad - hd; }
-                    double nn = vx * vx + vy * vy, dl = l1 - l2n;
-                    cxx = l2n + dl * (vx * vx) / nn;
-                    cxy = dl * (vx * vy) / nn;
-                    cyy = l2n + dl * (vy * vy) / nn;
-                }
-                double det = cxx * cyy - cxy * cxy;
-                int jx = (int)(c % L.njx), jy = (int)(c / L.njx);
-                double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
-                double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
-                const float b01 = (float)(-(cxy / det));
-                ra = make_float4((float)(cx + mx), (float)(cy + my), (float)(cyy / det), b01);
-                rb = make_float4(b01, (float)(cxx / det), (float)n, 1.0f);
-            }
-        }
+        const long long *s = reinterpret_cast<const long long *>(L.sums) + 5 * c;
+        float4 ra, rb;
+        finalize_record(L.cnt[c], s[0], s[1], s[2], s[3], s[4], (int)(c % L.njx), (int)(c / L.njx), L.ox, L.oy, L.st, L.res, L.ov,
+                        min_points, eig_ratio, ra, rb);
         cells[2 * c] = ra;
         cells[2 * c + 1] = rb;
     }
@@ -181,9 +153,9 @@ static constexpr int EVAL_THREADS = 256;
 #define NDT2D_PIPE 0
 #endif
 #ifndef NDT2D_QUEUE
-#define NDT2D_QUEUE 0 // 0: one global atomic work queue; 1: contiguous per-block ranges (tuning experiment)
+#define NDT2D_QUEUE 0 // 0: one global atomic work queue; 1: static per-block ranges (tuning experiment, slower)
 #endif
-static constexpr bool EVAL_PIPE = NDT2D_PIPE != 0;
+static constexpr int EVAL_PIPE = NDT2D_PIPE == 1 ? 1 : 0; // the cp.async variant (2) is an align-kernel option only
 
 // Block stages the scan in shared memory once (coalesced float2 loads), then each warp takes poses
 // from a grid-stride loop. FULL: ten f64 sums per pose; otherwise the score only (sweep).
@@ -214,8 +186,8 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_poses(const LevelDev L, c
         }
         Pose32 q = pose_to_f32(tx, ty, th);
         Eval E;
-        if (STAGED) eval_warp<OV, FULL, true, EVAL_PIPE && OV == 0>(L, sp, n, q, lane, E);
-        else eval_warp<OV, FULL, false, false>(L, xy, n, q, lane, E);
+        if (STAGED) eval_warp<OV, FULL, true, OV == 0 ? EVAL_PIPE : 0>(L, sp, n, q, lane, E);
+        else eval_warp<OV, FULL, false, 0>(L, xy, n, q, lane, E);
         if (lane == 0) {
             if (FULL) {
 #pragma unroll
@@ -236,6 +208,7 @@ static constexpr int ALIGN_THREADS = 256;
 #ifndef NDT2D_ALIGN_MIN_BLOCKS
 #define NDT2D_ALIGN_MIN_BLOCKS 3
 #endif
+static constexpr int ALIGN_STAGE_BYTES = NDT2D_PIPE == 2 ? 2 * kStageBytes : 0; // per warp
 static constexpr int ALIGN_MIN_BLOCKS = NDT2D_ALIGN_MIN_BLOCKS; // 3: 24 warps/SM at 80 registers (2: 16 warps at 128; measured equal)
 
 // SPEC 5, one pyramid level. Every lane carries the same f64 state (the butterfly reduction gives
@@ -246,38 +219,47 @@ struct ScanView {
     int n;
 };
 
-// Per-warp LM state kept in shared memory so that it does not occupy registers while the point loop runs.
+// Per-warp LM state. Every lane computes the same f64 values (the butterfly gives all lanes identical sums), so one
+// copy per warp in shared memory is the whole solver state: nothing but a few ints stays live in registers
+// across the evaluation call (register spills of warp-uniform doubles would cost 32 lanes x 8 B of local memory each).
 struct WarpState {
     double v[10];   // the last accepted evaluation (SPEC 5's E)
-    int count, pad;
     double t[10];   // the trial evaluation
-    int tcount, tpad;
+    double p[3];    // the current pose
+    double pn[3];   // the trial pose
+    double lambda;
+    int count, tcount;
+    unsigned stage, pad; // shared address of this warp's record staging buffers (cp.async variant)
 };
 
-// One SPEC 4 evaluation written to shared memory (lane t stores sum t). Deliberately not inlined: the point
-// loop gets its own register allocation, independent of the f64 solver state of the caller.
+// One SPEC 4 evaluation at ws->p (trial == 0, result to ws->v) or ws->pn (trial != 0, result to ws->t); lane t stores
+// sum t. Deliberately not inlined: the point loop gets its own register allocation, independent of the f64 solver.
 template <int OV, bool STAGED>
-__device__ __noinline__ void eval_to_smem(const LevelDev *L, const float2 *pts, int n, double px, double py, double pth,
-                                          double *out, int *out_count)
+__device__ __noinline__ void eval_to_smem(const LevelDev *L, const float2 *pts, int n, WarpState *ws, int trial)
 {
     const int lane = threadIdx.x & 31;
+    const double *pose = trial ? ws->pn : ws->p;
     Eval E;
-    eval_warp<OV, true, STAGED, STAGED && (NDT2D_PIPE != 0) && OV == 0>(*L, pts, n, pose_to_f32(px, py, pth), lane, E);
+    eval_warp<OV, true, STAGED, (STAGED && OV == 0) ? NDT2D_PIPE : 0>(*L, pts, n, pose_to_f32(pose[0], pose[1], pose[2]), lane, E,
+                                                                        ws->stage);
     __syncwarp();
+    double *out = trial ? ws->t : ws->v;
 #pragma unroll
     for (int t = 0; t < 10; ++t)
         if (lane == t) out[t] = E.v[t];
-    if (lane == 10) *out_count = E.count;
+    if (lane == 10) *(trial ? &ws->tcount : &ws->count) = E.count;
     __syncwarp();
 }
 
+// SPEC 5, one pyramid level, starting from and finishing in ws->p. The control flow is warp-uniform.
 template <int OV, bool STAGED>
-__device__ __forceinline__ int align_level(const LevelDev *L, const ndt2d_params &P, const ScanView &v, double p[3],
-                                           WarpState *ws, int &evals_total)
+__device__ __forceinline__ int align_level(const LevelDev *L, const ndt2d_params &P, const ScanView &v, WarpState *ws,
+                                           int &evals_total)
 {
     const int n = v.n;
-    double lambda = P.lambda_init;
-    eval_to_smem<OV, STAGED>(L, v.pts, n, p[0], p[1], p[2], ws->v, &ws->count);
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) ws->lambda = P.lambda_init;
+    eval_to_smem<OV, STAGED>(L, v.pts, n, ws, 0); // ends with __syncwarp()
     int evals = 1, status = NDT2D_MAX_ITERATIONS;
     if (n == 0 || ws->count == 0) {
         evals_total += evals;
@@ -286,6 +268,7 @@ __device__ __forceinline__ int align_level(const LevelDev *L, const ndt2d_params
     for (;;) {
         if (evals >= P.max_iterations) break;
         double d[3];
+        double lambda = ws->lambda;
         bool stalled = false;
         {
             double g[3] = {ws->v[1], ws->v[2], ws->v[3]};
@@ -305,22 +288,33 @@ __device__ __forceinline__ int align_level(const LevelDev *L, const ndt2d_params
             double sc = P.max_step_rot / fabs(d[2]);
             d[0] *= sc; d[1] *= sc; d[2] *= sc; nt *= sc;
         }
-        bool small = (nt < P.eps_trans) && (fabs(d[2]) < P.eps_rot);
-        double pn0 = p[0] + d[0], pn1 = p[1] + d[1], pn2 = p[2] + d[2];
-        eval_to_smem<OV, STAGED>(L, v.pts, n, pn0, pn1, pn2, ws->t, &ws->tcount);
+        const bool small = (nt < P.eps_trans) && (fabs(d[2]) < P.eps_rot);
+        __syncwarp();
+        if (lane == 0) {
+            ws->pn[0] = ws->p[0] + d[0];
+            ws->pn[1] = ws->p[1] + d[1];
+            ws->pn[2] = ws->p[2] + d[2];
+            ws->lambda = lambda;
+        }
+        __syncwarp();
+        eval_to_smem<OV, STAGED>(L, v.pts, n, ws, 1);
         evals += 1;
-        if (ws->t[0] > ws->v[0]) {
-            p[0] = pn0; p[1] = pn1; p[2] = pn2;
-            __syncwarp();
-            const int lane = threadIdx.x & 31;
+        lambda = ws->lambda;
+        const bool better = ws->t[0] > ws->v[0];
+        __syncwarp();
+        if (better) {
             if (lane < 10) ws->v[lane] = ws->t[lane];
             if (lane == 10) ws->count = ws->tcount;
-            __syncwarp();
+            if (lane >= 11 && lane < 14) ws->p[lane - 11] = ws->pn[lane - 11];
             lambda = fmax(lambda / P.lambda_down, P.lambda_min);
+            if (lane == 14) ws->lambda = lambda;
+            __syncwarp();
             if (small) { status = NDT2D_CONVERGED; break; }
         } else {
             if (small) { status = NDT2D_CONVERGED; break; }
             lambda = lambda * P.lambda_up;
+            if (lane == 14) ws->lambda = lambda;
+            __syncwarp();
             if (lambda > P.lambda_max) { status = NDT2D_STALLED; break; }
         }
     }
@@ -342,9 +336,12 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
     WarpState *ws = reinterpret_cast<WarpState *>(smem_raw) + warp;
     float2 *slot = reinterpret_cast<float2 *>(smem_raw + (ALIGN_THREADS / 32) * sizeof(WarpState)) + (size_t)warp * a.cap_points;
     const float2 far = make_float2(1e18f, 1e18f);
+    if (lane == 0)
+        ws->stage = (unsigned)__cvta_generic_to_shared(smem_raw + (ALIGN_THREADS / 32) * (sizeof(WarpState) + (size_t)a.cap_points * sizeof(float2))) +
+                    (unsigned)warp * ALIGN_STAGE_BYTES;
+    __syncwarp();
 #if NDT2D_QUEUE == 1
-    // locality-preserving queue: each block owns a contiguous range of scans and its warps pull from a
-    // block-local counter, so the 8 warps of a block work on neighbouring scans (which gather the same cells)
+    // static ranges (tuning experiment): each block owns a contiguous range of scans
     __shared__ unsigned s_next;
     const unsigned q_lo = (unsigned)(((unsigned long long)blockIdx.x * (unsigned)a.nscans) / gridDim.x);
     const unsigned q_hi = (unsigned)(((unsigned long long)(blockIdx.x + 1) * (unsigned)a.nscans) / gridDim.x);
@@ -406,16 +403,17 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
             for (int i = v.n + lane; i < npad; i += 32) slot[i] = far;
             __syncwarp();
         }
-        double p[3] = {__ldg(a.init + 3 * (size_t)job), __ldg(a.init + 3 * (size_t)job + 1), __ldg(a.init + 3 * (size_t)job + 2)};
+        if (lane < 3) ws->p[lane] = __ldg(a.init + 3 * (size_t)job + lane);
+        __syncwarp();
         int evals = 0, status = NDT2D_NO_OVERLAP;
-        for (int l = 0; l < a.nlevels; ++l) status = align_level<OV, SM>(&a.lv[l], a.prm, v, p, ws, evals);
+        for (int l = 0; l < a.nlevels; ++l) status = align_level<OV, SM>(&a.lv[l], a.prm, v, ws, evals);
         if (lane == 0) {
             const WarpState &E = *ws;
             ndt2d_result *r = a.res + job;
             const double TWO_PI = 6.283185307179586476925286766559;
-            r->pose[0] = p[0];
-            r->pose[1] = p[1];
-            r->pose[2] = p[2] - TWO_PI * rint(p[2] / TWO_PI);
+            r->pose[0] = E.p[0];
+            r->pose[1] = E.p[1];
+            r->pose[2] = E.p[2] - TWO_PI * rint(E.p[2] / TWO_PI);
             r->score = E.v[0];
             r->grad[0] = E.v[1]; r->grad[1] = E.v[2]; r->grad[2] = E.v[3];
             r->hessian[0] = E.v[4]; r->hessian[1] = E.v[5]; r->hessian[2] = E.v[6];
@@ -588,11 +586,18 @@ cudaError_t launch_eval_poses(const LaunchCfg &c, const LevelDev &L, const float
                      : launch_eval_t<0, false, false>(c, L, d_xy, n, d_poses, npose, d_out, out_stride, d_count);
 }
 
+// dynamic shared memory of one k_align block whose warps stage scans of up to cap_points points (0: no staging)
+size_t align_smem_bytes(int cap_points)
+{
+    return (cap_points > 0 ? (size_t)cap_points * sizeof(float2) + ALIGN_STAGE_BYTES : 0) * (ALIGN_THREADS / 32) +
+           (ALIGN_THREADS / 32) * sizeof(WarpState);
+}
+
 template <int OV, bool STAGED, bool RANGES>
 static cudaError_t launch_align_t(const LaunchCfg &c, const AlignArgs &a)
 {
     auto kern = k_align<OV, STAGED, RANGES>;
-    size_t smem = ((STAGED || RANGES) ? (size_t)a.cap_points * sizeof(float2) : 0) * (ALIGN_THREADS / 32) + (ALIGN_THREADS / 32) * sizeof(WarpState);
+    size_t smem = align_smem_bytes((STAGED || RANGES) ? a.cap_points : 0);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
