@@ -206,26 +206,6 @@ __device__ __forceinline__ Cell4 load_cell(const float4 *__restrict__ cells, uns
     return r;
 }
 
-// ---- asynchronous gather: the 32 B record goes global -> shared memory without passing through registers ----
-#ifndef NDT2D_ASYNC_CG
-#define NDT2D_ASYNC_CG 0 // 1: cp.async.cg (bypass L1)
-#endif
-__device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src)
-{
-#if NDT2D_ASYNC_CG
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-#else
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-#endif
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void lds_pair(unsigned addr, u64 &a, u64 &b)
-{
-    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
-}
-
 // ---- SPEC 4 per-pair terms, scalar form (diagnostic kernel k_point_terms) --------------------------------
 __device__ __forceinline__ bool pair_terms_scalar(const Cell4 &c, const PointPk &p, float T[10])
 {
@@ -405,16 +385,10 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
 
 // SPEC 4 for one warp. Lane l owns points 64 j + l (A) and 64 j + 32 + l (B), i.e. partials l and l + 32: each of the
 // two gather requests of an iteration then covers 32 consecutive beams (few distinct cache lines per request).
-// PIPE: software pipelining, the records of iteration j+1 are requested before iteration j is computed, so the
-// L2 round trip of the gathers overlaps this warp's own arithmetic (costs ~28 registers).
-// PIPE == 2 (K = 1 only): the records of step j+1 are copied asynchronously (cp.async) into this warp's staging
-// buffer at shared address `stage` (two buffers of 64 records) while step j is computed; no registers are held
-// by loads in flight. Stage layout: [first halves of the 64 records][second halves], 16 B per lane and half.
-static constexpr int kStageBytes = 64 * 32;
-
+// PIPE: software pipelining, the records of step j+1 are requested before step j is computed, so the L2 round
+// trip of the gathers overlaps this warp's own arithmetic (costs ~30 registers).
 template <int OV, bool FULL, bool SMEM, int PIPE>
-__device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E,
-                                          unsigned stage = 0)
+__device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E)
 {
     Partials S;
     S.s0 = S.s3 = S.s9 = 0ull;
@@ -428,70 +402,30 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
     G.org = pk(L.ox, L.oy); G.inv = bc(L.inv_st); G.nhx = (unsigned)L.nhx; G.nhy = (unsigned)L.nhy; G.njx = (unsigned)L.njx;
     G.sentinel = (unsigned)L.njx * (unsigned)L.njy;
     const int npad = (n + 63) & ~63;
-    if (PIPE == 2 && OV == 0) {
-        const int steps = npad >> 6;
-        const unsigned st0 = stage + 16u * (unsigned)lane, st1 = st0 + kStageBytes;
-        auto issue = [&](int it, unsigned sb, PointPk &A, PointPk &B) {
-            float2 a, b;
-            load_two<SMEM>(pts, n, (it << 6) + lane, a, b);
-            A = transform_point(P, a.x, a.y);
-            B = transform_point(P, b.x, b.y);
-            unsigned bA, bB;
-            const bool inA = cell_base(G, mul2(sub2(A.XY, G.org), G.inv), bA);
-            const bool inB = cell_base(G, mul2(sub2(B.XY, G.org), G.inv), bB);
-            const float4 *pa = cells + 2 * (size_t)(inA ? bA : G.sentinel);
-            const float4 *pb = cells + 2 * (size_t)(inB ? bB : G.sentinel);
-            cp_async16(sb, pa);
-            cp_async16(sb + 1024u, pa + 1);
-            cp_async16(sb + 512u, pb);
-            cp_async16(sb + 1536u, pb + 1);
-            cp_async_commit();
-        };
-        auto consume = [&](unsigned sb, const PointPk &A, const PointPk &B) {
-            Cell4 cA, cB;
-            lds_pair(sb, cA.mu, cA.B0);
-            lds_pair(sb + 1024u, cA.B1, cA.nv);
-            lds_pair(sb + 512u, cB.mu, cB.B0);
-            lds_pair(sb + 1536u, cB.B1, cB.nv);
-            accumulate_cell<FULL>(cA, cB, A, B, S, cnt);
-        };
-        PointPk A0, B0, A1, B1;
-        if (steps > 0) {
-            issue(0, st0, A0, B0);
-            int it = 0;
-#pragma unroll 1
-            for (;;) {
-                const bool m1 = it + 1 < steps;
-                if (m1) issue(it + 1, st1, A1, B1); else cp_async_commit();
-                cp_async_wait<1>();
-                consume(st0, A0, B0);
-                if (!m1) break;
-                const bool m2 = it + 2 < steps;
-                if (m2) issue(it + 2, st0, A0, B0); else cp_async_commit();
-                cp_async_wait<1>();
-                consume(st1, A1, B1);
-                if (!m2) break;
-                it += 2;
-            }
-        }
-    } else if (PIPE == 1) {
-        // ping-pong: the records of step j+1 are requested before step j is computed; no register copies
-        Fetched<OV> F0, F1;
+    if (PIPE == 1 && OV == 0) {
+        // Software pipeline over registers, two steps per trip: the records of the next step are requested before
+        // the current step is computed. Inside the loop every fetch and every use is unconditional: ptxas sinks a
+        // load into the branch that uses it and merges conditionally loaded registers with a copy at the join,
+        // and either puts a consumer right behind the load it was meant to overlap. An odd step count is made
+        // even by one un-pipelined step up front; the last trip re-fetches the final step and drops it.
         int i = lane;
-        if (i < npad) fetch<OV, SMEM>(cells, G, P, pts, n, i, F0);
+        if ((npad >> 6) & 1) {
+            Fetched<OV> cur;
+            fetch<OV, SMEM>(cells, G, P, pts, n, i, cur);
+            accumulate_cell<FULL>(cur.cA[0], cur.cB[0], cur.A, cur.B, S, cnt);
+            i += 64;
+        }
+        if (i < npad) {
+            const int last = npad - 64 + lane;
+            Fetched<OV> F0, F1;
+            fetch<OV, SMEM>(cells, G, P, pts, n, i, F0);
 #pragma unroll 1
-        while (i < npad) {
-            const bool m1 = i + 64 < npad;
-            if (m1) fetch<OV, SMEM>(cells, G, P, pts, n, i + 64, F1);
-#pragma unroll
-            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(F0.cA[k], F0.cB[k], F0.A, F0.B, S, cnt);
-            if (!m1) break;
-            const bool m2 = i + 128 < npad;
-            if (m2) fetch<OV, SMEM>(cells, G, P, pts, n, i + 128, F0);
-#pragma unroll
-            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(F1.cA[k], F1.cB[k], F1.A, F1.B, S, cnt);
-            i += 128;
-            if (!m2) break;
+            for (; i < npad; i += 128) {
+                fetch<OV, SMEM>(cells, G, P, pts, n, i + 64, F1);
+                accumulate_cell<FULL>(F0.cA[0], F0.cB[0], F0.A, F0.B, S, cnt);
+                fetch<OV, SMEM>(cells, G, P, pts, n, min(i + 128, last), F0);
+                accumulate_cell<FULL>(F1.cA[0], F1.cB[0], F1.A, F1.B, S, cnt);
+            }
         }
     } else {
 #pragma unroll kUnroll

@@ -155,7 +155,7 @@ static constexpr int EVAL_THREADS = 256;
 #ifndef NDT2D_QUEUE
 #define NDT2D_QUEUE 0 // 0: one global atomic work queue; 1: static per-block ranges (tuning experiment, slower)
 #endif
-static constexpr int EVAL_PIPE = NDT2D_PIPE == 1 ? 1 : 0; // the cp.async variant (2) is an align-kernel option only
+static constexpr int EVAL_PIPE = NDT2D_PIPE;
 
 // Block stages the scan in shared memory once (coalesced float2 loads), then each warp takes poses
 // from a grid-stride loop. FULL: ten f64 sums per pose; otherwise the score only (sweep).
@@ -204,11 +204,13 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_poses(const LevelDev L, c
 // (2c) batched align: one warp per scan, the whole LM loop on the device
 // ------------------------------------------------------------------------------------------------
 
-static constexpr int ALIGN_THREADS = 256;
+#ifndef NDT2D_ALIGN_THREADS
+#define NDT2D_ALIGN_THREADS 256
+#endif
+static constexpr int ALIGN_THREADS = NDT2D_ALIGN_THREADS;
 #ifndef NDT2D_ALIGN_MIN_BLOCKS
 #define NDT2D_ALIGN_MIN_BLOCKS 3
 #endif
-static constexpr int ALIGN_STAGE_BYTES = NDT2D_PIPE == 2 ? 2 * kStageBytes : 0; // per warp
 static constexpr int ALIGN_MIN_BLOCKS = NDT2D_ALIGN_MIN_BLOCKS; // 3: 24 warps/SM at 80 registers (2: 16 warps at 128; measured equal)
 
 // SPEC 5, one pyramid level. Every lane carries the same f64 state (the butterfly reduction gives
@@ -229,7 +231,6 @@ struct WarpState {
     double pn[3];   // the trial pose
     double lambda;
     int count, tcount;
-    unsigned stage, pad; // shared address of this warp's record staging buffers (cp.async variant)
 };
 
 // One SPEC 4 evaluation at ws->p (trial == 0, result to ws->v) or ws->pn (trial != 0, result to ws->t); lane t stores
@@ -240,8 +241,7 @@ __device__ __noinline__ void eval_to_smem(const LevelDev *L, const float2 *pts, 
     const int lane = threadIdx.x & 31;
     const double *pose = trial ? ws->pn : ws->p;
     Eval E;
-    eval_warp<OV, true, STAGED, (STAGED && OV == 0) ? NDT2D_PIPE : 0>(*L, pts, n, pose_to_f32(pose[0], pose[1], pose[2]), lane, E,
-                                                                        ws->stage);
+    eval_warp<OV, true, STAGED, (STAGED && OV == 0) ? NDT2D_PIPE : 0>(*L, pts, n, pose_to_f32(pose[0], pose[1], pose[2]), lane, E);
     __syncwarp();
     double *out = trial ? ws->t : ws->v;
 #pragma unroll
@@ -336,10 +336,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
     WarpState *ws = reinterpret_cast<WarpState *>(smem_raw) + warp;
     float2 *slot = reinterpret_cast<float2 *>(smem_raw + (ALIGN_THREADS / 32) * sizeof(WarpState)) + (size_t)warp * a.cap_points;
     const float2 far = make_float2(1e18f, 1e18f);
-    if (lane == 0)
-        ws->stage = (unsigned)__cvta_generic_to_shared(smem_raw + (ALIGN_THREADS / 32) * (sizeof(WarpState) + (size_t)a.cap_points * sizeof(float2))) +
-                    (unsigned)warp * ALIGN_STAGE_BYTES;
-    __syncwarp();
+
 #if NDT2D_QUEUE == 1
     // static ranges (tuning experiment): each block owns a contiguous range of scans
     __shared__ unsigned s_next;
@@ -589,7 +586,7 @@ cudaError_t launch_eval_poses(const LaunchCfg &c, const LevelDev &L, const float
 // dynamic shared memory of one k_align block whose warps stage scans of up to cap_points points (0: no staging)
 size_t align_smem_bytes(int cap_points)
 {
-    return (cap_points > 0 ? (size_t)cap_points * sizeof(float2) + ALIGN_STAGE_BYTES : 0) * (ALIGN_THREADS / 32) +
+    return (cap_points > 0 ? (size_t)cap_points * sizeof(float2) : 0) * (ALIGN_THREADS / 32) +
            (ALIGN_THREADS / 32) * sizeof(WarpState);
 }
 
