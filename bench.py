@@ -151,6 +151,15 @@ def ncu_traffic(kernel, args, scans):
         return None
 
 
+def ncu_traffic_sweep(args, hyps):
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "k_eval_poses/sweep/hyps=%d/res=%s/K=%d" % (hyps, "-".join(str(r) for r in args.res), 4 if args.overlap else 1)
+        return tab.get(key, {}).get("dram_bytes")
+    except Exception:
+        return None
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -464,7 +473,8 @@ def run_sweep(args):
                 "e2e": {"value": len(hyp) * args.steps / (e2e_ms / 1e3), "unit": "hypotheses/s", "h2d_bytes_per_step": int((hi - lo) * 12 + len(xy) * 8),
                         "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / args.steps, "api": "ndt2d_sweep + combine_topk"},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                             "traffic": ncu_traffic_sweep(args, len(hyp)) if world == 1 else None,
                              "kernel": "k_eval_poses (score only)", "peak_source": peak_src, "bytes_per_hypothesis": per_hyp,
                              "convention": "gather traffic (see DESIGN.md section 4); scan and cells are cache-resident"},
                 "best_hypothesis_abs_err_vs_truth": truth_err, "clocks": clocks}

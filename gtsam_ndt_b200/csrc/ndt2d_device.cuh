@@ -1,5 +1,5 @@
 // Device-side building blocks of the 2D NDT path: lattice index (SPEC 2), per-pair terms (SPEC 4),
-// expneg (SPEC 4.1), the warp evaluation with SPEC 4's fixed summation order, and the damped 3x3 solve
+// expneg (SPEC 4.1), the warp evaluation with SPEC 4's fixed summation order, and the damped closed-form 3x3 solve
 // (SPEC 5). Compiled with -fmad=false: only the explicit fma calls below fuse, exactly as SPEC.md writes them.
 // Reference file:line: none exists (/root/reference/README.md:1 is the whole mount).
 //
@@ -238,6 +238,7 @@ __device__ __forceinline__ bool pair_terms_scalar(const Cell4 &c, const PointPk 
 struct Eval {
     double v[10];
     int count;
+    int slot; // transposed finish only: v[0] is sum number `slot`
 };
 
 __device__ __forceinline__ double warp_sum(double x)
@@ -245,6 +246,31 @@ __device__ __forceinline__ double warp_sum(double x)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     return x; // SPEC 4's butterfly: D[l] + D[l xor o] is commutative, every lane ends with the same bits
+}
+
+// The same ten butterflies, transposed: in every round a lane keeps half of the sums it still holds and hands the
+// other half to its partner, so 12 exchange-and-add steps replace 50. Sum t of lane l goes through exactly the
+// additions of SPEC 4's butterfly (D[l] + D[l xor o] with the operands possibly swapped, and IEEE addition
+// commutes), so the bits are the butterfly's. Returns the one finished sum this lane ends up with; `t` is its index.
+__device__ __forceinline__ double xchg_add(double keep, double send, int o) { return keep + __shfl_xor_sync(0xffffffffu, send, o); }
+
+__device__ __forceinline__ double warp_sum10_transposed(const double V[10], int lane, int &t)
+{
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+    double W[5], X[3], Y[2];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) W[i] = xchg_add(h4 ? V[i + 5] : V[i], h4 ? V[i] : V[i + 5], 16);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) X[i] = xchg_add(h3 ? W[i + 3] : W[i], h3 ? W[i] : W[i + 3], 8);
+    X[2] = xchg_add(W[2], W[2], 8);
+    Y[0] = xchg_add(h2 ? X[2] : X[0], h2 ? X[0] : X[2], 4);
+    Y[1] = xchg_add(X[1], X[1], 4);
+    double Z = xchg_add(h1 ? Y[1] : Y[0], h1 ? Y[0] : Y[1], 2);
+    Z = xchg_add(Z, Z, 1);
+    const int xi = h1 ? 1 : (h2 ? 2 : 0);           // which X this lane finished
+    const int wi = xi == 2 ? 2 : xi + (h3 ? 3 : 0); // which W
+    t = wi + (h4 ? 5 : 0);
+    return Z;
 }
 
 // f32 partial sums of one lane = SPEC 4's partials p = lane (point A) and lane + 32 (point B)
@@ -387,7 +413,8 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
 // two gather requests of an iteration then covers 32 consecutive beams (few distinct cache lines per request).
 // PIPE: software pipelining, the records of step j+1 are requested before step j is computed, so the L2 round
 // trip of the gathers overlaps this warp's own arithmetic (costs ~30 registers).
-template <int OV, bool FULL, bool SMEM, int PIPE>
+// TR (FULL only): finish with the transposed reduction; E.v[0] is then sum number E.slot, the other E.v are unset.
+template <int OV, bool FULL, bool SMEM, int PIPE, bool TR = false>
 __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E)
 {
     Partials S;
@@ -437,48 +464,55 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
         }
     }
     // SPEC 4: D[l] = (double)P[l] + (double)P[l+32], then the butterfly
-    E.v[0] = warp_sum((double)lo32(S.s0) + (double)hi32(S.s0));
+    E.slot = 0;
     if (FULL) {
-        E.v[1] = warp_sum((double)lo32(S.s12[0]) + (double)lo32(S.s12[1]));
-        E.v[2] = warp_sum((double)hi32(S.s12[0]) + (double)hi32(S.s12[1]));
-        E.v[3] = warp_sum((double)lo32(S.s3) + (double)hi32(S.s3));
-        E.v[4] = warp_sum((double)lo32(S.s45[0]) + (double)lo32(S.s45[1]));
-        E.v[5] = warp_sum((double)hi32(S.s45[0]) + (double)hi32(S.s45[1]));
-        E.v[6] = warp_sum((double)lo32(S.s68[0]) + (double)lo32(S.s68[1]));
-        E.v[7] = warp_sum((double)S.s7[0] + (double)S.s7[1]);
-        E.v[8] = warp_sum((double)hi32(S.s68[0]) + (double)hi32(S.s68[1]));
-        E.v[9] = warp_sum((double)lo32(S.s9) + (double)hi32(S.s9));
+        double D[10];
+        D[0] = (double)lo32(S.s0) + (double)hi32(S.s0);
+        D[1] = (double)lo32(S.s12[0]) + (double)lo32(S.s12[1]);
+        D[2] = (double)hi32(S.s12[0]) + (double)hi32(S.s12[1]);
+        D[3] = (double)lo32(S.s3) + (double)hi32(S.s3);
+        D[4] = (double)lo32(S.s45[0]) + (double)lo32(S.s45[1]);
+        D[5] = (double)hi32(S.s45[0]) + (double)hi32(S.s45[1]);
+        D[6] = (double)lo32(S.s68[0]) + (double)lo32(S.s68[1]);
+        D[7] = (double)S.s7[0] + (double)S.s7[1];
+        D[8] = (double)hi32(S.s68[0]) + (double)hi32(S.s68[1]);
+        D[9] = (double)lo32(S.s9) + (double)hi32(S.s9);
+        if (TR) {
+            E.v[0] = warp_sum10_transposed(D, lane, E.slot);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 10; ++t) E.v[t] = warp_sum(D[t]);
+        }
     } else {
+        E.v[0] = warp_sum((double)lo32(S.s0) + (double)hi32(S.s0));
 #pragma unroll
         for (int t = 1; t < 10; ++t) E.v[t] = 0.0;
     }
     E.count = __reduce_add_sync(0xffffffffu, cnt);
 }
 
-// ---- SPEC 5: damped Cholesky solve in f64, no contraction. g = v[1..3], H6 = v[4..9] -------------------
+// ---- SPEC 5: damped 3x3 solve in f64, closed form, no contraction (-fmad=false). g = v[1..3], H6 = v[4..9] ----
+// Adjugate over determinant with Sylvester's criterion as the positive-definiteness test: about 60 instructions
+// and one reciprocal, where a Cholesky factorisation costs three square roots and twelve divisions (each ~25
+// instructions in f64). __drcp_rn is the correctly rounded reciprocal, i.e. the oracle's 1.0 / det bit for bit.
 __device__ __forceinline__ bool solve3(const double *g, const double *H6, double lambda, double d[3])
 {
-    double A00 = H6[0] + lambda * fmax(fabs(H6[0]), 1e-9);
-    double A11 = H6[3] + lambda * fmax(fabs(H6[3]), 1e-9);
-    double A22 = H6[5] + lambda * fmax(fabs(H6[5]), 1e-9);
-    double A01 = H6[1], A02 = H6[2], A12 = H6[4];
-    double p0 = A00;
-    if (!(p0 > 0.0)) return false;
-    double L00 = sqrt(p0);
-    double L10 = A01 / L00, L20 = A02 / L00;
-    double p1 = A11 - L10 * L10;
-    if (!(p1 > 0.0)) return false;
-    double L11 = sqrt(p1);
-    double L21 = (A12 - L20 * L10) / L11;
-    double p2 = (A22 - L20 * L20) - L21 * L21;
-    if (!(p2 > 0.0)) return false;
-    double L22 = sqrt(p2);
-    double y0 = -g[0] / L00;
-    double y1 = (-g[1] - L10 * y0) / L11;
-    double y2 = ((-g[2] - L20 * y0) - L21 * y1) / L22;
-    d[2] = y2 / L22;
-    d[1] = (y1 - L21 * d[2]) / L11;
-    d[0] = ((y0 - L10 * d[1]) - L20 * d[2]) / L00;
+    const double A00 = H6[0] + lambda * fmax(fabs(H6[0]), 1e-9);
+    const double A11 = H6[3] + lambda * fmax(fabs(H6[3]), 1e-9);
+    const double A22 = H6[5] + lambda * fmax(fabs(H6[5]), 1e-9);
+    const double A01 = H6[1], A02 = H6[2], A12 = H6[4];
+    const double C00 = A11 * A22 - A12 * A12;
+    const double C01 = A02 * A12 - A01 * A22;
+    const double C02 = A01 * A12 - A02 * A11;
+    const double C11 = A00 * A22 - A02 * A02;
+    const double C12 = A01 * A02 - A00 * A12;
+    const double C22 = A00 * A11 - A01 * A01;
+    const double det = (A00 * C00 + A01 * C01) + A02 * C02;
+    if (!(A00 > 0.0) || !(C22 > 0.0) || !(det > 0.0)) return false;
+    const double r = __drcp_rn(det);
+    d[0] = -(((C00 * g[0] + C01 * g[1]) + C02 * g[2]) * r);
+    d[1] = -(((C01 * g[0] + C11 * g[1]) + C12 * g[2]) * r);
+    d[2] = -(((C02 * g[0] + C12 * g[1]) + C22 * g[2]) * r);
     return true;
 }
 

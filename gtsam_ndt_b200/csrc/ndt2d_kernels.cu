@@ -150,17 +150,23 @@ __global__ void k_point_terms(const LevelDev L, const float2 *__restrict__ xy, i
 
 static constexpr int EVAL_THREADS = 256;
 #ifndef NDT2D_PIPE
-#define NDT2D_PIPE 0
+#define NDT2D_PIPE 0      // align kernel: 1 = register software pipeline (K = 1)
+#endif
+#ifndef NDT2D_EVAL_PIPE
+#define NDT2D_EVAL_PIPE 0 // the same for k_eval_poses (evaluate / sweep)
+#endif
+#ifndef NDT2D_EVAL_BLOCKS
+#define NDT2D_EVAL_BLOCKS 4 // resident k_eval_poses blocks per SM
 #endif
 #ifndef NDT2D_QUEUE
 #define NDT2D_QUEUE 0 // 0: one global atomic work queue; 1: static per-block ranges (tuning experiment, slower)
 #endif
-static constexpr int EVAL_PIPE = NDT2D_PIPE;
+static constexpr int EVAL_PIPE = NDT2D_EVAL_PIPE;
 
 // Block stages the scan in shared memory once (coalesced float2 loads), then each warp takes poses
 // from a grid-stride loop. FULL: ten f64 sums per pose; otherwise the score only (sweep).
 template <int OV, bool FULL, bool F32POSE, bool STAGED>
-__global__ void __launch_bounds__(EVAL_THREADS) k_eval_poses(const LevelDev L, const float2 *__restrict__ xy, int n,
+__global__ void __launch_bounds__(EVAL_THREADS, NDT2D_EVAL_BLOCKS) k_eval_poses(const LevelDev L, const float2 *__restrict__ xy, int n,
                                                                const void *__restrict__ poses, int64_t npose,
                                                                double *__restrict__ out, int out_stride,
                                                                int32_t *__restrict__ count)
@@ -241,13 +247,11 @@ __device__ __noinline__ void eval_to_smem(const LevelDev *L, const float2 *pts, 
     const int lane = threadIdx.x & 31;
     const double *pose = trial ? ws->pn : ws->p;
     Eval E;
-    eval_warp<OV, true, STAGED, (STAGED && OV == 0) ? NDT2D_PIPE : 0>(*L, pts, n, pose_to_f32(pose[0], pose[1], pose[2]), lane, E);
+    eval_warp<OV, true, STAGED, (STAGED && OV == 0) ? NDT2D_PIPE : 0, true>(*L, pts, n, pose_to_f32(pose[0], pose[1], pose[2]), lane, E);
     __syncwarp();
     double *out = trial ? ws->t : ws->v;
-#pragma unroll
-    for (int t = 0; t < 10; ++t)
-        if (lane == t) out[t] = E.v[t];
-    if (lane == 10) *(trial ? &ws->tcount : &ws->count) = E.count;
+    out[E.slot] = E.v[0]; // lanes holding the same sum store the same bits
+    if (lane == 0) *(trial ? &ws->tcount : &ws->count) = E.count;
     __syncwarp();
 }
 
@@ -279,16 +283,16 @@ __device__ __forceinline__ int align_level(const LevelDev *L, const ndt2d_params
             }
         }
         if (stalled) { status = NDT2D_STALLED; break; }
-        double nt = sqrt(d[0] * d[0] + d[1] * d[1]);
-        if (nt > P.max_step_trans) {
-            double sc = P.max_step_trans / nt;
-            d[0] *= sc; d[1] *= sc; d[2] *= sc; nt = P.max_step_trans;
+        double n2 = d[0] * d[0] + d[1] * d[1]; // squared translation step: no sqrt unless the step is clamped
+        if (n2 > P.max_step_trans * P.max_step_trans) {
+            double sc = P.max_step_trans / sqrt(n2);
+            d[0] *= sc; d[1] *= sc; d[2] *= sc; n2 = P.max_step_trans * P.max_step_trans;
         }
         if (fabs(d[2]) > P.max_step_rot) {
             double sc = P.max_step_rot / fabs(d[2]);
-            d[0] *= sc; d[1] *= sc; d[2] *= sc; nt *= sc;
+            d[0] *= sc; d[1] *= sc; d[2] *= sc; n2 = n2 * (sc * sc);
         }
-        const bool small = (nt < P.eps_trans) && (fabs(d[2]) < P.eps_rot);
+        const bool small = (n2 < P.eps_trans * P.eps_trans) && (fabs(d[2]) < P.eps_rot);
         __syncwarp();
         if (lane == 0) {
             ws->pn[0] = ws->p[0] + d[0];
@@ -550,7 +554,7 @@ static cudaError_t launch_eval_t(const LaunchCfg &c, const LevelDev &L, const fl
                                  int64_t npose, double *d_out, int out_stride, int32_t *d_count)
 {
     size_t smem = (size_t)((n + 63) & ~63) * sizeof(float2);
-    int grid = grid_for(npose, EVAL_THREADS / 32, c.sm_count, 4);
+    int grid = grid_for(npose, EVAL_THREADS / 32, c.sm_count, NDT2D_EVAL_BLOCKS);
     if (smem <= (size_t)c.max_smem_optin - 1024) {
         auto kern = k_eval_poses<OV, FULL, F32POSE, true>;
         if (smem > 48 * 1024) {

@@ -418,30 +418,27 @@ int oracle_point_terms(const oracle_matcher *m, int level, const float *xy, int 
     return 0;
 }
 
-/* SPEC 5: damped 3x3 Cholesky solve. H6 = {H00,H01,H02,H11,H12,H22}. Returns 1 when solved. */
+/* SPEC 5: damped 3x3 solve in closed form (adjugate / determinant), positive definite by Sylvester's
+ * criterion. H6 = {H00,H01,H02,H11,H12,H22}. Returns 1 when solved. Every a*b - c*d below is two rounded
+ * products and one rounded difference (the file is compiled with -ffp-contract=off). */
 int oracle_solve(const double g[3], const double H6[6], double lambda, double d[3])
 {
     double A00 = H6[0] + lambda * fmax(fabs(H6[0]), 1e-9);
     double A11 = H6[3] + lambda * fmax(fabs(H6[3]), 1e-9);
     double A22 = H6[5] + lambda * fmax(fabs(H6[5]), 1e-9);
     double A01 = H6[1], A02 = H6[2], A12 = H6[4];
-    double p0 = A00;
-    if (!(p0 > 0.0)) return 0;
-    double L00 = sqrt(p0);
-    double L10 = A01 / L00, L20 = A02 / L00;
-    double p1 = A11 - L10 * L10;
-    if (!(p1 > 0.0)) return 0;
-    double L11 = sqrt(p1);
-    double L21 = (A12 - L20 * L10) / L11;
-    double p2 = (A22 - L20 * L20) - L21 * L21;
-    if (!(p2 > 0.0)) return 0;
-    double L22 = sqrt(p2);
-    double y0 = -g[0] / L00;
-    double y1 = (-g[1] - L10 * y0) / L11;
-    double y2 = ((-g[2] - L20 * y0) - L21 * y1) / L22;
-    d[2] = y2 / L22;
-    d[1] = (y1 - L21 * d[2]) / L11;
-    d[0] = ((y0 - L10 * d[1]) - L20 * d[2]) / L00;
+    double C00 = A11 * A22 - A12 * A12;
+    double C01 = A02 * A12 - A01 * A22;
+    double C02 = A01 * A12 - A02 * A11;
+    double C11 = A00 * A22 - A02 * A02;
+    double C12 = A01 * A02 - A00 * A12;
+    double C22 = A00 * A11 - A01 * A01;
+    double det = (A00 * C00 + A01 * C01) + A02 * C02;
+    if (!(A00 > 0.0) || !(C22 > 0.0) || !(det > 0.0)) return 0;
+    double r = 1.0 / det;
+    d[0] = -(((C00 * g[0] + C01 * g[1]) + C02 * g[2]) * r);
+    d[1] = -(((C01 * g[0] + C11 * g[1]) + C12 * g[2]) * r);
+    d[2] = -(((C02 * g[0] + C12 * g[1]) + C22 * g[2]) * r);
     return 1;
 }
 
@@ -464,16 +461,16 @@ static int align_level(const level_t *L, const oracle_params *P, const float *xy
             if (lambda > P->lambda_max) { stalled = 1; break; }
         }
         if (stalled) { status = 2; break; }
-        double nt = sqrt(d[0] * d[0] + d[1] * d[1]);
-        if (nt > P->max_step_trans) {
-            double sc = P->max_step_trans / nt;
-            d[0] *= sc; d[1] *= sc; d[2] *= sc; nt = P->max_step_trans;
+        double n2 = d[0] * d[0] + d[1] * d[1];      /* squared translation step: no sqrt unless the step is clamped */
+        if (n2 > P->max_step_trans * P->max_step_trans) {
+            double sc = P->max_step_trans / sqrt(n2);
+            d[0] *= sc; d[1] *= sc; d[2] *= sc; n2 = P->max_step_trans * P->max_step_trans;
         }
         if (fabs(d[2]) > P->max_step_rot) {
             double sc = P->max_step_rot / fabs(d[2]);
-            d[0] *= sc; d[1] *= sc; d[2] *= sc; nt *= sc;
+            d[0] *= sc; d[1] *= sc; d[2] *= sc; n2 = n2 * (sc * sc);
         }
-        int small = (nt < P->eps_trans) && (fabs(d[2]) < P->eps_rot);
+        int small = (n2 < P->eps_trans * P->eps_trans) && (fabs(d[2]) < P->eps_rot);
         double pn[3] = {p[0] + d[0], p[1] + d[1], p[2] + d[2]};
         eval_t En;
         evaluate_level(L, xy, n, pn, En.v, &En.count, NULL);
