@@ -19,7 +19,8 @@
 #define NDT2D_UNROLL 1
 #endif
 #ifndef NDT2D_LDMODE
-#define NDT2D_LDMODE 0 // cell gather instruction variant (tuning experiments; 0 = ld.global.nc 256-bit)
+#define NDT2D_LDMODE 4 // cell gather instruction variant; 4 = ld.global.nc.L1::no_allocate, one 256-bit load (measured best:
+                       // a gathered record is rarely reused before L1 evicts it, and not allocating spares the fill bandwidth)
 #endif
 
 namespace ndt2d {
@@ -202,6 +203,12 @@ __device__ __forceinline__ Cell4 load_cell(const float4 *__restrict__ cells, uns
     asm("ld.global.nc.L1::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.mu), "=l"(r.B0), "=l"(r.B1), "=l"(r.nv) : "l"(p));
 #elif NDT2D_LDMODE == 4
     asm("ld.global.nc.L1::no_allocate.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.mu), "=l"(r.B0), "=l"(r.B1), "=l"(r.nv) : "l"(p));
+#elif NDT2D_LDMODE == 5
+    asm("ld.global.cg.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.mu), "=l"(r.B0), "=l"(r.B1), "=l"(r.nv) : "l"(p));
+#elif NDT2D_LDMODE == 6
+    asm("ld.global.nc.L1::no_allocate.L2::256B.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.mu), "=l"(r.B0), "=l"(r.B1), "=l"(r.nv) : "l"(p));
+#elif NDT2D_LDMODE == 7
+    asm("ld.global.nc.L1::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.mu), "=l"(r.B0), "=l"(r.B1), "=l"(r.nv) : "l"(p));
 #endif
     return r;
 }

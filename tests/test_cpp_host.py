@@ -7,14 +7,15 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "examples", "odometry_demo")
+SLAM = os.path.join(ROOT, "examples", "slam_frontend")
 
 
-def _compile():
+def _compile(exe=EXE):
     from gtsam_ndt_b200 import build
     assert os.path.exists(build.LIB_CUDA)
     libdir = os.path.dirname(build.LIB_CUDA)
     cmd = ["/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "examples", "odometry_demo.cpp"), "-L", libdir, "-lndt2d", f"-Wl,-rpath,{libdir}", "-o", EXE]
+           exe + ".cpp", "-L", libdir, "-lndt2d", f"-Wl,-rpath,{libdir}", "-o", exe]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
 
 
@@ -33,3 +34,31 @@ def test_cpp_example_runs_on_gpu():
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "final odometry error" in r.stdout
+
+
+def test_slam_frontend_compiles_and_fails_loudly_without_gpu():
+    import torch
+    _compile(SLAM)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    r = subprocess.run([SLAM, "/dev/null"], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_slam_frontend_writes_a_pose_graph(tmp_path):
+    """configs[4] without GTSAM: GPU odometry + loop-closure factors, exported as a g2o pose graph."""
+    _compile(SLAM)
+    out = tmp_path / "graph.g2o"
+    r = subprocess.run([SLAM, str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = out.read_text().splitlines()
+    vertices = [ln.split() for ln in lines if ln.startswith("VERTEX_SE2")]
+    edges = [ln.split() for ln in lines if ln.startswith("EDGE_SE2")]
+    assert len(vertices) == 97 and len(edges) == 97          # 96 odometry edges + the loop closure 0-96
+    assert edges[-1][1:3] == ["0", "96"]
+    for e in edges:                                          # information matrices are positive definite
+        i = [float(x) for x in e[6:12]]
+        c22 = i[0] * i[3] - i[1] * i[1]
+        det = i[0] * (i[3] * i[5] - i[4] * i[4]) - i[1] * (i[1] * i[5] - i[4] * i[2]) + i[2] * (i[1] * i[4] - i[3] * i[2])
+        assert i[0] > 0 and c22 > 0 and det > 0

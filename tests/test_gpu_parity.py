@@ -219,6 +219,33 @@ def test_unusable_points_are_ignored(mods, small_world):
     assert rg["status"] == 3 and rg["count"] == 0
 
 
+@pytest.mark.parametrize("overlap", [0, 1])
+def test_lattice_edges_in_the_gather_path(mods, overlap):
+    """The evaluation kernels test `inside` on integers (floor-to-int, unsigned compare) and send outside points to a
+    sentinel record; SPEC 2 states it on floats. Points exactly on, one ulp below and one ulp above every kind of
+    lattice boundary (low edge, high edge, interior cell edges, (-1, 0), huge, -0.0) must give the oracle's sums."""
+    grid = (-8.0, -6.0, 16.0, 12.0)
+    m, o = make_pair(mods, [0.5], grid, overlap=overlap)
+    rng = np.random.default_rng(11)
+    tgt = np.stack([rng.uniform(-8, 8, 60000), rng.uniform(-6, 6, 60000)], 1).astype(np.float32)
+    m.set_target(tgt); o.set_target(tgt)
+    def around(v):
+        v = np.float32(v)
+        return [np.nextafter(v, np.float32(-np.inf)), v, np.nextafter(v, np.float32(np.inf))]
+    xs = sum((around(v) for v in (-8.0, -8.25, -7.5, 0.0, 7.5, 7.75, 8.0, 8.25)), []) + [np.float32(-0.0), np.float32(1e9), np.float32(-1e9)]
+    ys = sum((around(v) for v in (-6.0, -6.25, -5.5, 0.0, 5.5, 5.75, 6.0, 6.25)), []) + [np.float32(-0.0), np.float32(1e9), np.float32(-1e9)]
+    pts = np.array([[x, y] for x in xs for y in ys], np.float32)
+    pose = np.zeros(3)                                   # identity: transformed points are the points themselves
+    assert np.array_equal(m.cell_index(pts, pose), o.cell_index(pts, pose))
+    eg, cg = m.evaluate(pts, pose); eo, co = o.evaluate(pts, pose)
+    assert cg == co and co > 0 and np.array_equal(eg, eo)
+    hyp = np.array([[0, 0, 0], [1e-3, -1e-3, 1e-4], [0.25, 0.25, 0.0]], np.float32)
+    sg, _, _ = m.sweep(pts, hyp, k=1); so = o.sweep(pts, hyp)[0]
+    assert np.array_equal(sg, so)
+    rg, ro = m.align(pts, pose), o.align(pts, pose)      # the LM loop on the same degenerate scan agrees as well
+    assert_results_match(np.array([rg]), np.array([ro]))
+
+
 def test_align_permutation_invariant_and_idempotent(mods, small_world):
     from gtsam_ndt_b200 import synth
     m, _ = make_pair(mods, [1.0, 0.5])
