@@ -140,10 +140,39 @@ struct Pose32 {
     float c, s, tx, ty;
 };
 
+// SPEC 4.2: sin and cos of the pose angle as a fixed sequence of f64 operations (two-constant Cody-Waite reduction,
+// fdlibm kernel polynomials, quadrant from the low bits of the magic sum): the oracle's bits, and about a third of
+// the instructions of the library sincos with its Payne-Hanek branch.
+__device__ __forceinline__ void sincos_spec(double th, double &sn_out, double &cs_out)
+{
+    const double MAGIC = 6755399441055744.0; // 1.5 * 2^52
+    const double t = __fma_rn(th, 0.63661977236758138, MAGIC);
+    const double k = __dadd_rn(t, -MAGIC);
+    const int q = __double2loint(t) & 3;
+    double r = __fma_rn(-k, 1.5707963267948966, th);
+    r = __fma_rn(-k, 6.123233995736766e-17, r);
+    const double z = __dmul_rn(r, r);
+    double ps = __fma_rn(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = __fma_rn(z, ps, 2.75573137070700676789e-06);
+    ps = __fma_rn(z, ps, -1.98412698298579493134e-04);
+    ps = __fma_rn(z, ps, 8.33333333332248946124e-03);
+    ps = __fma_rn(z, ps, -1.66666666666666324348e-01);
+    const double sn = __fma_rn(__dmul_rn(r, z), ps, r);
+    double pc = __fma_rn(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = __fma_rn(z, pc, -2.75573143513906633035e-07);
+    pc = __fma_rn(z, pc, 2.48015872894767294178e-05);
+    pc = __fma_rn(z, pc, -1.38888888888741095749e-03);
+    pc = __fma_rn(z, pc, 4.16666666666666019037e-02);
+    const double cs = __fma_rn(__dmul_rn(z, z), pc, __fma_rn(z, -0.5, 1.0));
+    const double s4 = (q & 1) ? cs : sn, c4 = (q & 1) ? sn : cs;
+    sn_out = (q & 2) ? -s4 : s4;
+    cs_out = ((q + 1) & 2) ? -c4 : c4;
+}
+
 __device__ __forceinline__ Pose32 pose_to_f32(double tx, double ty, double th)
 {
     double sn, cs;
-    sincos(th, &sn, &cs);
+    sincos_spec(th, sn, cs);
     Pose32 q;
     q.c = (float)cs;
     q.s = (float)sn;

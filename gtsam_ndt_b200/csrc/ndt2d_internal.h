@@ -54,9 +54,18 @@ cudaError_t launch_eval_poses(const LaunchCfg &c, const LevelDev &L, const float
                               int64_t *launches);
 cudaError_t launch_align(const LaunchCfg &c, const AlignArgs &a, int64_t *launches);
 size_t align_smem_bytes(int cap_points); // dynamic shared memory per k_align block
-// top-k of scores by (-score, index); k small. d_work: nhyp bytes of scratch (mask).
+// Publication of a shard's best hypothesis into every rank's exchange table (peer pointers, NVLink stores).
+struct PublishArgs {
+    ndt2d_best *table[NDT2D_MAX_RANKS]; // table[r] = rank r's table as seen from this device (world entries used)
+    int world, rank, row;               // row = query % nslots; world == 0: nothing to publish
+    long long index_offset;
+    unsigned long long epoch;           // query + 1
+};
+
+// top-k of scores by (-score, index); k small. d_work: nhyp bytes of scratch (mask). pub (optional, k == 1): the
+// finishing block also stores the winner into the peers' exchange tables.
 cudaError_t launch_topk(const LaunchCfg &c, const double *d_scores, int64_t nhyp, int k, int64_t *d_idx, double *d_val,
-                        unsigned long long *d_scratch, int64_t *launches);
+                        unsigned long long *d_scratch, int64_t *launches, const PublishArgs *pub = nullptr);
 int topk_scratch_words(int sm_count);
 // finite bounding box of points: d_box[4] = ordered-int encoded {xmin, ymin, xmax, ymax} (see bbox_decode)
 cudaError_t launch_bbox(const LaunchCfg &c, const float2 *d_xy, int64_t n, int *d_box, int64_t *launches);

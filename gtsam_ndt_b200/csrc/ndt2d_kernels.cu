@@ -442,9 +442,12 @@ __device__ __forceinline__ bool better(double s1, long long i1, double s2, long 
 }
 
 // scratch layout: [0] ticket counter, then per block {score bits, index}
+// pub.world > 0 (multi-GPU sweep): the finishing warp also stores the winner into row pub.row, column pub.rank of
+// every rank's exchange table - lane r writes to rank r over NVLink (or locally for r == rank) - record first, a
+// system-scope fence, then the epoch that tells the reader the record is complete.
 __global__ void __launch_bounds__(256) k_argmax_pass(const double *__restrict__ scores, int64_t n, int pass,
                                                      int64_t *__restrict__ best_idx, double *__restrict__ best_val,
-                                                     unsigned long long *__restrict__ scratch)
+                                                     unsigned long long *__restrict__ scratch, const PublishArgs pub)
 {
     __shared__ double s_val[8];
     __shared__ long long s_idx[8];
@@ -496,6 +499,13 @@ __global__ void __launch_bounds__(256) k_argmax_pass(const double *__restrict__ 
             best_idx[pass] = bi;
             best_val[pass] = bi >= 0 ? bv : 0.0;
             scratch[0] = 0ull; // ready for the next pass
+        }
+        if (lane < pub.world) {
+            ndt2d_best *dst = pub.table[lane] + (size_t)pub.row * pub.world + pub.rank;
+            dst->index = bi >= 0 ? bi + pub.index_offset : -1;
+            dst->score = bi >= 0 ? bv : 0.0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(&dst->epoch) = pub.epoch;
         }
     }
 }
@@ -636,13 +646,15 @@ cudaError_t launch_align(const LaunchCfg &c, const AlignArgs &a, int64_t *launch
 }
 
 cudaError_t launch_topk(const LaunchCfg &c, const double *d_scores, int64_t nhyp, int k, int64_t *d_idx, double *d_val,
-                        unsigned long long *d_scratch, int64_t *launches)
+                        unsigned long long *d_scratch, int64_t *launches, const PublishArgs *pub)
 {
     int grid = grid_for(nhyp, 256 * 4, c.sm_count, 4);
     cudaError_t e = cudaMemsetAsync(d_scratch, 0, sizeof(unsigned long long), c.stream);
     if (e != cudaSuccess) return e;
+    PublishArgs none;
+    memset(&none, 0, sizeof(none));
     for (int pass = 0; pass < k; ++pass) {
-        k_argmax_pass<<<grid, 256, 0, c.stream>>>(d_scores, nhyp, pass, d_idx, d_val, d_scratch);
+        k_argmax_pass<<<grid, 256, 0, c.stream>>>(d_scores, nhyp, pass, d_idx, d_val, d_scratch, (pub && pass == 0) ? *pub : none);
         ++*launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

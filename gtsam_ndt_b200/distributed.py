@@ -68,6 +68,47 @@ def sweep_sharded(score_shard, nhyp, k=1):
     return combine_topk(idx, score, k)
 
 
+def all_gather_blobs(blob):
+    """All-gather one fixed-size bytes object per rank (e.g. a 64-byte CUDA IPC handle); returns the list by rank.
+    Works on both back ends: the bytes travel as a uint8 tensor on the back end's device."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [bytes(blob)]
+    dev = _device_for_backend()
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+    out = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, mine)
+    return [bytes(t.cpu().numpy().tobytes()) for t in out]
+
+
+class PeerExchange:
+    """Best-hypothesis combine of a sharded sweep through peer memory (include/ndt2d.h, ndt2d_exchange_*).
+
+    Every rank's arg-max kernel stores its best (global index, score) directly into every rank's table over NVLink,
+    so the combine is part of the sweep launch and no collective runs per query; torch.distributed is used once, to
+    hand the CUDA IPC handles round. `nslots` bounds the number of queries in flight."""
+
+    def __init__(self, matcher, nslots=64):
+        self.m = matcher
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.nslots = nslots
+        handle = matcher.exchange_create(self.world, self.rank, nslots)
+        matcher.exchange_open(all_gather_blobs(handle))
+        if self.world > 1:
+            dist.barrier()          # every table is open everywhere before anyone publishes
+
+    def publish(self, d_xy, n, d_hyp, nhyp, d_scores, index_offset, query, level=0):
+        self.m.sweep_publish(d_xy, n, d_hyp, nhyp, d_scores, index_offset, query, level)
+
+    def wait(self, query, timeout_ms=10000):
+        return self.m.exchange_wait(query, timeout_ms)
+
+    def close(self):
+        if self.world > 1:
+            dist.barrier()          # nobody frees a table a peer may still be writing to
+        self.m.exchange_close()
+
+
 def align_sharded_counts(nscans):
     """[lo, hi) of this rank's scans for a batched align; results stay on the rank that computed them."""
     rank = dist.get_rank() if dist.is_initialized() else 0

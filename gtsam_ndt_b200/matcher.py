@@ -240,6 +240,31 @@ class NdtMatcher2D:
         self._ck(self._L.ndt2d_sweep_device(self._h, level, _ptr(d_xy), n, _ptr(d_hyp), nhyp, _ptr(d_scores), k,
                                             _ptr(d_best_idx), _ptr(d_best_score)))
 
+    # ---- multi-GPU sweep: best-hypothesis exchange over peer memory (one process per GPU) ----
+    def exchange_create(self, world, rank, nslots=64):
+        """Allocate this rank's exchange table; returns its 64-byte CUDA IPC handle (bytes) for the other ranks."""
+        h = (C.c_ubyte * 64)()
+        self._ck(self._L.ndt2d_exchange_create(self._h, world, rank, nslots, C.cast(h, C.c_void_p)))
+        return bytes(h)
+
+    def exchange_open(self, handles):
+        """handles: world x 64 bytes (entry r from rank r)."""
+        buf = np.frombuffer(b"".join(handles) if isinstance(handles, (list, tuple)) else bytes(handles), np.uint8).copy()
+        self._ck(self._L.ndt2d_exchange_open(self._h, _ptr(buf)))
+
+    def sweep_publish(self, d_xy, n, d_hyp, nhyp, d_scores, index_offset, query, level=0):
+        """Sweep this rank's shard on the device and store its best (global index, score) into every rank's table."""
+        self._ck(self._L.ndt2d_sweep_publish(self._h, level, _ptr(d_xy), n, _ptr(d_hyp), nhyp, _ptr(d_scores), index_offset, query))
+
+    def exchange_wait(self, query, timeout_ms=10000):
+        """Global best (index, score) of `query` once every rank has published it (host-side poll of the own table)."""
+        bi, bs = C.c_int64(-1), C.c_double(0.0)
+        self._ck(self._L.ndt2d_exchange_wait(self._h, query, timeout_ms, C.byref(bi), C.byref(bs)))
+        return bi.value, bs.value
+
+    def exchange_close(self):
+        self._ck(self._L.ndt2d_exchange_close(self._h))
+
     def relocalize(self, xy, hyp, k=4, level=0):
         xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
         hyp = np.ascontiguousarray(hyp, np.float32).reshape(-1, 3)

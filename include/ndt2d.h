@@ -41,7 +41,8 @@ enum {
     NDT2D_EINVAL = 1,   /* bad argument */
     NDT2D_ECUDA = 2,    /* CUDA runtime error (no device, launch failure, ...) */
     NDT2D_ENOTARGET = 3,/* align/evaluate/sweep before set_target */
-    NDT2D_ENOMEM = 4
+    NDT2D_ENOMEM = 4,
+    NDT2D_ETIMEOUT = 5  /* ndt2d_exchange_wait: a rank did not publish in time */
 };
 
 /* align status, SPEC.md section 5 */
@@ -167,6 +168,39 @@ int ndt2d_sweep_device(ndt2d_matcher *m, int level, const float *d_xy, int n, co
 /* sweep, then full align from each of the k best hypotheses; res[k] sorted like the top-k */
 int ndt2d_relocalize(ndt2d_matcher *m, int level, const float *xy, int n, const float *hyp, int64_t nhyp,
                      int k, int64_t *best_idx, ndt2d_result *res);
+
+/* ---- multi-GPU sweep: best-hypothesis exchange over peer memory (north_star: "independent ... pose
+ *      hypotheses are split per GPU", only the best-hypothesis scores are combined) --------------
+ * One process per GPU. Each rank owns a table of nslots x world records; the last block of the
+ * arg-max kernel of a sharded sweep stores this rank's best {index, score, query + 1} straight into
+ * row (query % nslots), column rank of EVERY rank's table (NVLink peer stores from inside the kernel:
+ * the combine is part of the sweep launch, there is no separate collective). Reading the result is a
+ * host-side poll of the caller's own table: nothing ever spins on the device.
+ * Reference interface replaced: none citable (/root/reference/README.md:1 is the whole mount). */
+#define NDT2D_IPC_HANDLE_BYTES 64
+#define NDT2D_MAX_RANKS 16
+typedef struct ndt2d_best {
+    int64_t index;      /* global hypothesis index, -1 when the shard was empty */
+    double score;
+    uint64_t epoch;     /* query + 1; written last */
+    uint64_t reserved;
+} ndt2d_best;
+
+/* allocate this rank's table and return its CUDA IPC handle (64 bytes) for the other ranks */
+int ndt2d_exchange_create(ndt2d_matcher *m, int world, int rank, int nslots, unsigned char *handle);
+/* handles = world x 64 bytes, entry r from rank r (the own entry is ignored); opens the peers' tables */
+int ndt2d_exchange_open(ndt2d_matcher *m, const unsigned char *handles);
+/* sweep of this rank's shard + top-1 + publication, asynchronous on the handle's stream. Hypothesis j of
+ * the shard has global index index_offset + j. d_scores may be NULL. Slot discipline: row query % nslots is
+ * overwritten by query + nslots, so a rank must have waited for query q - nslots/2 (or a later one) before it
+ * publishes q; then no rank can overwrite a row another rank is still waiting on. */
+int ndt2d_sweep_publish(ndt2d_matcher *m, int level, const float *d_xy, int n, const float *d_hyp,
+                        int64_t nhyp, double *d_scores, int64_t index_offset, uint64_t query);
+/* block until every rank has published `query` (or timeout_ms elapsed: NDT2D_ETIMEOUT), then return the
+ * best hypothesis by (-score, index), as an unsharded ndt2d_sweep would (SPEC.md section 6) */
+int ndt2d_exchange_wait(ndt2d_matcher *m, uint64_t query, int timeout_ms, int64_t *best_index, double *best_score);
+/* frees the own table and closes the peers'. Synchronise the ranks first: a peer must not publish afterwards. */
+int ndt2d_exchange_close(ndt2d_matcher *m);
 
 /* ---- pinned host memory for callers that want full-speed copies ------------------------------ */
 int ndt2d_host_alloc(void **p, size_t bytes);

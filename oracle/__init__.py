@@ -190,6 +190,13 @@ def expneg(h):
     return lib().oracle_expneg(C.c_float(h))
 
 
+def sincos(th):
+    """SPEC 4.2: (sin, cos) of a pose angle by the specified f64 sequence."""
+    sn, cs = C.c_double(0), C.c_double(0)
+    lib().oracle_sincos(C.c_double(th), C.byref(sn), C.byref(cs))
+    return sn.value, cs.value
+
+
 def solve(g, H6, lam):
     g = np.ascontiguousarray(g, np.float64)
     H6 = np.ascontiguousarray(H6, np.float64)

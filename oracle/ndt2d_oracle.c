@@ -270,12 +270,45 @@ int oracle_get_sums(const oracle_matcher *m, int level, uint32_t *n, int64_t *su
     return 0;
 }
 
+/* SPEC 4.2: sin and cos of the pose angle as a fixed sequence of f64 operations (two-constant Cody-Waite
+ * reduction to [-pi/4, pi/4], the fdlibm kernel polynomials, quadrant from the low bits of the magic sum), so
+ * that every implementation gets the same bits; absolute error below 2e-16 for |theta| < 1e5. */
+void oracle_sincos(double th, double *sn_out, double *cs_out)
+{
+    const double MAGIC = 6755399441055744.0;                       /* 1.5 * 2^52 */
+    double t = fma(th, 0.63661977236758138, MAGIC);                /* round(th * 2/pi) in the low mantissa bits */
+    double k = t - MAGIC;
+    uint64_t tb;
+    memcpy(&tb, &t, 8);
+    int q = (int)(tb & 3u);
+    double r = fma(-k, 1.5707963267948966, th);                    /* pi/2 = 1.5707963267948966 + 6.123233995736766e-17 */
+    r = fma(-k, 6.123233995736766e-17, r);
+    double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double sn = fma(r * z, ps, r);                                 /* r + r^3 P(z) */
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double cs = fma(z * z, pc, fma(z, -0.5, 1.0));                 /* 1 - z/2 + z^2 Q(z) */
+    double s4 = (q & 1) ? cs : sn, c4 = (q & 1) ? sn : cs;         /* quadrant: q = 0 (s,c) 1 (c,-s) 2 (-s,-c) 3 (-c,s) */
+    *sn_out = (q & 2) ? -s4 : s4;
+    *cs_out = ((q + 1) & 2) ? -c4 : c4;
+}
+
 /* SPEC 4: pose to f32 */
 typedef struct { float c, s, tx, ty; } pose32;
 static pose32 pose_to_f32(const double p[3])
 {
     pose32 q;
-    q.c = (float)cos(p[2]); q.s = (float)sin(p[2]);
+    double sn, cs;
+    oracle_sincos(p[2], &sn, &cs);
+    q.c = (float)cs; q.s = (float)sn;
     q.tx = (float)p[0]; q.ty = (float)p[1];
     return q;
 }

@@ -80,6 +80,7 @@ int oracle_polar_to_points(const float *ranges_f32, const uint16_t *ranges_u16, 
                            float range_min, float range_max, float *xy_out);
 /* the bit-exact pieces, exposed for unit tests */
 float oracle_expneg(float h);
+void oracle_sincos(double th, double *sn, double *cs); /* SPEC 4.2 */
 int oracle_solve(const double g[3], const double H6[6], double lambda, double d[3]);
 int oracle_num_threads(void);
 

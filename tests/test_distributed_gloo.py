@@ -40,6 +40,9 @@ def _worker(rank, world, port, q):
         exp = np.lexsort((np.arange(len(full)), -full))[:5]
         ok = np.array_equal(gi, exp) and np.array_equal(gs, full[exp])
         lo, hi = D.align_sharded_counts(101)
+        # the plumbing of the peer-memory exchange: one 64-byte blob per rank (a CUDA IPC handle on the GPU box), by rank
+        blobs = D.all_gather_blobs(bytes([rank + 1]) * 64)
+        ok = ok and blobs == [bytes([r + 1]) * 64 for r in range(world)]
         q.put((rank, bool(ok), (lo, hi), gi.tolist()))
     finally:
         dist.destroy_process_group()
