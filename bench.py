@@ -38,13 +38,16 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 10; 50 for --workload sweep, whose steps are 0.3-2 ms)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="scan2map", choices=["scan2map", "pyramid", "sweep"],
                     help="scan2map: BASELINE configs[1] (default, the metric's config); pyramid: configs[2] (2.0/1.0/0.5 m, "
                          "10k scans, 0.2 m / 3 deg prior error); sweep: configs[3] (1M hypotheses x one 1080-pt scan)")
     ap.add_argument("--hyps", type=int, default=1000000, help="sweep: total hypotheses (sharded across GPUs)")
+    ap.add_argument("--combine", default="p2p", choices=["p2p", "nccl"],
+                    help="sweep on N > 1 GPUs: best-hypothesis combine by peer-memory stores from the arg-max kernel (p2p) "
+                         "or by an NCCL all-gather on a side stream (nccl)")
     ap.add_argument("--scans", type=int, default=None, help="scans per step per GPU (65536 x 1080 x 8 B = 566 MB, far above the 126 MB L2)")
     ap.add_argument("--map-scans", type=int, default=2048, help="scans fused into the target map")
     ap.add_argument("--res", type=float, nargs="+", default=None)
@@ -59,6 +62,8 @@ def parse_args():
     a = ap.parse_args()
     dflt = {"scan2map": (65536, [0.25], [0.03, 0.3]), "pyramid": (10000, [2.0, 1.0, 0.5], [0.2, 3.0]), "sweep": (1, [0.25], [0.0, 0.0])}[a.workload]
     a.scans = a.scans or dflt[0]
+    if a.steps is None:
+        a.steps = 50 if a.workload == "sweep" else 10
     a.res = a.res or dflt[1]
     a.perturb = a.perturb or dflt[2]
     return a
@@ -421,23 +426,42 @@ def run_sweep(args):
     nrot = max(2, int(math.ceil(160e6 / max(1, (hi - lo) * 20))))
     d_hyps = [torch.from_numpy(hyp[lo:hi].copy()).to(dev) for _ in range(nrot)]
     d_scores_rot = [torch.zeros(hi - lo, dtype=torch.float64, device=dev) for _ in range(nrot)]
-    # the library writes (local best index, best score bits) straight into one 16-byte buffer, which is what is
-    # all-gathered: no arithmetic kernels between the sweep and the collective (the shard offset is added on the host).
-    # Successive sweeps are independent queries, so the 16 B combine of query i runs on a side stream while the
-    # kernel of query i+1 runs on the main stream (two buffers; events order producer and consumer both ways).
+    # Successive sweeps are independent queries. Combine of the per-GPU bests, two implementations:
+    #  p2p  - ndt2d_sweep_publish: the arg-max kernel's final block stores this rank's best (global index, score) into
+    #         every rank's table over NVLink; no collective per query; the host polls its own table LAG queries later.
+    #  nccl - the library writes (local best index, score bits) into one 16-byte buffer that is all-gathered on a side
+    #         stream while the next query's kernel runs on the main stream (two buffers, events both ways).
+    LAG, NSLOTS = 8, 64
+    ex, combine = None, "none (1 GPU)"
+    if world > 1 and args.combine == "p2p":
+        try:
+            ex = D.PeerExchange(m, nslots=NSLOTS)
+            combine = "p2p: peer-memory stores from the arg-max kernel (ndt2d_sweep_publish), host poll %d queries behind" % LAG
+        except Exception as e:      # e.g. CUDA IPC not permitted in this container: say so and use the NCCL path
+            print(f"[bench] peer-memory exchange unavailable ({e}); using the NCCL combine", file=sys.stderr)
+            ex = None
+    if world > 1 and ex is None:
+        combine = "nccl: all-gather of one 16 B pair per rank on a side stream, overlapping the next sweep"
     pair = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(2)]
     gathered = [torch.zeros(2 * world, dtype=torch.int64, device=dev) for _ in range(2)]
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    comm = torch.cuda.Stream(device=dev) if world > 1 and ex is None else None
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
-    state = {"i": 0, "pending": [False, False]}
+    state = {"i": 0, "pending": [False, False], "waited": 0, "best": None}
 
     def step():
-        b = state["i"] & 1
+        i = state["i"]
         state["i"] += 1
+        r = i % nrot
+        if ex is not None:
+            ex.publish(d_xy, len(xy), d_hyps[r], hi - lo, d_scores_rot[r], lo, i)
+            if i >= LAG:
+                state["best"] = ex.wait(i - LAG)
+                state["waited"] = i - LAG + 1
+            return
+        b = i & 1
         if world > 1 and state["pending"][b]:
             stream.wait_event(consumed[b])        # the combine of query i-2 has read pair[b]
-        r = (state["i"] - 1) % nrot
         m.sweep_device(d_xy, len(xy), d_hyps[r], hi - lo, d_scores_rot[r], 1, pair[b].data_ptr(), pair[b].data_ptr() + 8)
         if world > 1:   # best-hypothesis combine: 16 B per rank
             ready[b].record(stream)
@@ -448,8 +472,12 @@ def run_sweep(args):
             state["pending"][b] = True
 
     def drain():
-        """main stream waits for every outstanding combine (called before the closing timing event)"""
-        if world > 1:
+        """every outstanding combine has delivered its result (called before the closing timing event)"""
+        if ex is not None:
+            for q in range(state["waited"], state["i"]):
+                state["best"] = ex.wait(q)
+            state["waited"] = state["i"]
+        elif world > 1:
             for b in range(2):
                 if state["pending"][b]:
                     stream.wait_event(consumed[b])
@@ -501,7 +529,7 @@ def run_sweep(args):
                 "config": {"workload": "configs[3]: relocalisation, %d pose hypotheses (0.2 m x 0.2 m x 3 deg lattice) x one %d-pt scan vs 200x200 m map at %s m cells (K=%d), hypotheses sharded over %d GPU(s)"
                                        % (len(hyp), len(xy), args.res[0], K, world),
                            "l2": "steps rotate through %d copies of the shard's hypotheses and score buffers (%.0f MB in total > 126 MB L2); the scan and the cell table are cache-resident by design" % (nrot, nrot * (hi - lo) * 20 / 1e6),
-                           "parallelism": "hypotheses sharded per GPU; all-gather of one (score, index) pair per rank, issued on a side stream so that it overlaps the next query's sweep"},
+                           "parallelism": "hypotheses sharded per GPU; combine of one (score, index) pair per rank: " + combine},
                 "e2e": {"value": len(hyp) * args.steps / (e2e_ms / 1e3), "unit": "hypotheses/s", "h2d_bytes_per_step": int((hi - lo) * 12 + len(xy) * 8),
                         "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / args.steps, "api": "ndt2d_sweep + combine_topk"},
                 "gpu_launches": int(launches),
@@ -510,7 +538,11 @@ def run_sweep(args):
                              "kernel": "k_eval_poses (score only)", "peak_source": peak_src, "bytes_per_hypothesis": per_hyp,
                              "convention": "gather traffic (see DESIGN.md section 4); scan and cells are cache-resident"},
                 "best_hypothesis_abs_err_vs_truth": truth_err, "clocks": clocks}
+        if ex is not None and state["best"] is not None:
+            line["combine_equals_host_api_result"] = bool(int(state["best"][0]) == int(gi[0]) and float(state["best"][1]) == float(gs[0]))
         print(json.dumps(line), flush=True)
+    if ex is not None:
+        ex.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
@@ -542,6 +574,9 @@ def cpu_baseline(args, xy, offsets, init, map_xy, res_gpu):
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -85,7 +85,8 @@ struct ndt2d_matcher {
     int ex_world = 0, ex_rank = 0, ex_slots = 0;
     ndt2d_best *ex_table[NDT2D_MAX_RANKS] = {};
     bool ex_opened[NDT2D_MAX_RANKS] = {};
-    ndt2d_best *ex_host = nullptr; // pinned staging for the host-side poll, 2 x world records
+    ndt2d_best *ex_host = nullptr; // pinned staging for the host-side poll: two snapshots of the whole table
+    std::vector<char> ex_verified_ok; // per row: the second snapshot holds a verified, complete row
     int chunk_scans = 4096; // measured on PCIe 5 x16: 4096-scan chunks shorten the un-overlapped first copy and last kernel (f32 ranges 10.1 -> 10.7-11.5 M matches/s)
     int64_t launches = 0;
     std::string err;
@@ -900,7 +901,7 @@ int ndt2d_exchange_create(ndt2d_matcher *m, int world, int rank, int nslots, uns
     ndt2d_best *own = nullptr;
     CK(m, cudaMalloc(reinterpret_cast<void **>(&own), bytes)); // its own allocation: IPC handles name whole allocations
     cudaError_t e = cudaMemset(own, 0, bytes);                 // epoch 0 = nothing published
-    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&m->ex_host), 2 * (size_t)world * sizeof(ndt2d_best), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&m->ex_host), 2 * bytes, cudaHostAllocDefault);
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, own);
     if (e != cudaSuccess) {
@@ -912,6 +913,7 @@ int ndt2d_exchange_create(ndt2d_matcher *m, int world, int rank, int nslots, uns
     memcpy(handle, &h, sizeof(h));
     m->ex_world = world; m->ex_rank = rank; m->ex_slots = nslots;
     m->ex_table[rank] = own;
+    m->ex_verified_ok.assign((size_t)nslots, 0);
     return NDT2D_OK;
 }
 
@@ -962,38 +964,64 @@ int ndt2d_sweep_publish(ndt2d_matcher *m, int level, const float *d_xy, int n, c
     return NDT2D_OK;
 }
 
+// best of one complete row by (-score, index), SPEC 6
+static void exchange_pick(const ndt2d_best *row, int W, int64_t *best_index, double *best_score)
+{
+    int64_t bi = -1;
+    double bs = 0.0;
+    for (int r = 0; r < W; ++r) {
+        const ndt2d_best &b = row[r];
+        if (b.index < 0 || b.score != b.score) continue;
+        if (bi < 0 || b.score > bs || (b.score == bs && b.index < bi)) { bi = b.index; bs = b.score; }
+    }
+    *best_index = bi;
+    *best_score = bs;
+}
+
+// The poll copies the WHOLE table (nslots x world x 32 B, a few KB) to pinned memory on the copy stream, so that it never
+// waits for kernels queued on the handle's stream. A row is trusted only from a snapshot taken after an earlier snapshot
+// already showed all its epochs (record, system fence, epoch: a complete epoch guarantees the record was written before
+// the later copy started). The verified snapshot is kept, so waiting for several finished queries costs two copies in all.
 int ndt2d_exchange_wait(ndt2d_matcher *m, uint64_t query, int timeout_ms, int64_t *best_index, double *best_score)
 {
     if (!m || !best_index || !best_score) return NDT2D_EINVAL;
     if (m->ex_world == 0) return fail(m, NDT2D_EINVAL, "exchange_wait before exchange_create");
     DeviceGuard g(m->device);
     const int W = m->ex_world;
-    const ndt2d_best *row = m->ex_table[m->ex_rank] + (size_t)(query % (uint64_t)m->ex_slots) * W;
-    const size_t bytes = (size_t)W * sizeof(ndt2d_best);
+    const size_t rows = (size_t)m->ex_slots, bytes = rows * W * sizeof(ndt2d_best);
+    const size_t row = (size_t)(query % (uint64_t)m->ex_slots);
+    ndt2d_best *probe = m->ex_host, *verified = m->ex_host + rows * W;
+    auto complete = [&](const ndt2d_best *t) {
+        for (int r = 0; r < W; ++r)
+            if (t[row * W + r].epoch != query + 1) return false;
+        return true;
+    };
+    if (m->ex_verified_ok[row] && complete(verified)) {
+        exchange_pick(verified + row * W, W, best_index, best_score);
+        return NDT2D_OK;
+    }
     const auto t0 = std::chrono::steady_clock::now();
     for (;;) {
-        // the poll runs on the copy stream so that it never waits for the kernels queued on the handle's stream
-        CK(m, cudaMemcpyAsync(m->ex_host, row, bytes, cudaMemcpyDeviceToHost, m->copy_stream));
+        CK(m, cudaMemcpyAsync(probe, m->ex_table[m->ex_rank], bytes, cudaMemcpyDeviceToHost, m->copy_stream));
         CK(m, cudaStreamSynchronize(m->copy_stream));
-        bool all = true;
-        for (int r = 0; r < W; ++r) all = all && (m->ex_host[r].epoch == query + 1);
-        if (all) break;
+        if (complete(probe)) break;
         const auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
         if (ms > timeout_ms) return fail(m, NDT2D_ETIMEOUT, "exchange_wait: query %llu not published by every rank within %d ms",
                                          (unsigned long long)query, timeout_ms);
     }
-    // every epoch was seen, so every record was complete before this second read started (record, fence, epoch)
-    CK(m, cudaMemcpyAsync(m->ex_host + W, row, bytes, cudaMemcpyDeviceToHost, m->copy_stream));
+    CK(m, cudaMemcpyAsync(verified, m->ex_table[m->ex_rank], bytes, cudaMemcpyDeviceToHost, m->copy_stream));
     CK(m, cudaStreamSynchronize(m->copy_stream));
-    int64_t bi = -1;
-    double bs = 0.0;
-    for (int r = 0; r < W; ++r) {
-        const ndt2d_best &b = m->ex_host[W + r];
-        if (b.index < 0 || b.score != b.score) continue;
-        if (bi < 0 || b.score > bs || (b.score == bs && b.index < bi)) { bi = b.index; bs = b.score; }
+    for (size_t q = 0; q < rows; ++q) {   // a row of the second snapshot is verified if the first one already showed it complete
+        bool same = true;
+        for (int r = 0; r < W; ++r)
+            same = same && probe[q * W + r].epoch == verified[q * W + r].epoch && probe[q * W + r].epoch == probe[q * W].epoch &&
+                   probe[q * W].epoch != 0;
+        m->ex_verified_ok[q] = same;
     }
-    *best_index = bi;
-    *best_score = bs;
+    if (!m->ex_verified_ok[row] || !complete(verified))   // the row moved on between the two copies: slot discipline broken
+        return fail(m, NDT2D_EINVAL, "exchange_wait: row of query %llu was overwritten while waiting (see the slot discipline in ndt2d.h)",
+                    (unsigned long long)query);
+    exchange_pick(verified + row * W, W, best_index, best_score);
     return NDT2D_OK;
 }
 
