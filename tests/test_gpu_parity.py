@@ -304,6 +304,36 @@ def test_sweep_matches_oracle(mods, small_world, overlap):
     assert list(bi2[5:]) == [-1, -1, -1] and sorted(bi2[:5]) == [0, 1, 2, 3, 4]
 
 
+def test_sweep_publish_world1_equals_sweep(mods, small_world):
+    """The peer-memory exchange with a single rank: the arg-max kernel publishes into the rank's own table and the host
+    poll returns what ndt2d_sweep returns (index shifted by index_offset); slots are reused as the epochs grow."""
+    import torch
+    m, o = make_pair(mods, [0.5], None)
+    m.set_target(small_world["map_xy"]); o.set_target(small_world["map_xy"])
+    xy = small_world["scans"][1]
+    rng = np.random.default_rng(5)
+    handle = m.exchange_create(1, 0, nslots=4)
+    assert len(handle) == 64
+    m.exchange_open([handle])
+    dev = torch.device("cuda", 0)
+    d_xy = torch.from_numpy(np.ascontiguousarray(xy, np.float32)).to(dev)
+    for q in range(10):
+        hyp = (small_world["init"][1] + rng.normal(size=(700 + q, 3)) * [0.3, 0.3, 0.03]).astype(np.float32)
+        hyp[5] = hyp[3]                                  # an exact tie: the smaller index wins
+        d_hyp = torch.from_numpy(hyp).to(dev)
+        m.sweep_publish(d_xy, len(xy), d_hyp, len(hyp), None, 1000 * q, q)
+        bi, bs = m.exchange_wait(q, timeout_ms=5000)
+        _, ri, rs = m.sweep(xy, hyp, k=1, want_scores=False)
+        so, oi, os_ = o.sweep(xy, hyp)
+        assert bi == int(ri[0]) + 1000 * q == oi + 1000 * q and bs == float(rs[0]) == os_
+        assert m.exchange_wait(q) == (bi, bs)            # answered from the verified snapshot
+    with pytest.raises(Exception):
+        m.exchange_wait(12345, timeout_ms=50)            # never published: NDT2D_ETIMEOUT, reported, no hang
+    m.exchange_close()
+    with pytest.raises(Exception):
+        m.sweep_publish(d_xy, len(xy), d_hyp, len(hyp), None, 0, 0)
+
+
 def test_relocalize_refines_topk(mods, small_world):
     m, o = make_pair(mods, [2.0, 0.5])
     m.set_target(small_world["map_xy"]); o.set_target(small_world["map_xy"])
