@@ -87,7 +87,7 @@ struct ndt2d_matcher {
     bool ex_opened[NDT2D_MAX_RANKS] = {};
     ndt2d_best *ex_host = nullptr; // pinned staging for the host-side poll: two snapshots of the whole table
     std::vector<char> ex_verified_ok; // per row: the second snapshot holds a verified, complete row
-    int chunk_scans = 4096; // measured on PCIe 5 x16: 4096-scan chunks shorten the un-overlapped first copy and last kernel (f32 ranges 10.1 -> 10.7-11.5 M matches/s)
+    int chunk_scans = 0; // NDT2D_CHUNK_SCANS override; 0 = choose by bytes (plan_chunks)
     int64_t launches = 0;
     std::string err;
 };
@@ -247,10 +247,15 @@ struct ChunkPlan {
     int nchunks, per;
 };
 
-ChunkPlan plan_chunks(const ndt2d_matcher *m, int nscans)
+// Chunk size: a copy-bound call (f32 ranges, float2 points) wants small chunks, which shorten the un-overlapped first
+// copy and last kernel (measured on PCIe 5 x16, 65 536 scans: 8192-scan chunks 10.1 M matches/s, 4096-scan chunks
+// 10.7-11.5 M); a kernel-bound call (u16 ranges) wants large ones, since every chunk is a launch with its own partial
+// last wave (15.9 M vs 15.1 M). About 18 MB per chunk gives 16 chunks for the former and 8 for the latter.
+ChunkPlan plan_chunks(const ndt2d_matcher *m, int nscans, size_t total_bytes)
 {
     ChunkPlan p;
-    p.nchunks = (nscans + m->chunk_scans - 1) / m->chunk_scans;
+    if (m->chunk_scans > 0) p.nchunks = (nscans + m->chunk_scans - 1) / m->chunk_scans;
+    else p.nchunks = (int)((total_bytes + (18u << 20) - 1) / (18u << 20));
     if (p.nchunks > ndt2d_matcher::MAX_CHUNKS) p.nchunks = ndt2d_matcher::MAX_CHUNKS;
     if (p.nchunks < 1) p.nchunks = 1;
     p.per = (nscans + p.nchunks - 1) / p.nchunks;
@@ -258,9 +263,9 @@ ChunkPlan plan_chunks(const ndt2d_matcher *m, int nscans)
 }
 
 template <typename CopyFn, typename LaunchFn>
-int run_pipeline(ndt2d_matcher *m, int nscans, ndt2d_result *res, CopyFn copy_chunk, LaunchFn launch_chunk)
+int run_pipeline(ndt2d_matcher *m, int nscans, size_t total_bytes, ndt2d_result *res, CopyFn copy_chunk, LaunchFn launch_chunk)
 {
-    const ChunkPlan pl = plan_chunks(m, nscans);
+    const ChunkPlan pl = plan_chunks(m, nscans, total_bytes);
     CK(m, cudaEventRecord(m->ev_begin, m->cfg.stream)); // earlier work on the handle's stream comes first
     CK(m, cudaStreamWaitEvent(m->copy_stream, m->ev_begin, 0));
     for (int i = 0; i < 2; ++i) CK(m, cudaStreamWaitEvent(m->work_stream[i], m->ev_begin, 0));
@@ -702,7 +707,7 @@ int ndt2d_align_batch(ndt2d_matcher *m, const float *xy, const int64_t *offsets,
     if ((rc = upload(m, m->b_off, offsets, (size_t)(nscans + 1) * 8))) return rc;
     if ((rc = upload(m, m->b_init, init, (size_t)nscans * 24))) return rc;
     return run_pipeline(
-        m, nscans, res,
+        m, nscans, (size_t)total * 8, res,
         [&](int s0, int s1, cudaStream_t cs) -> int {
             int64_t p0 = offsets[s0], p1 = offsets[s1];
             if (p1 > p0)
@@ -783,7 +788,7 @@ int ndt2d_align_batch_ranges(ndt2d_matcher *m, const void *ranges, int ranges_ar
     if ((rc = upload(m, m->b_init, init, (size_t)nscans * 24))) return rc;
     if ((rc = ensure_beams(m, nbeams, angle_min, angle_inc))) return rc; // on the main stream, before the work streams fork
     return run_pipeline(
-        m, nscans, res,
+        m, nscans, (size_t)nscans * nbeams * esz, res,
         [&](int s0, int s1, cudaStream_t cs) -> int {
             CK(m, cudaMemcpyAsync(m->b_ranges.as<unsigned char>() + (size_t)s0 * nbeams * esz,
                                   reinterpret_cast<const unsigned char *>(ranges) + (size_t)s0 * nbeams * esz,
