@@ -7,6 +7,7 @@
 // Build: g++ -std=c++17 -Iinclude examples/slam_frontend.cpp -Lgtsam_ndt_b200 -lndt2d -Wl,-rpath,$PWD/gtsam_ndt_b200
 // Run:   examples/slam_frontend [out.g2o]
 // Reference front end replaced: none citable (/root/reference/README.md:1 is the whole mount).
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -111,6 +112,7 @@ int main(int argc, char **argv)
         ndt2d::Pose2d prior{};
         double worst_rel = 0;
         int bad = 0;
+        const auto t_odo = std::chrono::steady_clock::now();
         for (int k = 1; k <= N; ++k) {
             ndt.setTarget(scans[k - 1]);
             ndt2d::Result r = ndt.align(scans[k], prior);
@@ -121,6 +123,7 @@ int main(int argc, char **argv)
             ndt2d::Pose2d t = between(truth[k - 1], truth[k]);
             worst_rel = std::fmax(worst_rel, std::hypot(t.x - prior.x, t.y - prior.y));
         }
+        const double odo_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_odo).count();
         double drift = std::hypot(est[N].x - truth[N].x, est[N].y - truth[N].y);
 
         // 2. loop closure: the last scan against the first; the search lattice is centred on the drifted estimate
@@ -134,7 +137,9 @@ int main(int argc, char **argv)
                     hyp.push_back(static_cast<float>(guess.y + 0.1 * iy));
                     hyp.push_back(static_cast<float>(guess.theta + 0.02 * it));
                 }
+        const auto t_loop = std::chrono::steady_clock::now();
         std::vector<ndt2d::Result> refined = ndt.relocalize(scans[N], hyp, 4, 1);   // sweep on the 1 m level, refine the 4 best
+        const double loop_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop).count();
         const ndt2d::Result *best = nullptr;
         for (const ndt2d::Result &r : refined)
             if (r.status == NDT2D_CONVERGED && (!best || r.score > best->score)) best = &r;
@@ -157,6 +162,8 @@ int main(int argc, char **argv)
         std::printf("odometry: %d edges, %d not converged, worst relative error %.4f m, dead-reckoning drift %.4f m after %d poses\n", N, bad,
                     worst_rel, drift, N);
         std::printf("loop closure 0-%d: %s, error vs truth %.4f m\n", N, best ? "accepted" : "none", loop_err);
+        std::printf("timing: %.3f ms per odometry step (set target scan + 3-level align, host buffers), %.3f ms for the loop-closure search "
+                    "(%zu hypotheses + 4 refinements)\n", odo_ms / N, loop_ms, hyp.size() / 3);
         std::printf("pose graph: %d vertices, %zu edges -> %s\n", N + 1, edges.size(), out_path.c_str());
         bool ok = bad == 0 && worst_rel < 0.03 && best && loop_err < 0.03;
         return ok ? 0 : 1;

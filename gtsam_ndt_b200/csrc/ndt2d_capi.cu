@@ -47,12 +47,28 @@ struct LevelMem {
     float4 *cells = nullptr;
     uint32_t *cnt = nullptr;
     unsigned long long *sums = nullptr;
+    int64_t cap = 0; // cells the three allocations can hold (plus the sentinel record)
     void release()
     {
         if (cells) cudaFree(cells);
         if (cnt) cudaFree(cnt);
         if (sums) cudaFree(sums);
         cells = nullptr; cnt = nullptr; sums = nullptr;
+        cap = 0;
+    }
+    // Grow-only: scan-to-scan odometry sets a new target of about the same size for every scan, and a
+    // cudaFree/cudaMalloc pair per level and call costs more than building the grid.
+    cudaError_t ensure(int64_t nc)
+    {
+        if (nc <= cap) return cudaSuccess;
+        release();
+        const int64_t want = nc + nc / 4 + 1024;
+        cudaError_t e = cudaMalloc(&cells, (size_t)(want + 1) * 32);
+        if (e == cudaSuccess) e = cudaMalloc(&cnt, (size_t)want * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&sums, (size_t)want * 40);
+        if (e != cudaSuccess) { release(); return e; }
+        cap = want;
+        return cudaSuccess;
     }
 };
 
@@ -127,10 +143,11 @@ struct DeviceGuard {
     }
 };
 
-void drop_target(ndt2d_matcher *m)
+// forget the target; keep_memory: the per-level allocations stay for the next target (set_target after set_target)
+void drop_target(ndt2d_matcher *m, bool keep_memory = false)
 {
     for (int l = 0; l < NDT2D_MAX_LEVELS; ++l) {
-        m->mem[l].release();
+        if (!keep_memory) m->mem[l].release();
         m->lv[l] = LevelDev{};
     }
     m->has_target = false;
@@ -166,11 +183,8 @@ int setup_level(ndt2d_matcher *m, int l, const float bbox[4])
     int64_t nc = (int64_t)L.njx * L.njy;
     if (nc >= (int64_t)1 << 31) return fail(m, NDT2D_EINVAL, "level %d: %lld cells exceed 2^31", l, (long long)nc);
     LevelMem &M = m->mem[l];
-    M.release();
+    CK(m, M.ensure(nc));
     // one extra all-zero record after the table: the gather target of points outside the lattice (never written again)
-    CK(m, cudaMalloc(&M.cells, (size_t)(nc + 1) * 32));
-    CK(m, cudaMalloc(&M.cnt, (size_t)nc * 4));
-    CK(m, cudaMalloc(&M.sums, (size_t)nc * 40));
     CK(m, cudaMemsetAsync(M.cells, 0, (size_t)(nc + 1) * 32, m->cfg.stream));
     CK(m, cudaMemsetAsync(M.cnt, 0, (size_t)nc * 4, m->cfg.stream));
     CK(m, cudaMemsetAsync(M.sums, 0, (size_t)nc * 40, m->cfg.stream));
@@ -473,7 +487,7 @@ int ndt2d_set_target_device(ndt2d_matcher *m, const float *d_xy, int64_t n)
     if (!m || n < 0 || (n > 0 && !d_xy)) return m ? fail(m, NDT2D_EINVAL, "bad target arguments") : NDT2D_EINVAL;
     DeviceGuard g(m->device);
     CK(m, cudaStreamSynchronize(m->cfg.stream));
-    drop_target(m);
+    drop_target(m, /*keep_memory=*/true);
     float bbox[4] = {0, 0, 0, 0};
     if (!m->explicit_grid) {
         int box[4];
