@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=None, help="timed steps (default 10; 50 for --workload sweep, whose steps are 0.3-2 ms)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="scan2map", choices=["scan2map", "pyramid", "sweep"],
+    ap.add_argument("--workload", default="scan2map", choices=["scan2map", "pyramid", "sweep", "build"],
                     help="scan2map: BASELINE configs[1] (default, the metric's config); pyramid: configs[2] (2.0/1.0/0.5 m, "
                          "10k scans, 0.2 m / 3 deg prior error); sweep: configs[3] (1M hypotheses x one 1080-pt scan)")
     ap.add_argument("--hyps", type=int, default=1000000, help="sweep: total hypotheses (sharded across GPUs)")
@@ -60,7 +60,8 @@ def parse_args():
     ap.add_argument("--ref-scans", type=int, default=0, help="scans per step of the reference arm (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
-    dflt = {"scan2map": (65536, [0.25], [0.03, 0.3]), "pyramid": (10000, [2.0, 1.0, 0.5], [0.2, 3.0]), "sweep": (1, [0.25], [0.0, 0.0])}[a.workload]
+    dflt = {"scan2map": (65536, [0.25], [0.03, 0.3]), "pyramid": (10000, [2.0, 1.0, 0.5], [0.2, 3.0]), "sweep": (1, [0.25], [0.0, 0.0]),
+            "build": (1, [0.25], [0.0, 0.0])}[a.workload]
     a.scans = a.scans or dflt[0]
     if a.steps is None:
         a.steps = 50 if a.workload == "sweep" else 10
@@ -389,6 +390,75 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+def run_build(args):
+    """north_star stage (1), the cell-grid build: `--map-scans` x 1080 map points binned into the 200 x 200 m lattice
+    (integer accumulation with warp-level segmented reduction, then per-cell finalisation). One step = one
+    ndt2d_set_target_device on device-resident points; single GPU (every rank builds its own replica of the map)."""
+    import torch
+    import gtsam_ndt_b200 as g
+    from gtsam_ndt_b200 import synth
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the NDT path has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    K = 4 if args.overlap else 1
+    sc = synth.SCAN_1080
+    map_xy = synth.make_map(args.map_scans, traj_len=args.map_scans, **sc)
+    stream = torch.cuda.current_stream()
+    m = g.NdtMatcher2D(args.res, device=local, stream=stream.cuda_stream, overlap=args.overlap)
+    m.set_grid(-100.0, -100.0, 200.0, 200.0)
+    # rotate through copies of the point cloud totalling more than the 126 MB L2 (timing rule: inputs not L2-resident)
+    nrot = max(2, int(math.ceil(160e6 / (map_xy.nbytes))))
+    d_maps = [torch.from_numpy(map_xy).to(dev) for _ in range(nrot)]
+    for i in range(args.warmup):
+        m.set_target_device(d_maps[i % nrot], len(map_xy))
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = m.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        m.set_target_device(d_maps[i % nrot], len(map_xy))
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = m.kernel_launches - l0
+    # e2e: host points through ndt2d_set_target (pinned memory, copy in the timed region, host-synchronous)
+    h_map = torch.from_numpy(map_xy).pin_memory()
+    m.set_target(h_map.numpy())
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.set_target(h_map.numpy())
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.stop()
+    ncells = sum(m.geometry(lv)["njx"] * m.geometry(lv)["njy"] for lv in range(len(args.res)))
+    valid = int((m.cells(len(args.res) - 1)[..., 7] != 0).sum())
+    # algorithmic bytes of one build: every point read once per level; every cell's count and five sums cleared, then
+    # read and written once by the atomics' read-modify-write at least, read by the finalisation; every record written
+    per_build = len(args.res) * len(map_xy) * 8 + ncells * (44 + 2 * 44 + 44 + 32)
+    hbm, peak_src = peaks()
+    achieved = per_build / (ms / 1e3) / 1e9
+    line = {"metric": "NDT map points binned/sec (cell-grid build)", "value": len(map_xy) / (ms / 1e3), "unit": "points/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "i64 fixed-point sums, f64 finalisation, f32 records", "data": "synthetic",
+            "config": {"workload": "north_star stage 1: cell-grid build, %d map points into the 200x200 m lattice at %s m cells (K=%d): %d cells, %d valid on the finest level"
+                                   % (len(map_xy), "/".join(str(r) for r in args.res), K, ncells, valid),
+                       "l2": "steps rotate through %d copies of the point cloud (%.0f MB > 126 MB L2)" % (nrot, nrot * map_xy.nbytes / 1e6),
+                       "parallelism": "replicas only (each rank builds its own copy of the map)"},
+            "e2e": {"value": len(map_xy) / (e2e_ms / 1e3), "unit": "points/s", "h2d_bytes_per_step": int(map_xy.nbytes), "d2h_bytes_per_step": 0,
+                    "ms_per_step": e2e_ms, "api": "ndt2d_set_target"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "kernel": "k_accumulate + k_finalize (+ 3 clears) per level", "peak_source": peak_src, "bytes_per_build": per_build,
+                         "convention": "points 8 B per level; per cell: clear 44 B, atomic read-modify-write 88 B, finalise read 44 B, record 32 B"},
+            "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
 def run_sweep(args):
     """BASELINE configs[3]: relocalisation, `--hyps` pose hypotheses x one 1080-pt scan vs the global map, hypotheses
     sharded across the GPUs, best-hypothesis combine as the only collective. One step = one full sweep + combine."""
@@ -582,5 +652,7 @@ if __name__ == "__main__":
         run_reference(a)
     elif a.workload == "sweep":
         run_sweep(a)
+    elif a.workload == "build":
+        run_build(a)
     else:
         run_native(a)
