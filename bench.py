@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=None, help="timed steps (default 10; 50 for --workload sweep, whose steps are 0.3-2 ms)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="scan2map", choices=["scan2map", "pyramid", "sweep", "build"],
+    ap.add_argument("--workload", default="scan2map", choices=["scan2map", "pyramid", "sweep", "build", "newton"],
                     help="scan2map: BASELINE configs[1] (default, the metric's config); pyramid: configs[2] (2.0/1.0/0.5 m, "
                          "10k scans, 0.2 m / 3 deg prior error); sweep: configs[3] (1M hypotheses x one 1080-pt scan)")
     ap.add_argument("--hyps", type=int, default=1000000, help="sweep: total hypotheses (sharded across GPUs)")
@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     dflt = {"scan2map": (65536, [0.25], [0.03, 0.3]), "pyramid": (10000, [2.0, 1.0, 0.5], [0.2, 3.0]), "sweep": (1, [0.25], [0.0, 0.0]),
-            "build": (1, [0.25], [0.0, 0.0])}[a.workload]
+            "build": (1, [0.25], [0.0, 0.0]), "newton": (1, [0.25], [0.0, 0.0])}[a.workload]
     a.scans = a.scans or dflt[0]
     if a.steps is None:
         a.steps = 50 if a.workload == "sweep" else 10
@@ -459,6 +459,82 @@ def run_build(args):
     print(json.dumps(line), flush=True)
 
 
+def run_newton(args):
+    """north_star stage (2) in isolation: the Newton-step evaluation (score, 3-gradient, 3x3 Hessian) of one 1080-point
+    scan at `--hyps` poses scattered like LM iterates around the true pose (k_eval_poses<FULL>, ndt2d_evaluate_device).
+    This is SURVEY.md 8(d)'s unit of work with no solver and no iteration control around it. Single GPU."""
+    import torch
+    import gtsam_ndt_b200 as g
+    from gtsam_ndt_b200 import synth
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the NDT path has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    K = 4 if args.overlap else 1
+    sc = synth.SCAN_1080
+    map_xy = synth.make_map(args.map_scans, traj_len=args.map_scans, **sc)
+    ranges, poses = synth.scans(1, traj_len=1000, first=137, **sc)
+    xy = synth.polar_to_points(ranges[0], sc["angle_min"], sc["angle_inc"])
+    npose = args.hyps
+    rng = np.random.default_rng(7)
+    P = poses[0] + rng.normal(size=(npose, 3)) * np.array([0.03, 0.03, math.radians(0.3)])
+    stream = torch.cuda.current_stream()
+    m = g.NdtMatcher2D(args.res, device=local, stream=stream.cuda_stream, overlap=args.overlap)
+    m.set_grid(-100.0, -100.0, 200.0, 200.0)
+    m.set_target(map_xy)
+    d_xy = torch.from_numpy(xy).to(dev)
+    nrot = max(2, int(math.ceil(160e6 / (npose * (24 + 80 + 4)))))      # poses in, sums and counts out: rotate beyond the L2
+    d_P = [torch.from_numpy(P).to(dev) for _ in range(nrot)]
+    d_out = [torch.zeros(npose * 10, dtype=torch.float64, device=dev) for _ in range(nrot)]
+    d_cnt = [torch.zeros(npose, dtype=torch.int32, device=dev) for _ in range(nrot)]
+    for i in range(args.warmup):
+        m.evaluate_device(d_xy, len(xy), d_P[i % nrot], npose, d_out[i % nrot], d_cnt[i % nrot])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = m.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        m.evaluate_device(d_xy, len(xy), d_P[i % nrot], npose, d_out[i % nrot], d_cnt[i % nrot])
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = m.kernel_launches - l0
+    # e2e: host poses in, host sums out, through ndt2d_evaluate (pinned memory, copies in the timed region)
+    h_P = torch.from_numpy(P).pin_memory()
+    m.evaluate(xy, h_P.numpy())
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 5)):
+        out, cnt = m.evaluate(xy, h_P.numpy())
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / max(1, args.steps // 5)
+    clocks = sampler.stop()
+    dev_out = d_out[(args.steps - 1) % nrot].cpu().numpy().reshape(npose, 10)
+    per_eval = eval_bytes(len(xy), K)
+    hbm, peak_src = peaks()
+    achieved = npose * per_eval / (ms / 1e3) / 1e9
+    line = {"metric": "NDT Newton-step evaluations/sec (1080-pt scan: score, gradient, Hessian)", "value": npose / (ms / 1e3), "unit": "evaluations/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 per point, f64 sums", "data": "synthetic",
+            "config": {"workload": "north_star stage 2: Newton-step kernel alone, one %d-pt scan at %d poses (sigma 3 cm / 0.3 deg around the truth) vs 200x200 m map at %s m cells (K=%d)"
+                                   % (len(xy), npose, args.res[0], K),
+                       "l2": "steps rotate through %d copies of the pose and result buffers (%.0f MB > 126 MB L2); the scan and the cell table are cache-resident by design"
+                             % (nrot, nrot * npose * 108 / 1e6),
+                       "parallelism": "replicas only"},
+            "e2e": {"value": npose / (e2e_ms / 1e3), "unit": "evaluations/s", "h2d_bytes_per_step": int(npose * 24 + len(xy) * 8),
+                    "d2h_bytes_per_step": int(npose * 84), "ms_per_step": e2e_ms, "api": "ndt2d_evaluate",
+                    "equals_device_run": bool(np.array_equal(out, dev_out))},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "kernel": "k_eval_poses<FULL> (one warp per pose, scan staged per block)", "peak_source": peak_src, "bytes_per_eval": per_eval,
+                         "convention": "gather traffic (DESIGN.md section 4): every point read and 32 B record gather counts; scan and cells are cache-resident"},
+            "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
 def run_sweep(args):
     """BASELINE configs[3]: relocalisation, `--hyps` pose hypotheses x one 1080-pt scan vs the global map, hypotheses
     sharded across the GPUs, best-hypothesis combine as the only collective. One step = one full sweep + combine."""
@@ -654,5 +730,7 @@ if __name__ == "__main__":
         run_sweep(a)
     elif a.workload == "build":
         run_build(a)
+    elif a.workload == "newton":
+        run_newton(a)
     else:
         run_native(a)

@@ -162,11 +162,12 @@ static constexpr int EVAL_THREADS = 256;
 #define NDT2D_QUEUE 0 // 0: one global atomic work queue; 1: static per-block ranges (tuning experiment, slower)
 #endif
 static constexpr int EVAL_PIPE = NDT2D_EVAL_PIPE;
+static constexpr int EVAL_BLOCKS_FULL = 3; // the full evaluation needs the align kernel's 80 registers: 24 warps per SM
 
 // Block stages the scan in shared memory once (coalesced float2 loads), then each warp takes poses
 // from a grid-stride loop. FULL: ten f64 sums per pose; otherwise the score only (sweep).
 template <int OV, bool FULL, bool F32POSE, bool STAGED>
-__global__ void __launch_bounds__(EVAL_THREADS, NDT2D_EVAL_BLOCKS) k_eval_poses(const LevelDev L, const float2 *__restrict__ xy, int n,
+__global__ void __launch_bounds__(EVAL_THREADS, FULL ? EVAL_BLOCKS_FULL : NDT2D_EVAL_BLOCKS) k_eval_poses(const LevelDev L, const float2 *__restrict__ xy, int n,
                                                                const void *__restrict__ poses, int64_t npose,
                                                                double *__restrict__ out, int out_stride,
                                                                int32_t *__restrict__ count)
@@ -192,17 +193,12 @@ __global__ void __launch_bounds__(EVAL_THREADS, NDT2D_EVAL_BLOCKS) k_eval_poses(
         }
         Pose32 q = pose_to_f32(tx, ty, th);
         Eval E;
-        if (STAGED) eval_warp<OV, FULL, true, OV == 0 ? EVAL_PIPE : 0>(L, sp, n, q, lane, E);
-        else eval_warp<OV, FULL, false, 0>(L, xy, n, q, lane, E);
-        if (lane == 0) {
-            if (FULL) {
-#pragma unroll
-                for (int t = 0; t < 10; ++t) out[(size_t)j * out_stride + t] = E.v[t];
-            } else {
-                out[(size_t)j * out_stride] = E.v[0];
-            }
-            if (count) count[j] = E.count;
-        }
+        // FULL: the transposed reduction leaves sum number E.slot in every lane (lanes with the same slot hold the same bits)
+        if (STAGED) eval_warp<OV, FULL, true, OV == 0 ? EVAL_PIPE : 0, FULL>(L, sp, n, q, lane, E);
+        else eval_warp<OV, FULL, false, 0, FULL>(L, xy, n, q, lane, E);
+        if (FULL) out[(size_t)j * out_stride + E.slot] = E.v[0];
+        else if (lane == 0) out[(size_t)j * out_stride] = E.v[0];
+        if (count && lane == 0) count[j] = E.count;
     }
 }
 
@@ -564,7 +560,7 @@ static cudaError_t launch_eval_t(const LaunchCfg &c, const LevelDev &L, const fl
                                  int64_t npose, double *d_out, int out_stride, int32_t *d_count)
 {
     size_t smem = (size_t)((n + 63) & ~63) * sizeof(float2);
-    int grid = grid_for(npose, EVAL_THREADS / 32, c.sm_count, NDT2D_EVAL_BLOCKS);
+    int grid = grid_for(npose, EVAL_THREADS / 32, c.sm_count, FULL ? EVAL_BLOCKS_FULL : NDT2D_EVAL_BLOCKS);
     if (smem <= (size_t)c.max_smem_optin - 1024) {
         auto kern = k_eval_poses<OV, FULL, F32POSE, true>;
         if (smem > 48 * 1024) {
