@@ -159,6 +159,21 @@ def ncu_traffic(kernel, args, scans):
         return None
 
 
+def gather_pipe(kernel_key, kernel_ms, clocks, sm_count):
+    """The path's real ceiling next to the HBM figure: an SM's L1TEX data pipe takes one cycle per distinct 32 B sector of
+    a gather. Sector count per launch from the committed ncu capture of this configuration."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        sectors = tab[kernel_key]["l1tex_sectors"]
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        peak = sm_count * mhz * 1e6
+        ach = sectors / (kernel_ms / 1e3)
+        return {"sectors_per_launch": sectors, "achieved_sectors_per_s": ach, "peak_sectors_per_s": peak, "frac": ach / peak,
+                "note": "l1tex__t_sectors_pipe_lsu_mem_global_op_ld from the ncu capture; peak = SMs x SM clock (one sector per cycle per SM)"}
+    except Exception:
+        return None
+
+
 def ncu_traffic_sweep(args, hyps):
     try:
         tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -368,7 +383,9 @@ def run_native(args):
                          "convention": "gather traffic: every point read and 32 B cell gather counts, bytes/eval = N*(8+32K)+92; "
                                        "cells are served by L1/L2, so this is not DRAM utilisation",
                          "evals_per_launch": float(iters.sum()), "bytes_per_eval": eval_bytes(npts, K),
-                         "evals_per_s": total_evals_per_step * args.steps / (ms / 1e3)},
+                         "evals_per_s": total_evals_per_step * args.steps / (ms / 1e3),
+                         "gather_pipe": gather_pipe("k_align/%s/scans=%d/res=%s/K=%d" % (args.workload, B, "-".join(str(r) for r in args.res), K),
+                                                    kernel_ms, clocks, torch.cuda.get_device_properties(local).multi_processor_count)},
             "mean_iterations": float(iters.mean()), "status_counts": np.bincount(res["status"], minlength=4).tolist(),
             "map_build_ms": build_ms, "clocks": clocks,
         }
@@ -682,6 +699,8 @@ def run_sweep(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                              "traffic": ncu_traffic_sweep(args, len(hyp)) if world == 1 else None,
                              "kernel": "k_eval_poses (score only)", "peak_source": peak_src, "bytes_per_hypothesis": per_hyp,
+                             "gather_pipe": gather_pipe("k_eval_poses/sweep/hyps=%d/res=%s/K=%d" % (len(hyp), "-".join(str(r) for r in args.res), K),
+                                                        kernel_ms, clocks, torch.cuda.get_device_properties(local).multi_processor_count) if world == 1 else None,
                              "convention": "gather traffic (see DESIGN.md section 4); scan and cells are cache-resident"},
                 "best_hypothesis_abs_err_vs_truth": truth_err, "clocks": clocks}
         if ex is not None and state["best"] is not None:
