@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=None, help="timed steps (default 10; 50 for --workload sweep, whose steps are 0.3-2 ms)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="scan2map", choices=["scan2map", "pyramid", "sweep", "build", "newton"],
+    ap.add_argument("--workload", default="scan2map", choices=["scan2map", "pyramid", "sweep", "build", "newton", "odometry"],
                     help="scan2map: BASELINE configs[1] (default, the metric's config); pyramid: configs[2] (2.0/1.0/0.5 m, "
                          "10k scans, 0.2 m / 3 deg prior error); sweep: configs[3] (1M hypotheses x one 1080-pt scan)")
     ap.add_argument("--hyps", type=int, default=1000000, help="sweep: total hypotheses (sharded across GPUs)")
@@ -61,7 +61,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     dflt = {"scan2map": (65536, [0.25], [0.03, 0.3]), "pyramid": (10000, [2.0, 1.0, 0.5], [0.2, 3.0]), "sweep": (1, [0.25], [0.0, 0.0]),
-            "build": (1, [0.25], [0.0, 0.0]), "newton": (1, [0.25], [0.0, 0.0])}[a.workload]
+            "build": (1, [0.25], [0.0, 0.0]), "newton": (1, [0.25], [0.0, 0.0]),
+            "odometry": (16384, [0.5], [0.02, 0.2])}[a.workload]
     a.scans = a.scans or dflt[0]
     if a.steps is None:
         a.steps = 50 if a.workload == "sweep" else 10
@@ -476,6 +477,100 @@ def run_build(args):
     print(json.dumps(line), flush=True)
 
 
+def run_odometry(args):
+    """Batched scan-to-scan odometry (ndt2d_align_pairs): `--scans` consecutive 1080-beam scans of the trajectory, pair
+    k = (scan k-1 as target, scan k as source), prior = true relative motion + `--perturb`. One step = every target's
+    grid built (one warp per target and level, hash tables) + every pair aligned. BASELINE configs[0] is the single
+    CPU case of this align (scan-to-scan, 0.5 m cells); the batched form is what a log or a set of loop-closure
+    candidates needs. Single GPU (pairs would shard like scans)."""
+    import torch
+    import gtsam_ndt_b200 as g
+    from gtsam_ndt_b200 import synth
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the NDT path has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    K = 4 if args.overlap else 1
+    sc = synth.SCAN_1080
+    n = args.scans
+    ranges, poses = synth.scans(n, traj_len=3770, first=0, step=1, **sc)      # the 377 m loop in 0.1 m steps (laps repeat with new noise)
+    xy, offsets = to_points(ranges)
+    pairs = np.stack([np.arange(n - 1), np.arange(1, n)], 1).astype(np.int32)
+    c, s_ = np.cos(poses[:-1, 2]), np.sin(poses[:-1, 2])
+    d = poses[1:] - poses[:-1]
+    rel = np.stack([c * d[:, 0] + s_ * d[:, 1], -s_ * d[:, 0] + c * d[:, 1], d[:, 2]], 1)
+    init = rel + synth.uniform3(n - 1) * np.array([args.perturb[0], args.perturb[0], math.radians(args.perturb[1])])
+    stream = torch.cuda.current_stream()
+    m = g.NdtMatcher2D(args.res, device=local, stream=stream.cuda_stream, overlap=args.overlap)
+    d_xy = torch.from_numpy(xy).to(dev)
+    d_off = torch.from_numpy(offsets).to(dev)
+    d_init = torch.from_numpy(np.ascontiguousarray(init)).to(dev)
+    d_res = torch.zeros((n - 1) * 144, dtype=torch.uint8, device=dev)
+    for _ in range(args.warmup):
+        m.align_pairs_device(d_xy, d_off, offsets, pairs, d_init, d_res)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = m.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        m.align_pairs_device(d_xy, d_off, offsets, pairs, d_init, d_res)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = m.kernel_launches - l0
+    res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=g.RESULT_DTYPE)
+    # e2e: pinned host scans through ndt2d_align_pairs, copies and result read-back in the timed region
+    h_xy = torch.from_numpy(xy).pin_memory()
+    m.align_pairs(h_xy.numpy(), offsets, pairs, init)
+    t0 = time.perf_counter()
+    reps = max(1, args.steps // 2)
+    for _ in range(reps):
+        rh = m.align_pairs(h_xy.numpy(), offsets, pairs, init)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
+    clocks = sampler.stop()
+    # the same pairs one at a time through set_target + align (what a front end without the batched call does)
+    t0 = time.perf_counter()
+    nseq = min(256, n - 1)
+    scans_list = xy.reshape(n, -1, 2)
+    same = True
+    for p in range(nseq):
+        m.set_target(scans_list[pairs[p, 0]])
+        one = m.align(scans_list[pairs[p, 1]], init[p])
+        same = same and one.tobytes() == res[p].tobytes()
+    seq_ms = (time.perf_counter() - t0) * 1e3 / nseq
+    err = res["pose"] - rel
+    good = res["status"] == 0
+    iters = res["iterations"].astype(np.int64)
+    hbm, peak_src = peaks()
+    alg_bytes = float(iters.sum()) * eval_bytes(1080, K)
+    achieved = alg_bytes / (ms / 1e3) / 1e9
+    line = {"metric": "NDT scan-to-scan matches/sec (1080-pt 2D scans, batched pairs)", "value": (n - 1) / (ms / 1e3), "unit": "matches/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 per point, f64 sums and solver", "data": "synthetic",
+            "config": {"workload": "batched scan-to-scan odometry: %d consecutive 1080-beam scans 0.1 m apart, pair k = (scan k-1 -> scan k), %s m cells (K=%d), "
+                                   "per-target grids in hash tables, prior error %.2f m / %.1f deg" % (n, "/".join(str(r) for r in args.res), K, args.perturb[0], args.perturb[1]),
+                       "l2": "per-step scan input %.0f MB; per-target tables %.1f GB are rebuilt every step" % (xy.nbytes / 1e6, (n - 1) * len(args.res) * 4097 * 76 / 1e9),
+                       "parallelism": "replicas only in this bench (pairs shard like scans)"},
+            "e2e": {"value": (n - 1) / (e2e_ms / 1e3), "unit": "matches/s", "h2d_bytes_per_step": int(xy.nbytes + offsets.nbytes + init.nbytes),
+                    "d2h_bytes_per_step": int((n - 1) * 144), "ms_per_step": e2e_ms, "api": "ndt2d_align_pairs",
+                    "equals_device_run": bool(rh.tobytes() == res.tobytes())},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "kernel": "k_align<PAIRS> (hash-table gathers) after k_pairs_build", "peak_source": peak_src,
+                         "bytes_per_eval": eval_bytes(1080, K), "evals_per_launch": float(iters.sum()),
+                         "convention": "gather traffic (DESIGN.md section 4); the build's traffic is not counted"},
+            "mean_iterations": float(iters.mean()), "status_counts": np.bincount(res["status"], minlength=4).tolist(),
+            "median_abs_err_vs_truth_m": float(np.median(np.abs(err[good, :2]))) if good.any() else None,
+            "sequential_set_target_plus_align": {"ms_per_pair": seq_ms, "pairs": nseq, "bit_identical_to_batched": bool(same)},
+            "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
 def run_newton(args):
     """north_star stage (2) in isolation: the Newton-step evaluation (score, 3-gradient, 3x3 Hessian) of one 1080-point
     scan at `--hyps` poses scattered like LM iterates around the true pose (k_eval_poses<FULL>, ndt2d_evaluate_device).
@@ -751,5 +846,7 @@ if __name__ == "__main__":
         run_build(a)
     elif a.workload == "newton":
         run_newton(a)
+    elif a.workload == "odometry":
+        run_odometry(a)
     else:
         run_native(a)

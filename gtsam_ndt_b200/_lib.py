@@ -55,6 +55,8 @@ SIGNATURES = {
                                            C.c_float, C.c_float, _V, _V]),
     "ndt2d_align_batch_ranges_device": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_float,
                                                   C.c_float, C.c_float, _V, _V]),
+    "ndt2d_align_pairs": (C.c_int, [_V, _V, _V, C.c_int, _V, C.c_int, _V, _V]),
+    "ndt2d_align_pairs_device": (C.c_int, [_V, _V, _V, _V, C.c_int, _V, C.c_int, _V, _V]),
     "ndt2d_sweep": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, C.c_int64, _V, C.c_int, _V, _V]),
     "ndt2d_sweep_device": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, C.c_int64, _V, C.c_int, _V, _V]),
     "ndt2d_relocalize": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, C.c_int64, C.c_int, _V, _V]),

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -88,7 +89,7 @@ struct ndt2d_matcher {
     LevelDev lv[NDT2D_MAX_LEVELS]{};
     LevelMem mem[NDT2D_MAX_LEVELS];
     DevBuf b_xy, b_off, b_init, b_res, b_pose, b_out, b_cnt, b_idx, b_terms, b_hyp, b_scores, b_tki, b_tkv, b_scratch,
-        b_counter, b_beams, b_ranges, b_box;
+        b_counter, b_beams, b_ranges, b_box, b_ptab, b_pcnt, b_psums, b_pgeo, b_ptargets, b_ppairs, b_perr;
     double beams_amin = 0, beams_ainc = 0;
     int beams_n = 0;
     // host-buffer batch calls are cut into chunks: chunk i+1 is copied on copy_stream while chunk i computes
@@ -400,7 +401,7 @@ void ndt2d_destroy(ndt2d_matcher *m)
     ndt2d_exchange_close(m);
     DevBuf *bufs[] = {&m->b_xy, &m->b_off, &m->b_init, &m->b_res, &m->b_pose, &m->b_out, &m->b_cnt, &m->b_idx, &m->b_terms,
                       &m->b_hyp, &m->b_scores, &m->b_tki, &m->b_tkv, &m->b_scratch, &m->b_counter, &m->b_beams, &m->b_ranges,
-                      &m->b_box};
+                      &m->b_box, &m->b_ptab, &m->b_pcnt, &m->b_psums, &m->b_pgeo, &m->b_ptargets, &m->b_ppairs, &m->b_perr};
     for (DevBuf *b : bufs) b->release();
     if (m->copy_stream) {
         cudaStreamSynchronize(m->copy_stream);
@@ -856,6 +857,162 @@ int ndt2d_sweep(ndt2d_matcher *m, int level, const float *xy, int n, const float
         CK(m, cudaMemcpyAsync(best_score, m->b_tkv.p, (size_t)k * 8, cudaMemcpyDeviceToHost, m->cfg.stream));
     }
     return ndt2d_synchronize(m);
+}
+
+// ---- batched scan-to-scan (north_star stage 3, "batched multi-scan"): many (target scan, source scan) pairs per call ----
+
+static unsigned next_pow2(unsigned v)
+{
+    unsigned p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// d_xy / d_offsets / d_init / d_res: device; h_offsets / pairs: host (the chunking and the target list are host work).
+// One chunk = as many pairs as fit the table budget. Asynchronous on the handle's stream apart from the uploads of the
+// small per-chunk index lists; *err_out (optional) receives the device error flag after a synchronisation.
+static int align_pairs_impl(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, const int64_t *h_offsets, int nscans,
+                            const int32_t *pairs, int npairs, const double *d_init, ndt2d_result *d_res)
+{
+    int64_t max_src = 0, max_tgt = 0;
+    for (int p = 0; p < npairs; ++p) {
+        const int t = pairs[2 * p], s = pairs[2 * p + 1];
+        if (t < 0 || t >= nscans || s < 0 || s >= nscans) return fail(m, NDT2D_EINVAL, "pair %d: scan index out of range", p);
+        max_tgt = std::max(max_tgt, h_offsets[t + 1] - h_offsets[t]);
+        max_src = std::max(max_src, h_offsets[s + 1] - h_offsets[s]);
+    }
+    const int K = m->prm.overlap ? 4 : 1, L = m->nlevels;
+    // slots per table: 1.5 x the most cells a target can occupy (every point in cells of its own), rounded up to a power
+    // of two: at most 2/3 full in that worst case, typically a quarter (a 1080-beam scan occupies ~500 cells)
+    const uint64_t want = 3ull * (uint64_t)std::max<int64_t>(max_tgt, 16) * K / 2;
+    if (want > 65536) return fail(m, NDT2D_EINVAL, "align_pairs: target scans of %lld points need more than 65536 table slots",
+                                  (long long)max_tgt);
+    const unsigned cap = next_pow2((unsigned)want);
+    const size_t per_target = (size_t)L * (((size_t)cap + 1) * 32 + (size_t)cap * 44 + sizeof(LevelDev));
+    size_t budget = (size_t)8 << 30;
+    if (const char *e = getenv("NDT2D_PAIRS_BYTES")) budget = (size_t)strtoull(e, nullptr, 10);
+    const int tmax = (int)std::max<size_t>(1, std::min<size_t>(budget / per_target, (size_t)nscans));
+    CK(m, m->b_perr.ensure(4));
+    int rc;
+    CK(m, cudaMemsetAsync(m->b_perr.p, 0, 4, m->cfg.stream));
+    std::vector<int32_t> slot((size_t)nscans, -1), targets, resolved;
+    int p0 = 0;
+    while (p0 < npairs) {
+        // the next chunk: pairs in order until the chunk's distinct targets would exceed the budget
+        targets.clear();
+        resolved.clear();
+        int p1 = p0;
+        for (; p1 < npairs; ++p1) {
+            const int t = pairs[2 * p1];
+            if (slot[t] < 0) {
+                if ((int)targets.size() == tmax) break;
+                slot[t] = (int32_t)targets.size();
+                targets.push_back(t);
+            }
+            resolved.push_back(slot[t]);
+            resolved.push_back(pairs[2 * p1 + 1]);
+        }
+        const size_t T = targets.size(), TL = T * (size_t)L;
+        CK(m, m->b_ptab.ensure(TL * ((size_t)cap + 1) * 32));
+        // the accumulators are zero between builds (every finalisation zeroes what it consumed): clear them when they are (re)allocated
+        if (m->b_pcnt.cap < TL * cap * 4 || m->b_psums.cap < TL * cap * 40) {
+            CK(m, cudaStreamSynchronize(m->cfg.stream));
+            CK(m, m->b_pcnt.ensure(TL * cap * 4));
+            CK(m, m->b_psums.ensure(TL * cap * 40));
+            CK(m, cudaMemsetAsync(m->b_pcnt.p, 0, m->b_pcnt.cap, m->cfg.stream));
+            CK(m, cudaMemsetAsync(m->b_psums.p, 0, m->b_psums.cap, m->cfg.stream));
+        }
+        CK(m, m->b_pgeo.ensure(TL * sizeof(LevelDev)));
+        if ((rc = upload(m, m->b_ptargets, targets.data(), T * 4))) return rc;
+        if ((rc = upload(m, m->b_ppairs, resolved.data(), resolved.size() * 4))) return rc;
+        CK(m, cudaStreamSynchronize(m->cfg.stream)); // the vectors are reused by the next chunk
+        PairBuildArgs b;
+        memset(&b, 0, sizeof(b));
+        b.xy = reinterpret_cast<const float2 *>(d_xy);
+        b.offsets = d_offsets;
+        b.targets = m->b_ptargets.as<int32_t>();
+        b.ntargets = (int)T; b.nlevels = L; b.ov = m->prm.overlap; b.explicit_grid = m->explicit_grid ? 1 : 0;
+        for (int l = 0; l < L; ++l) b.res[l] = m->res[l];
+        b.gox = m->gox; b.goy = m->goy; b.gex = m->gex; b.gey = m->gey;
+        b.min_points = m->prm.min_points; b.eig_ratio = m->prm.eig_ratio;
+        b.cap = cap;
+        b.tab = m->b_ptab.as<float4>(); b.cnt = m->b_pcnt.as<uint32_t>(); b.sums = m->b_psums.as<unsigned long long>();
+        b.geo = m->b_pgeo.as<LevelDev>();
+        b.error = m->b_perr.as<int>();
+        CK(m, launch_pairs_build(m->cfg, b, &m->launches));
+        AlignArgs a;
+        fill_align_args(m, a);
+        a.xy = reinterpret_cast<const float2 *>(d_xy);
+        if (!a.xy) a.xy = m->b_counter.as<float2>();
+        a.offsets = d_offsets;
+        a.pairs = m->b_ppairs.as<int32_t>();
+        a.geo = m->b_pgeo.as<LevelDev>();
+        a.init = d_init + 3 * (size_t)p0;
+        a.res = d_res + p0;
+        a.nscans = p1 - p0;
+        a.cap_points = align_cap_points(m, (int)max_src);
+        CK(m, launch_align(m->cfg, a, &m->launches));
+        for (int32_t t : targets) slot[t] = -1;
+        p0 = p1;
+    }
+    return NDT2D_OK;
+}
+
+static int align_pairs_check(ndt2d_matcher *m)
+{
+    int err = 0;
+    CK(m, cudaMemcpyAsync(&err, m->b_perr.p, 4, cudaMemcpyDeviceToHost, m->cfg.stream));
+    int rc = ndt2d_synchronize(m);
+    if (rc) return rc;
+    if (err) return fail(m, NDT2D_EINVAL, "align_pairs: the auto-fitted lattice of a target scan exceeds 2^31 cells "
+                                          "(a point far from the rest?); its pairs were returned with status NO_OVERLAP");
+    return NDT2D_OK;
+}
+
+static int align_pairs_validate(ndt2d_matcher *m, const int64_t *offsets, int nscans, const int32_t *pairs, int npairs)
+{
+    if (nscans < 0 || npairs < 0 || (nscans > 0 && !offsets) || (npairs > 0 && !pairs)) return fail(m, NDT2D_EINVAL, "bad arguments");
+    if (m->nlevels < 1) return fail(m, NDT2D_EINVAL, "no resolution set");
+    for (int b = 0; b < nscans; ++b) {
+        int64_t nb = offsets[b + 1] - offsets[b];
+        if (nb < 0 || nb > 0x7fffffff) return fail(m, NDT2D_EINVAL, "offsets not monotone at scan %d", b);
+    }
+    if (nscans > 0 && offsets[0] < 0) return fail(m, NDT2D_EINVAL, "bad offsets");
+    return NDT2D_OK;
+}
+
+int ndt2d_align_pairs_device(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, const int64_t *offsets, int nscans,
+                             const int32_t *pairs, int npairs, const double *d_init, ndt2d_result *d_res)
+{
+    if (!m) return NDT2D_EINVAL;
+    int rc = align_pairs_validate(m, offsets, nscans, pairs, npairs);
+    if (rc) return rc;
+    if (npairs == 0) return NDT2D_OK;
+    if (!d_offsets || !d_init || !d_res) return fail(m, NDT2D_EINVAL, "bad arguments");
+    DeviceGuard g(m->device);
+    return align_pairs_impl(m, d_xy, d_offsets, offsets, nscans, pairs, npairs, d_init, d_res);
+}
+
+int ndt2d_align_pairs(ndt2d_matcher *m, const float *xy, const int64_t *offsets, int nscans, const int32_t *pairs, int npairs,
+                      const double *init, ndt2d_result *res)
+{
+    if (!m) return NDT2D_EINVAL;
+    int rc = align_pairs_validate(m, offsets, nscans, pairs, npairs);
+    if (rc) return rc;
+    if (npairs == 0) return NDT2D_OK;
+    if (!init || !res) return fail(m, NDT2D_EINVAL, "bad arguments");
+    const int64_t total = offsets[nscans];
+    if (total > 0 && !xy) return fail(m, NDT2D_EINVAL, "bad offsets / xy");
+    DeviceGuard g(m->device);
+    if ((rc = upload(m, m->b_xy, xy, (size_t)total * 8))) return rc;
+    if ((rc = upload(m, m->b_off, offsets, (size_t)(nscans + 1) * 8))) return rc;
+    if ((rc = upload(m, m->b_init, init, (size_t)npairs * 24))) return rc;
+    CK(m, m->b_res.ensure((size_t)npairs * sizeof(ndt2d_result)));
+    rc = align_pairs_impl(m, m->b_xy.as<float>(), m->b_off.as<int64_t>(), offsets, nscans, pairs, npairs, m->b_init.as<double>(),
+                          m->b_res.as<ndt2d_result>());
+    if (rc) return rc;
+    CK(m, cudaMemcpyAsync(res, m->b_res.p, (size_t)npairs * sizeof(ndt2d_result), cudaMemcpyDeviceToHost, m->cfg.stream));
+    return align_pairs_check(m);
 }
 
 int ndt2d_relocalize(ndt2d_matcher *m, int level, const float *xy, int n, const float *hyp, int64_t nhyp, int k,

@@ -416,8 +416,18 @@ struct Fetched {
 struct LatticePk {
     u64 org, inv;
     unsigned nhx, nhy, njx;
-    unsigned sentinel; // index of the all-zero record that follows the njx*njy cells of the table
+    unsigned sentinel; // index of the all-zero record that follows the cells of the table
+    unsigned mask;     // hash tables only: slots - 1
 };
+
+// slot of a cell key in a per-target hash table: Fibonacci hashing, bits 15.. of the product (tables have <= 2^16 slots)
+__device__ __forceinline__ unsigned hash_slot(unsigned key, unsigned mask) { return ((key * 0x9E3779B1u) >> 15) & mask; }
+
+// The record of cell `key`: the dense table is indexed directly; a hash table is probed linearly until the key or an empty
+// slot turns up (an empty slot is an all-zero, invalid record: a cell without target points). Outside the lattice: the
+// sentinel record either way.
+template <bool HASH>
+__device__ __forceinline__ Cell4 fetch_cell(const float4 *__restrict__ cells, const LatticePk &G, bool inside, unsigned key);
 
 // SPEC 2 in integers: for a finite f, (f >= 0 && f < (float)nh) == ((unsigned)floor_to_int(f) < nh), because the
 // conversion saturates (huge -> INT_MAX, very negative -> INT_MIN) and rounds (-1, 0) down to -1; inside the
@@ -431,7 +441,24 @@ __device__ __forceinline__ bool cell_base(const LatticePk &G, u64 f, unsigned &b
     return (ix < G.nhx) && (iy < G.nhy);
 }
 
-template <int OV, bool SMEM>
+template <bool HASH>
+__device__ __forceinline__ Cell4 fetch_cell(const float4 *__restrict__ cells, const LatticePk &G, bool inside, unsigned key)
+{
+    if (!HASH) return load_cell(cells, inside ? key : G.sentinel);
+    unsigned s = inside ? hash_slot(key, G.mask) : G.sentinel;
+    Cell4 r = load_cell(cells, s);
+    if (inside) {
+        for (;;) {
+            const unsigned k = (unsigned)__float_as_int(lo32(r.nv));
+            if (k == key || k == kEmptyKey) break;
+            s = (s + 1u) & G.mask;
+            r = load_cell(cells, s);
+        }
+    }
+    return r;
+}
+
+template <int OV, bool SMEM, bool HASH = false>
 __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const LatticePk &G, const PosePk &P, const float2 *pts,
                                       int n, int i, Fetched<OV> &F)
 {
@@ -444,11 +471,44 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
     const bool inB = cell_base(G, mul2(sub2(F.B.XY, G.org), G.inv), bB);
     // K = 1: one record per point. K = 4: two rows of two adjacent records (64 contiguous bytes per row).
     // Outside the lattice: the sentinel record (all zero = invalid), so the gather needs no predicate.
+    if (!HASH) {
 #pragma unroll
-    for (int k = 0; k < Fetched<OV>::NC; ++k) {
-        const unsigned o = (k & 1) + (k >> 1) * G.njx;
-        F.cA[k] = load_cell(cells, inA ? bA + o : G.sentinel);
-        F.cB[k] = load_cell(cells, inB ? bB + o : G.sentinel);
+        for (int k = 0; k < Fetched<OV>::NC; ++k) {
+            const unsigned o = (k & 1) + (k >> 1) * G.njx;
+            F.cA[k] = fetch_cell<false>(cells, G, inA, bA + o);
+            F.cB[k] = fetch_cell<false>(cells, G, inB, bB + o);
+        }
+    } else {
+        // hash tables: the first probes of all cells go out together; only then are the (rare) collisions chased
+        unsigned sA[Fetched<OV>::NC], sB[Fetched<OV>::NC];
+#pragma unroll
+        for (int k = 0; k < Fetched<OV>::NC; ++k) {
+            const unsigned o = (k & 1) + (k >> 1) * G.njx;
+            sA[k] = inA ? hash_slot(bA + o, G.mask) : G.sentinel;
+            sB[k] = inB ? hash_slot(bB + o, G.mask) : G.sentinel;
+            F.cA[k] = load_cell(cells, sA[k]);
+            F.cB[k] = load_cell(cells, sB[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < Fetched<OV>::NC; ++k) {
+            const unsigned o = (k & 1) + (k >> 1) * G.njx;
+            if (inA) {
+                for (;;) {
+                    const unsigned key = (unsigned)__float_as_int(lo32(F.cA[k].nv));
+                    if (key == bA + o || key == kEmptyKey) break;
+                    sA[k] = (sA[k] + 1u) & G.mask;
+                    F.cA[k] = load_cell(cells, sA[k]);
+                }
+            }
+            if (inB) {
+                for (;;) {
+                    const unsigned key = (unsigned)__float_as_int(lo32(F.cB[k].nv));
+                    if (key == bB + o || key == kEmptyKey) break;
+                    sB[k] = (sB[k] + 1u) & G.mask;
+                    F.cB[k] = load_cell(cells, sB[k]);
+                }
+            }
+        }
     }
 }
 
@@ -457,7 +517,8 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
 // PIPE: software pipelining, the records of step j+1 are requested before step j is computed, so the L2 round
 // trip of the gathers overlaps this warp's own arithmetic (costs ~30 registers).
 // TR (FULL only): finish with the transposed reduction; E.v[0] is then sum number E.slot, the other E.v are unset.
-template <int OV, bool FULL, bool SMEM, int PIPE, bool TR = false>
+// HASH: L.cells is a per-target hash table (L.hash_mask), see fetch_cell().
+template <int OV, bool FULL, bool SMEM, int PIPE, bool TR = false, bool HASH = false>
 __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E)
 {
     Partials S;
@@ -470,7 +531,8 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
     const PosePk P = pose_pack(q);
     LatticePk G;
     G.org = pk(L.ox, L.oy); G.inv = bc(L.inv_st); G.nhx = (unsigned)L.nhx; G.nhy = (unsigned)L.nhy; G.njx = (unsigned)L.njx;
-    G.sentinel = (unsigned)L.njx * (unsigned)L.njy;
+    G.mask = L.hash_mask;
+    G.sentinel = HASH ? L.hash_mask + 1u : (unsigned)L.njx * (unsigned)L.njy;
     const int npad = (n + 63) & ~63;
     if (PIPE == 1 && OV == 0) {
         // Software pipeline over registers, two steps per trip: the records of the next step are requested before
@@ -481,19 +543,19 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
         int i = lane;
         if ((npad >> 6) & 1) {
             Fetched<OV> cur;
-            fetch<OV, SMEM>(cells, G, P, pts, n, i, cur);
+            fetch<OV, SMEM, HASH>(cells, G, P, pts, n, i, cur);
             accumulate_cell<FULL>(cur.cA[0], cur.cB[0], cur.A, cur.B, S, cnt);
             i += 64;
         }
         if (i < npad) {
             const int last = npad - 64 + lane;
             Fetched<OV> F0, F1;
-            fetch<OV, SMEM>(cells, G, P, pts, n, i, F0);
+            fetch<OV, SMEM, HASH>(cells, G, P, pts, n, i, F0);
 #pragma unroll 1
             for (; i < npad; i += 128) {
-                fetch<OV, SMEM>(cells, G, P, pts, n, i + 64, F1);
+                fetch<OV, SMEM, HASH>(cells, G, P, pts, n, i + 64, F1);
                 accumulate_cell<FULL>(F0.cA[0], F0.cB[0], F0.A, F0.B, S, cnt);
-                fetch<OV, SMEM>(cells, G, P, pts, n, min(i + 128, last), F0);
+                fetch<OV, SMEM, HASH>(cells, G, P, pts, n, min(i + 128, last), F0);
                 accumulate_cell<FULL>(F1.cA[0], F1.cB[0], F1.A, F1.B, S, cnt);
             }
         }
@@ -501,7 +563,7 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
 #pragma unroll kUnroll
         for (int i = lane; i < npad; i += 64) {
             Fetched<OV> cur;
-            fetch<OV, SMEM>(cells, G, P, pts, n, i, cur);
+            fetch<OV, SMEM, HASH>(cells, G, P, pts, n, i, cur);
 #pragma unroll
             for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(cur.cA[k], cur.cB[k], cur.A, cur.B, S, cnt);
         }

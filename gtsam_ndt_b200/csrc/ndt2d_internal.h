@@ -15,7 +15,13 @@ struct LevelDev {
     float res, st, inv_st, ox, oy;
     float nhxf, nhyf;         // (float)nhx, (float)nhy
     int nhx, nhy, njx, njy, ov;
+    // 0: `cells` is the dense table indexed by jy*njx+jx. Otherwise `cells` is an open-addressing hash table of
+    // hash_mask+1 records keyed by that index (the key sits in the record's `n` word, 0xffffffff = empty slot), with the
+    // sentinel record at index hash_mask+1: the per-target tables of the batched scan-to-scan path (ndt2d_align_pairs).
+    unsigned hash_mask;
 };
+
+static constexpr unsigned kEmptyKey = 0xffffffffu;
 
 struct AlignArgs {
     LevelDev lv[NDT2D_MAX_LEVELS];
@@ -30,7 +36,11 @@ struct AlignArgs {
     float range_scale, range_min, range_max;
     const double *init;
     ndt2d_result *res;
-    int nscans;
+    // pairs mode (ndt2d_align_pairs): job p aligns scan pairs[2p+1] of the packed batch to the target whose per-level
+    // geometry and hash tables are geo[pairs[2p] * nlevels + l]; lv[] is unused
+    const int32_t *pairs;
+    const LevelDev *geo;
+    int nscans;              // jobs: scans, or pairs in pairs mode
     int cap_points;          // shared-memory slot capacity in points (0: read scans from global memory)
     unsigned int *counter;   // work queue head, zeroed before launch
 };
@@ -53,6 +63,25 @@ cudaError_t launch_eval_poses(const LaunchCfg &c, const LevelDev &L, const float
                               int poses_f32, int64_t npose, int full, double *d_out, int out_stride, int32_t *d_count,
                               int64_t *launches);
 cudaError_t launch_align(const LaunchCfg &c, const AlignArgs &a, int64_t *launches);
+
+// Batched scan-to-scan: one NDT grid per target scan, built by one warp per (target, level) into hash tables.
+struct PairBuildArgs {
+    const float2 *xy;
+    const int64_t *offsets;
+    const int32_t *targets;  // scan index of target slot t
+    int ntargets, nlevels, ov, explicit_grid;
+    float res[NDT2D_MAX_LEVELS];
+    float gox, goy, gex, gey;
+    int min_points;
+    double eig_ratio;
+    unsigned cap;            // slots per table (power of two); a table holds cap + 1 records (the last is the sentinel)
+    float4 *tab;             // ntargets * nlevels tables
+    uint32_t *cnt;           // ntargets * nlevels * cap
+    unsigned long long *sums; // ... * 5
+    LevelDev *geo;           // out: ntargets * nlevels
+    int *error;              // out: set to 1 + slot when a target's lattice would exceed 2^31 cells
+};
+cudaError_t launch_pairs_build(const LaunchCfg &c, const PairBuildArgs &a, int64_t *launches);
 size_t align_smem_bytes(int cap_points); // dynamic shared memory per k_align block
 // Publication of a shard's best hypothesis into every rank's exchange table (peer pointers, NVLink stores).
 struct PublishArgs {

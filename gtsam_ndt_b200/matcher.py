@@ -240,6 +240,25 @@ class NdtMatcher2D:
         self._ck(self._L.ndt2d_sweep_device(self._h, level, _ptr(d_xy), n, _ptr(d_hyp), nhyp, _ptr(d_scores), k,
                                             _ptr(d_best_idx), _ptr(d_best_score)))
 
+    def align_pairs(self, xy, offsets, pairs, init):
+        """Batched scan-to-scan: pairs[p] = (target scan, source scan) of the packed batch; equals set_target(target) +
+        align(source, init[p]) for every pair, in one call (per-target grids in hash tables)."""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        init = np.ascontiguousarray(init, np.float64).reshape(-1, 3)
+        assert len(init) == len(pairs)
+        res = np.zeros(len(pairs), RESULT_DTYPE)
+        self._ck(self._L.ndt2d_align_pairs(self._h, _ptr(xy), _ptr(offsets), len(offsets) - 1, _ptr(pairs), len(pairs), _ptr(init), _ptr(res)))
+        return res
+
+    def align_pairs_device(self, d_xy, d_offsets, offsets, pairs, d_init, d_res):
+        """Device-resident scans / initial poses / results; offsets (host copy) and pairs on the host. Asynchronous."""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        self._ck(self._L.ndt2d_align_pairs_device(self._h, _ptr(d_xy), _ptr(d_offsets), _ptr(offsets), len(offsets) - 1, _ptr(pairs),
+                                                  len(pairs), _ptr(d_init), _ptr(d_res)))
+
     # ---- multi-GPU sweep: best-hypothesis exchange over peer memory (one process per GPU) ----
     def exchange_create(self, world, rank, nslots=64):
         """Allocate this rank's exchange table; returns its 64-byte CUDA IPC handle (bytes) for the other ranks."""

@@ -158,6 +158,20 @@ int ndt2d_align_batch_ranges_device(ndt2d_matcher *m, const void *d_ranges, int 
                                     float range_min, float range_max, const double *d_init,
                                     ndt2d_result *d_res);
 
+/* ---- batched scan-to-scan (kernel stage 3, "batched multi-scan": odometry over a log, loop-closure candidates) ----
+ * All scans are packed as for ndt2d_align_batch (xy + offsets[nscans+1]). Pair p aligns scan pairs[2p+1] (source) to
+ * scan pairs[2p] (target) from init[3p..]: the result equals ndt2d_set_target(target scan) followed by
+ * ndt2d_align(source scan, init) bit for bit (same lattice - auto-fitted per target, or the ndt2d_set_grid one - same
+ * cells, same LM loop), but every target's grid is built once, by one warp, into a per-target hash table, and all pairs
+ * are aligned by one launch. Needs ndt2d_set_resolution(s) only; the handle's own target is not touched.
+ * Target scans are limited to 43 690 points (10 922 with overlapping grids). */
+int ndt2d_align_pairs(ndt2d_matcher *m, const float *xy, const int64_t *offsets, int nscans, const int32_t *pairs,
+                      int npairs, const double *init, ndt2d_result *res);
+/* scans, initial poses and results on the device; offsets (also given on the host) and pairs on the host, because
+ * the list of distinct targets and the chunking are host work. Asynchronous on the handle's stream. */
+int ndt2d_align_pairs_device(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, const int64_t *offsets,
+                             int nscans, const int32_t *pairs, int npairs, const double *d_init, ndt2d_result *d_res);
+
 /* ---- sweep (kernel stage 3: multi-hypothesis search for relocalisation / loop closure, SPEC 6) - */
 /* hyp[3*j..] = (tx, ty, theta) f32. scores (optional, nhyp doubles). Top-k (k >= 1) by
  * (-score, index) into best_idx[k], best_score[k]. */

@@ -108,6 +108,21 @@ class Matcher {
         return out;
     }
 
+    // batched scan-to-scan: pair p aligns scan pairs[p].second (source) to scan pairs[p].first (target) of the packed batch;
+    // equals setTarget(target) + align(source, init[p]) for every pair, with all grids built and all pairs aligned in one call
+    std::vector<Result> alignPairs(const std::vector<Point2f> &points, const std::vector<std::int64_t> &offsets,
+                                   const std::vector<std::pair<std::int32_t, std::int32_t>> &pairs, const std::vector<Pose2d> &init)
+    {
+        if (pairs.size() != init.size()) throw std::invalid_argument("alignPairs: one initial pose per pair");
+        if (offsets.empty()) throw std::invalid_argument("alignPairs: offsets must have nscans + 1 entries");
+        static_assert(sizeof(std::pair<std::int32_t, std::int32_t>) == 2 * sizeof(std::int32_t), "pairs must be packed int32 pairs");
+        std::vector<Result> out(pairs.size());
+        ck(ndt2d_align_pairs(h_, reinterpret_cast<const float *>(points.data()), offsets.data(), static_cast<int>(offsets.size() - 1),
+                             reinterpret_cast<const std::int32_t *>(pairs.data()), static_cast<int>(pairs.size()),
+                             reinterpret_cast<const double *>(init.data()), out.data()));
+        return out;
+    }
+
     // ---- multi-hypothesis search (relocalisation, loop-closure candidates) --------------------------
     // hypotheses: (x, y, theta) float triples. Returns the k best (index, score), best first.
     std::vector<std::pair<std::int64_t, double>> sweep(const std::vector<Point2f> &scan, const std::vector<float> &hyp_xyt, int k,
@@ -143,6 +158,31 @@ class Matcher {
         if (count) *count = c;
         return out;
     }
+
+    // ---- several GPUs, one process each: best-hypothesis exchange of a sharded sweep over peer memory ------
+    // exchangeCreate() returns this rank's 64-byte IPC handle; all-gather the handles with the host code's own
+    // transport (MPI, sockets, ...) and pass them, ordered by rank, to exchangeOpen().
+    std::array<unsigned char, NDT2D_IPC_HANDLE_BYTES> exchangeCreate(int world, int rank, int nslots = 64)
+    {
+        std::array<unsigned char, NDT2D_IPC_HANDLE_BYTES> h{};
+        ck(ndt2d_exchange_create(h_, world, rank, nslots, h.data()));
+        return h;
+    }
+    void exchangeOpen(const std::vector<unsigned char> &handles_by_rank) { ck(ndt2d_exchange_open(h_, handles_by_rank.data())); }
+    // device pointers; hypothesis j of the shard has global index index_offset + j; asynchronous
+    void sweepPublish(int level, const float *d_scan_xy, int n, const float *d_hyp_xyt, std::int64_t nhyp, std::int64_t index_offset,
+                      std::uint64_t query, double *d_scores = nullptr)
+    {
+        ck(ndt2d_sweep_publish(h_, level, d_scan_xy, n, d_hyp_xyt, nhyp, d_scores, index_offset, query));
+    }
+    std::pair<std::int64_t, double> exchangeWait(std::uint64_t query, int timeout_ms = 10000)
+    {
+        std::int64_t idx = -1;
+        double score = 0.0;
+        ck(ndt2d_exchange_wait(h_, query, timeout_ms, &idx, &score));
+        return {idx, score};
+    }
+    void exchangeClose() { ck(ndt2d_exchange_close(h_)); }
 
     ndt2d_matcher *handle() const { return h_; }
     void synchronize() { ck(ndt2d_synchronize(h_)); }

@@ -304,6 +304,47 @@ def test_sweep_matches_oracle(mods, small_world, overlap):
     assert list(bi2[5:]) == [-1, -1, -1] and sorted(bi2[:5]) == [0, 1, 2, 3, 4]
 
 
+def _between(a, b):
+    c, s_ = math.cos(a[2]), math.sin(a[2])
+    dx, dy = b[0] - a[0], b[1] - a[1]
+    return np.array([c * dx + s_ * dy, -s_ * dx + c * dy, b[2] - a[2]])
+
+
+@pytest.mark.parametrize("cfg", [dict(res=[0.5]), dict(res=[2.0, 1.0, 0.5]), dict(res=[1.0, 0.5], overlap=1),
+                                 dict(res=[0.5], grid=(-120.0, -120.0, 240.0, 240.0)), dict(res=[1.0], chunk_bytes=3_000_000)])
+def test_align_pairs_equals_set_target_plus_align(mods, cfg, monkeypatch):
+    """Batched scan-to-scan: every pair of ndt2d_align_pairs must be byte-identical to ndt2d_set_target(target scan) +
+    ndt2d_align(source scan) on the GPU, and to the same two calls of the CPU spec oracle. Covers pyramids, overlapping
+    grids, an explicit lattice, repeated and self targets, empty / tiny / unusable scans, and chunking of the table budget."""
+    from gtsam_ndt_b200 import synth
+    cfg = dict(cfg)
+    grid = cfg.pop("grid", None)
+    chunk = cfg.pop("chunk_bytes", None)
+    res = cfg.pop("res")
+    if chunk:
+        monkeypatch.setenv("NDT2D_PAIRS_BYTES", str(chunk))
+    m, o = make_pair(mods, res, grid, **cfg)
+    sc = synth.SCAN_1080
+    ranges, poses = synth.scans(14, traj_len=4000, first=50, step=9, sigma=0.01, **sc)     # neighbours 0.85 m apart
+    scans = synth.polar_to_points(ranges, sc["angle_min"], sc["angle_inc"])
+    scans = [s[:: (1 + i % 3)] for i, s in enumerate(scans)]                                # ragged: 1080 / 540 / 360 points
+    scans += [np.zeros((0, 2), np.float32), scans[0][:4], np.full((30, 2), np.nan, np.float32)]
+    E, T, N = 14, 15, 16                                                                    # empty, tiny, unusable
+    pairs = [(i, i + 1) for i in range(13)] + [(i + 1, i) for i in range(0, 13, 3)] + [(5, 5), (0, 4), (0, 2), (3, 9),
+             (E, 0), (0, E), (T, 1), (1, T), (N, 2), (2, N), (E, E)]
+    rng = np.random.default_rng(3)
+    pp = np.vstack([poses, np.zeros((3, 3))])
+    init = np.array([_between(pp[t], pp[s]) + rng.normal(size=3) * [0.03, 0.03, 0.003] for t, s in pairs])
+    xy, off = synth.pack(scans)
+    rg = m.align_pairs(xy, off, pairs, init)
+    assert (rg["status"][:13] == 0).sum() >= 11                                             # consecutive scans do align
+    for p, (t, s_) in enumerate(pairs):
+        m.set_target(scans[t]); o.set_target(scans[t])
+        one = m.align(scans[s_], init[p]); ref = o.align(scans[s_], init[p])
+        assert rg[p].tobytes() == one.tobytes(), (p, t, s_, rg[p], one)
+        assert rg[p].tobytes() == ref.tobytes(), (p, t, s_, rg[p], ref)
+
+
 def test_sweep_publish_world1_equals_sweep(mods, small_world):
     """The peer-memory exchange with a single rank: the arg-max kernel publishes into the rank's own table and the host
     poll returns what ndt2d_sweep returns (index shifted by index_offset); slots are reused as the epochs grow."""
