@@ -190,13 +190,15 @@ __global__ void __launch_bounds__(256) k_pairs_build(const PairBuildArgs a)
     // cell's slot (compare-and-swap on the key word) and add into its integer sums
     unsigned *keyword = reinterpret_cast<unsigned *>(rec);   // key of slot s = word 8 s + 6
     constexpr int K = OV ? 2 : 1;
+    float2 pnext = lane < n ? __ldg(src + lane) : make_float2(0.f, 0.f);   // the next window's point is requested one window ahead
     for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
+        const float2 p = pnext;
+        if (i + 32 < n) pnext = __ldg(src + i + 32);
         float X = 0.0f, Y = 0.0f;
         bool inside = false;
         int hx = 0, hy = 0;
         if (i < n) {
-            float2 p = __ldg(src + i);
             X = p.x;
             Y = p.y;
             inside = lattice(L, X, Y, hx, hy);
