@@ -810,6 +810,9 @@ static cudaError_t launch_align_t(const LaunchCfg &c, const AlignArgs &a)
 #ifdef NDT2D_MAX_BLOCKS_PER_SM
     if (per_sm > NDT2D_MAX_BLOCKS_PER_SM) per_sm = NDT2D_MAX_BLOCKS_PER_SM;
 #endif
+#ifdef NDT2D_PAIRS_BLOCKS_PER_SM
+    if (PAIRS && per_sm > NDT2D_PAIRS_BLOCKS_PER_SM) per_sm = NDT2D_PAIRS_BLOCKS_PER_SM; // fewer tables in flight: L2 residency experiment
+#endif
     int grid = grid_for(a.nscans, ALIGN_THREADS / 32, c.sm_count, per_sm);
     kern<<<grid, ALIGN_THREADS, smem, c.stream>>>(a);
     return cudaGetLastError();

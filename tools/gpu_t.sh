@@ -1,4 +1,7 @@
 #!/bin/bash
-python bench.py --workload odometry > gpurun_out/r1j_odometry.json 2>/dev/null; cut -c1-300 gpurun_out/r1j_odometry.json
-python bench.py --workload odometry --res 2.0 1.0 0.5 --perturb 0.1 1.0 > gpurun_out/r1j_odometry_pyramid.json 2>/dev/null; cut -c1-200 gpurun_out/r1j_odometry_pyramid.json
-python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+for v in "" build/variants/libndt2d_pb2.so build/variants/libndt2d_pb1.so; do
+NDT2D_LIB=$v python bench.py --workload odometry 2>&1 | tail -1 | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print('$v', round(d['value']/1e6,3),'M/s', round(d['ms_per_step'],3),'ms')"
+done
+python bench.py --no-cpu-baseline 2>/dev/null | python -c "
+import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('scan2map', round(d['value']/1e6,2))"
