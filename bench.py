@@ -205,7 +205,7 @@ def run_reference(args):
     o = oracle.Oracle(args.res, overlap=args.overlap)
     o.set_grid(-100.0, -100.0, 200.0, 200.0)
     cores = host_cores()      # torchrun exports OMP_NUM_THREADS=1; the arm uses every core the process may run on
-    nref = args.ref_scans or max(64, min(args.scans, 256 * cores))   # ~70 ms of work per step: the threads' start-up cost is amortised
+    nref = args.ref_scans or max(64, min(args.scans, 1024 * cores))   # ~0.3 s of work per step: start-up costs are amortised
     ranges, poses, init, map_xy = make_workload(args, 0, count=nref)
     o.set_target(map_xy)
     xy, off = to_points(ranges)

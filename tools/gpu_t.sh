@@ -1,7 +1,6 @@
 #!/bin/bash
-for v in "" build/variants/libndt2d_pb2.so build/variants/libndt2d_pb1.so; do
-NDT2D_LIB=$v python bench.py --workload odometry 2>&1 | tail -1 | python -c "
-import sys,json; d=json.loads(sys.stdin.read()); print('$v', round(d['value']/1e6,3),'M/s', round(d['ms_per_step'],3),'ms')"
-done
-python bench.py --no-cpu-baseline 2>/dev/null | python -c "
-import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('scan2map', round(d['value']/1e6,2))"
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -2
+python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+python bench.py > gpurun_out/final_bench.json 2>/dev/null; python -c "
+import json; d=json.loads(open('gpurun_out/final_bench.json').read().strip().splitlines()[-1]); print('value',round(d['value']/1e6,2),'e2e',round(d['e2e']['value']/1e6,2),d['e2e']['input'],'frac',round(d['roofline']['frac'],2),'traffic',d['roofline']['traffic'],'cpu',round(d['cpu_baseline']['value']),d['cpu_baseline']['cores'],'launches',d['gpu_launches'],d['clocks'])"
+python bench.py --impl reference | cut -c1-330
