@@ -492,21 +492,24 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
 #pragma unroll
         for (int k = 0; k < Fetched<OV>::NC; ++k) {
             const unsigned o = (k & 1) + (k >> 1) * G.njx;
+            // (tables are at most 2/3 full, so an empty slot ends every chain; the bound only guards against a corrupt table)
             if (inA) {
-                for (;;) {
+                for (unsigned probes = 0; probes <= G.mask; ++probes) {
                     const unsigned key = (unsigned)__float_as_int(lo32(F.cA[k].nv));
                     if (key == bA + o || key == kEmptyKey) break;
                     sA[k] = (sA[k] + 1u) & G.mask;
                     F.cA[k] = load_cell(cells, sA[k]);
                 }
+                if ((unsigned)__float_as_int(lo32(F.cA[k].nv)) != bA + o) F.cA[k].nv = 0ull;   // not found: invalid
             }
             if (inB) {
-                for (;;) {
+                for (unsigned probes = 0; probes <= G.mask; ++probes) {
                     const unsigned key = (unsigned)__float_as_int(lo32(F.cB[k].nv));
                     if (key == bB + o || key == kEmptyKey) break;
                     sB[k] = (sB[k] + 1u) & G.mask;
                     F.cB[k] = load_cell(cells, sB[k]);
                 }
+                if ((unsigned)__float_as_int(lo32(F.cB[k].nv)) != bB + o) F.cB[k].nv = 0ull;
             }
         }
     }

@@ -235,16 +235,21 @@ __global__ void __launch_bounds__(256) k_pairs_build(const PairBuildArgs a)
                 }
                 if (head && key >= 0) {
                     unsigned s = hash_slot((unsigned)key, L.hash_mask);
-                    for (;;) {
+                    bool placed = false;
+                    // the table is at most 2/3 full by construction; the probe count is bounded all the same, so that
+                    // inconsistent arguments (offsets on the device that differ from the host copy) cannot hang the GPU
+                    for (unsigned probes = 0; probes <= L.hash_mask; ++probes) {
                         unsigned was = atomicCAS(keyword + 8 * (size_t)s + 6, kEmptyKey, (unsigned)key);
                         if (was == kEmptyKey) {
                             const int pos = atomicAdd(&s_nlist[w], 1);
                             if (pos < PAIRS_LIST_CAP) s_list[w][pos] = (unsigned short)s;
+                            placed = true;
                             break;
                         }
-                        if (was == (unsigned)key) break;
+                        if (was == (unsigned)key) { placed = true; break; }
                         s = (s + 1u) & L.hash_mask;
                     }
+                    if (!placed) { atomicMax(a.error, t + 1); continue; }
                     atomicAdd(cnt + s, (unsigned)c);
                     unsigned long long *q = sums + 5 * (size_t)s;
                     atomicAdd(q + 0, (unsigned long long)sx);
