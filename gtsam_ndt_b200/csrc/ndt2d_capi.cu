@@ -105,6 +105,15 @@ struct ndt2d_matcher {
     ndt2d_best *ex_host = nullptr; // pinned staging for the host-side poll: two snapshots of the whole table
     std::vector<char> ex_verified_ok; // per row: the second snapshot holds a verified, complete row
     int chunk_scans = 0; // NDT2D_CHUNK_SCANS override; 0 = choose by bytes (plan_chunks)
+    // low-latency path of small host-buffer calls (a single align is 3 CUDA calls): pinned staging for one packed upload,
+    // results written by the kernel straight into mapped pinned memory, work-queue counters from a pre-zeroed ring
+    static constexpr size_t FAST_BYTES = 256 << 10;
+    static constexpr int FAST_SCANS = 256, RING = 4096;
+    unsigned char *fast_host = nullptr;      // pinned, FAST_BYTES
+    ndt2d_result *fast_res = nullptr;        // pinned + mapped, FAST_SCANS records
+    ndt2d_result *fast_res_dev = nullptr;    // its device address
+    DevBuf b_fast, b_ring;
+    int ring_pos = 0;
     int64_t launches = 0;
     std::string err;
 };
@@ -376,6 +385,8 @@ int ndt2d_create_on_stream(int device, void *cuda_stream, ndt2d_matcher **out)
             ndt2d_destroy(m);
             return fail(nullptr, NDT2D_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
+        m->cfg.block_align_max = -1;
+        if (const char *e = getenv("NDT2D_BLOCK_ALIGN_MAX")) m->cfg.block_align_max = atoi(e); // 0: always one warp per scan
         if (const char *e = getenv("NDT2D_CHUNK_SCANS")) {
             int v = atoi(e);
             if (v > 0) m->chunk_scans = v;
@@ -399,6 +410,10 @@ void ndt2d_destroy(ndt2d_matcher *m)
     cudaStreamSynchronize(m->cfg.stream);
     drop_target(m);
     ndt2d_exchange_close(m);
+    if (m->fast_host) cudaFreeHost(m->fast_host);
+    if (m->fast_res) cudaFreeHost(m->fast_res);
+    m->b_fast.release();
+    m->b_ring.release();
     DevBuf *bufs[] = {&m->b_xy, &m->b_off, &m->b_init, &m->b_res, &m->b_pose, &m->b_out, &m->b_cnt, &m->b_idx, &m->b_terms,
                       &m->b_hyp, &m->b_scores, &m->b_tki, &m->b_tkv, &m->b_scratch, &m->b_counter, &m->b_beams, &m->b_ranges,
                       &m->b_box, &m->b_ptab, &m->b_pcnt, &m->b_psums, &m->b_pgeo, &m->b_ptargets, &m->b_ppairs, &m->b_perr};
@@ -700,6 +715,49 @@ static int align_batch_device_impl(ndt2d_matcher *m, const float *d_xy, const in
     return NDT2D_OK;
 }
 
+// Small host-buffer batches (a single align above all): offsets, initial poses and points are packed into one pinned
+// buffer and go up in ONE copy, the kernel writes its results into mapped pinned memory, the queue counter comes from a
+// pre-zeroed ring: copy, launch, synchronise - instead of the ~15 calls of the chunked pipeline.
+static int align_batch_fast(ndt2d_matcher *m, const float *xy, const int64_t *offsets, int nscans, int64_t total, int64_t maxn,
+                            const double *init, ndt2d_result *res)
+{
+    if (!m->fast_host) {
+        CK(m, cudaHostAlloc(reinterpret_cast<void **>(&m->fast_host), ndt2d_matcher::FAST_BYTES, cudaHostAllocDefault));
+        CK(m, cudaHostAlloc(reinterpret_cast<void **>(&m->fast_res), ndt2d_matcher::FAST_SCANS * sizeof(ndt2d_result), cudaHostAllocMapped));
+        CK(m, cudaHostGetDevicePointer(reinterpret_cast<void **>(&m->fast_res_dev), m->fast_res, 0));
+        CK(m, m->b_fast.ensure(ndt2d_matcher::FAST_BYTES));
+        CK(m, m->b_ring.ensure(ndt2d_matcher::RING * 4));
+        CK(m, cudaMemsetAsync(m->b_ring.p, 0, ndt2d_matcher::RING * 4, m->cfg.stream));
+        m->ring_pos = 0;
+    }
+    if (m->ring_pos == ndt2d_matcher::RING) {   // every slot used once: zero the ring again (stream-ordered after its last user)
+        CK(m, cudaMemsetAsync(m->b_ring.p, 0, ndt2d_matcher::RING * 4, m->cfg.stream));
+        m->ring_pos = 0;
+    }
+    const size_t off_bytes = (size_t)(nscans + 1) * 8, init_bytes = (size_t)nscans * 24, xy_bytes = (size_t)total * 8;
+    unsigned char *h = m->fast_host;
+    memcpy(h, offsets, off_bytes);
+    memcpy(h + off_bytes, init, init_bytes);
+    if (xy_bytes) memcpy(h + off_bytes + init_bytes, xy, xy_bytes);
+    unsigned char *d = m->b_fast.as<unsigned char>();
+    CK(m, cudaMemcpyAsync(d, h, off_bytes + init_bytes + xy_bytes, cudaMemcpyHostToDevice, m->cfg.stream));
+    AlignArgs a;
+    fill_align_args(m, a);
+    a.offsets = reinterpret_cast<const int64_t *>(d);
+    a.init = reinterpret_cast<const double *>(d + off_bytes);
+    a.xy = reinterpret_cast<const float2 *>(d + off_bytes + init_bytes);
+    a.res = m->fast_res_dev;
+    a.nscans = nscans;
+    a.cap_points = align_cap_points(m, (int)maxn);
+    a.counter = m->b_ring.as<unsigned int>() + m->ring_pos++;
+    a.counter_is_zero = 1;
+    CK(m, launch_align(m->cfg, a, &m->launches));
+    int rc = ndt2d_synchronize(m);
+    if (rc) return rc;
+    memcpy(res, m->fast_res, (size_t)nscans * sizeof(ndt2d_result));
+    return NDT2D_OK;
+}
+
 int ndt2d_align_batch(ndt2d_matcher *m, const float *xy, const int64_t *offsets, int nscans, const double *init,
                       ndt2d_result *res)
 {
@@ -716,6 +774,9 @@ int ndt2d_align_batch(ndt2d_matcher *m, const float *xy, const int64_t *offsets,
     int64_t total = offsets[nscans];
     if (offsets[0] < 0 || (total > 0 && !xy)) return fail(m, NDT2D_EINVAL, "bad offsets / xy");
     DeviceGuard g(m->device);
+    if (nscans <= ndt2d_matcher::FAST_SCANS && offsets[0] == 0 &&
+        (size_t)(nscans + 1) * 8 + (size_t)nscans * 24 + (size_t)total * 8 <= ndt2d_matcher::FAST_BYTES)
+        return align_batch_fast(m, xy, offsets, nscans, total, maxn, init, res);
     int rc;
     CK(m, m->b_xy.ensure((size_t)(total ? total : 1) * 8));
     CK(m, m->b_res.ensure((size_t)nscans * sizeof(ndt2d_result)));

@@ -366,13 +366,10 @@ __device__ __forceinline__ void cell_factors(const Cell4 &cA, const Cell4 &cB, c
     }
 }
 
-// one cell for the lane's two points, accumulated into the lane's partials: acc_t = fma(e, c_t, acc_t)
+// acc_t = fma(e, c_t, acc_t) for the factors of one cell (SPEC 4's update of the lane's two partials)
 template <bool FULL>
-__device__ __forceinline__ void accumulate_cell(const Cell4 &cA, const Cell4 &cB, const PointPk &A, const PointPk &B, Partials &S,
-                                                int &cnt)
+__device__ __forceinline__ void apply_factors(const Factors &F, Partials &S)
 {
-    Factors F;
-    cell_factors<FULL>(cA, cB, A, B, F, cnt);
     S.s0 = add2(S.s0, F.e);
     if (FULL) {
         const float eA = lo32(F.e), eB = hi32(F.e);
@@ -387,6 +384,16 @@ __device__ __forceinline__ void accumulate_cell(const Cell4 &cA, const Cell4 &cB
         S.s7[1] = __fmaf_rn(eB, F.c7[1], S.s7[1]);
         S.s9 = fma2(F.e, F.c9, S.s9);
     }
+}
+
+// one cell for the lane's two points, accumulated into the lane's partials: acc_t = fma(e, c_t, acc_t)
+template <bool FULL>
+__device__ __forceinline__ void accumulate_cell(const Cell4 &cA, const Cell4 &cB, const PointPk &A, const PointPk &B, Partials &S,
+                                                int &cnt)
+{
+    Factors F;
+    cell_factors<FULL>(cA, cB, A, B, F, cnt);
+    apply_factors<FULL>(F, S);
 }
 
 // Where the warp's points come from: AoS float2 in shared memory, sanitised and padded with the far-away
@@ -520,6 +527,9 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
 // PIPE: software pipelining, the records of step j+1 are requested before step j is computed, so the L2 round
 // trip of the gathers overlaps this warp's own arithmetic (costs ~30 registers).
 // TR (FULL only): finish with the transposed reduction; E.v[0] is then sum number E.slot, the other E.v are unset.
+template <bool FULL, bool TR>
+__device__ __forceinline__ void finish_partials(const Partials &S, int cnt, int lane, Eval &E);
+
 // HASH: L.cells is a per-target hash table (L.hash_mask), see fetch_cell().
 template <int OV, bool FULL, bool SMEM, int PIPE, bool TR = false, bool HASH = false>
 __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E)
@@ -571,7 +581,14 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
             for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(cur.cA[k], cur.cB[k], cur.A, cur.B, S, cnt);
         }
     }
-    // SPEC 4: D[l] = (double)P[l] + (double)P[l+32], then the butterfly
+    finish_partials<FULL, TR>(S, cnt, lane, E);
+}
+
+// SPEC 4: D[l] = (double)P[l] + (double)P[l+32], then the butterfly (plain: every lane gets all ten sums; TR: the
+// transposed form, E.v[0] = sum number E.slot)
+template <bool FULL, bool TR>
+__device__ __forceinline__ void finish_partials(const Partials &S, int cnt, int lane, Eval &E)
+{
     E.slot = 0;
     if (FULL) {
         double D[10];

@@ -43,12 +43,14 @@ struct AlignArgs {
     int nscans;              // jobs: scans, or pairs in pairs mode
     int cap_points;          // shared-memory slot capacity in points (0: read scans from global memory)
     unsigned int *counter;   // work queue head, zeroed before launch
+    int counter_is_zero;     // host side only: the caller guarantees *counter == 0 (no memset in launch_align)
 };
 
 struct LaunchCfg {
     int sm_count;
     int max_smem_optin;
     cudaStream_t stream;
+    int block_align_max;     // calls with at most this many scans use the block-per-scan align kernel (-1: 2 x SMs)
 };
 
 // all launchers return the cudaError_t of the launch; *launches is incremented per kernel launched

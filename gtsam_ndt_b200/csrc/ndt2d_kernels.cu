@@ -513,6 +513,182 @@ __device__ __forceinline__ int align_level(const LevelDev *L, const ndt2d_params
     return status;
 }
 
+// ------------------------------------------------------------------------------------------------
+// (2d) low-latency align: one BLOCK per scan, for calls with few scans (a single align above all)
+// ------------------------------------------------------------------------------------------------
+// With one warp per scan an evaluation is 17 dependent (gather, compute) steps, ~9 us; a lone align is latency, not
+// throughput. Here the eight warps of a block compute the SPEC 4 factors (e, c1..c9) of different 64-point steps at
+// the same time and park them in shared memory; warp 0 then applies them to the 64 partial sums in the order SPEC 4
+// prescribes (increasing point index, cell order within a point), so the sums - and everything after - are the bits
+// of the one-warp kernel. The LM logic is executed by every thread on the same shared-memory state (uniform).
+
+static constexpr int BLOCK_ALIGN_THREADS = 256; // 8 warps (18 warps, one round for 1080 points, measured no faster: the serial part dominates)
+static constexpr int FACTOR_WORDS = 10; // u64 per lane and (step, cell): e, c12[2], c45[2], c68[2], c3, c9, c7 pair
+
+template <int OV>
+__device__ __forceinline__ void eval_block(const LevelDev *L, const float2 *pts, int n, WarpState *ws, int trial, u64 *fac)
+{
+    constexpr int NC = OV ? 4 : 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double *pose = trial ? ws->pn : ws->p;
+    const PosePk P = pose_pack(pose_to_f32(pose[0], pose[1], pose[2]));
+    LatticePk G;
+    G.org = pk(L->ox, L->oy); G.inv = bc(L->inv_st); G.nhx = (unsigned)L->nhx; G.nhy = (unsigned)L->nhy; G.njx = (unsigned)L->njx;
+    G.mask = 0;
+    G.sentinel = (unsigned)L->njx * (unsigned)L->njy;
+    const float4 *__restrict__ cells = L->cells;
+    const int nsteps = (n + 63) >> 6;
+    for (int step = warp; step < nsteps; step += BLOCK_ALIGN_THREADS / 32) {
+        Fetched<OV> F;
+        fetch<OV, true, false>(cells, G, P, pts, n, (step << 6) + lane, F);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            Factors X;
+            int c = 0;
+            cell_factors<true>(F.cA[k], F.cB[k], F.A, F.B, X, c);
+            u64 *o = fac + ((size_t)(step * NC + k) * FACTOR_WORDS) * 32 + lane;
+            o[0 * 32] = X.e;
+            o[1 * 32] = X.c12[0]; o[2 * 32] = X.c12[1];
+            o[3 * 32] = X.c45[0]; o[4 * 32] = X.c45[1];
+            o[5 * 32] = X.c68[0]; o[6 * 32] = X.c68[1];
+            o[7 * 32] = X.c3; o[8 * 32] = X.c9;
+            o[9 * 32] = pk(X.c7[0], X.c7[1]);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        Partials S;
+        S.s0 = S.s3 = S.s9 = 0ull;
+        S.s7[0] = S.s7[1] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) S.s12[k] = S.s45[k] = S.s68[k] = 0ull;
+        int cnt = 0;
+        for (int e = 0; e < nsteps * NC; ++e) {
+            const u64 *o = fac + ((size_t)e * FACTOR_WORDS) * 32 + lane;
+            Factors X;
+            X.e = o[0 * 32];
+            X.c12[0] = o[1 * 32]; X.c12[1] = o[2 * 32];
+            X.c45[0] = o[3 * 32]; X.c45[1] = o[4 * 32];
+            X.c68[0] = o[5 * 32]; X.c68[1] = o[6 * 32];
+            X.c3 = o[7 * 32]; X.c9 = o[8 * 32];
+            upk(o[9 * 32], X.c7[0], X.c7[1]);
+            // a contributing pair has e = exp(-h) with h < 30, never zero; a skipped pair has e = 0 exactly
+            cnt += (lo32(X.e) != 0.0f ? 1 : 0) + (hi32(X.e) != 0.0f ? 1 : 0);
+            apply_factors<true>(X, S);
+        }
+        Eval E;
+        finish_partials<true, true>(S, cnt, lane, E);
+        double *out = trial ? ws->t : ws->v;
+        out[E.slot] = E.v[0];
+        if (lane == 0) *(trial ? &ws->tcount : &ws->count) = E.count;
+    }
+    __syncthreads();
+}
+
+template <int OV>
+__device__ __forceinline__ int align_level_block(const LevelDev *L, const ndt2d_params &P, const float2 *pts, int n, WarpState *ws,
+                                                 u64 *fac, int &evals_total)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0) ws->lambda = P.lambda_init;
+    eval_block<OV>(L, pts, n, ws, 0, fac); // begins its second half with __syncthreads(), ends with one
+    int evals = 1, status = NDT2D_MAX_ITERATIONS;
+    if (n == 0 || ws->count == 0) {
+        evals_total += evals;
+        return NDT2D_NO_OVERLAP;
+    }
+    for (;;) {
+        if (evals >= P.max_iterations) break;
+        double d[3];
+        double lambda = ws->lambda;
+        bool stalled = false;
+        {
+            double g[3] = {ws->v[1], ws->v[2], ws->v[3]};
+            double H6[6] = {ws->v[4], ws->v[5], ws->v[6], ws->v[7], ws->v[8], ws->v[9]};
+            while (!solve3(g, H6, lambda, d)) {
+                lambda = lambda * P.lambda_fail_up;
+                if (lambda > P.lambda_max) { stalled = true; break; }
+            }
+        }
+        if (stalled) { status = NDT2D_STALLED; break; }
+        double n2 = d[0] * d[0] + d[1] * d[1];
+        if (n2 > P.max_step_trans * P.max_step_trans) {
+            double sc = P.max_step_trans / sqrt(n2);
+            d[0] *= sc; d[1] *= sc; d[2] *= sc; n2 = P.max_step_trans * P.max_step_trans;
+        }
+        if (fabs(d[2]) > P.max_step_rot) {
+            double sc = P.max_step_rot / fabs(d[2]);
+            d[0] *= sc; d[1] *= sc; d[2] *= sc; n2 = n2 * (sc * sc);
+        }
+        const bool small = (n2 < P.eps_trans * P.eps_trans) && (fabs(d[2]) < P.eps_rot);
+        __syncthreads();
+        if (tid == 0) {
+            ws->pn[0] = ws->p[0] + d[0];
+            ws->pn[1] = ws->p[1] + d[1];
+            ws->pn[2] = ws->p[2] + d[2];
+            ws->lambda = lambda;
+        }
+        __syncthreads();
+        eval_block<OV>(L, pts, n, ws, 1, fac);
+        evals += 1;
+        lambda = ws->lambda;
+        const bool better = ws->t[0] > ws->v[0];
+        __syncthreads();
+        if (better) {
+            if (tid < 10) ws->v[tid] = ws->t[tid];
+            if (tid == 10) ws->count = ws->tcount;
+            if (tid >= 11 && tid < 14) ws->p[tid - 11] = ws->pn[tid - 11];
+            lambda = fmax(lambda / P.lambda_down, P.lambda_min);
+            if (tid == 14) ws->lambda = lambda;
+            __syncthreads();
+            if (small) { status = NDT2D_CONVERGED; break; }
+        } else {
+            if (small) { status = NDT2D_CONVERGED; break; }
+            lambda = lambda * P.lambda_up;
+            if (tid == 14) ws->lambda = lambda;
+            __syncthreads();
+            if (lambda > P.lambda_max) { status = NDT2D_STALLED; break; }
+        }
+    }
+    evals_total += evals;
+    return status;
+}
+
+template <int OV>
+__global__ void __launch_bounds__(BLOCK_ALIGN_THREADS) k_align_block(const __grid_constant__ AlignArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpState *ws = reinterpret_cast<WarpState *>(smem_raw);
+    float2 *pts = reinterpret_cast<float2 *>(smem_raw + sizeof(WarpState));
+    u64 *fac = reinterpret_cast<u64 *>(smem_raw + sizeof(WarpState) + (size_t)a.cap_points * sizeof(float2));
+    const int job = blockIdx.x, tid = threadIdx.x;
+    const int64_t o0 = __ldg(a.offsets + job), o1 = __ldg(a.offsets + job + 1);
+    const int n = (int)(o1 - o0), npad = (n + 63) & ~63;
+    const float2 *src = a.xy + o0;
+    for (int i = tid; i < npad; i += BLOCK_ALIGN_THREADS) pts[i] = i < n ? sanitize(__ldg(src + i)) : make_float2(1e18f, 1e18f);
+    if (tid < 3) ws->p[tid] = __ldg(a.init + 3 * (size_t)job + tid);
+    __syncthreads();
+    int evals = 0, status = NDT2D_NO_OVERLAP;
+    for (int l = 0; l < a.nlevels; ++l) status = align_level_block<OV>(&a.lv[l], a.prm, pts, n, ws, fac, evals);
+    if (tid == 0) {
+        const WarpState &E = *ws;
+        ndt2d_result *r = a.res + job;
+        const double TWO_PI = 6.283185307179586476925286766559;
+        r->pose[0] = E.p[0];
+        r->pose[1] = E.p[1];
+        r->pose[2] = E.p[2] - TWO_PI * rint(E.p[2] / TWO_PI);
+        r->score = E.v[0];
+        r->grad[0] = E.v[1]; r->grad[1] = E.v[2]; r->grad[2] = E.v[3];
+        r->hessian[0] = E.v[4]; r->hessian[1] = E.v[5]; r->hessian[2] = E.v[6];
+        r->hessian[3] = E.v[5]; r->hessian[4] = E.v[7]; r->hessian[5] = E.v[8];
+        r->hessian[6] = E.v[6]; r->hessian[7] = E.v[8]; r->hessian[8] = E.v[9];
+        r->iterations = evals;
+        r->status = status;
+        r->count = E.count;
+        r->reserved = 0;
+    }
+}
+
 // Persistent kernel: warps pull scan indices from a global counter until the batch is drained.
 // STAGED: the scan is copied once into this warp's shared-memory slot and re-read from there on
 // every iteration (an align touches its points 10-30 times, its HBM bytes once).
@@ -837,11 +1013,32 @@ cudaError_t launch_pairs_build(const LaunchCfg &c, const PairBuildArgs &a, int64
 cudaError_t launch_align(const LaunchCfg &c, const AlignArgs &a, int64_t *launches)
 {
     if (a.nscans <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), c.stream);
-    if (e != cudaSuccess) return e;
+    if (!a.counter_is_zero) {
+        cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), c.stream);
+        if (e != cudaSuccess) return e;
+    }
     ++*launches;
     const bool ranges = (a.xy == nullptr);
     const bool staged = a.cap_points > 0;
+    // few scans: latency matters, not throughput - one block per scan (k_align_block) if its factor buffer fits
+    if (!ranges && staged && !a.pairs && a.nscans <= (c.block_align_max >= 0 ? c.block_align_max : 2 * c.sm_count)) {
+        const int NC = a.prm.overlap ? 4 : 1;
+        const size_t smem = sizeof(WarpState) + (size_t)a.cap_points * sizeof(float2) +
+                            (size_t)(a.cap_points / 64) * NC * FACTOR_WORDS * 32 * sizeof(u64);
+        if (smem <= (size_t)c.max_smem_optin) {
+            cudaError_t e2 = cudaSuccess;
+            if (a.prm.overlap) {
+                if (smem > 48 * 1024) e2 = cudaFuncSetAttribute(k_align_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e2 != cudaSuccess) return e2;
+                k_align_block<1><<<a.nscans, BLOCK_ALIGN_THREADS, smem, c.stream>>>(a);
+            } else {
+                if (smem > 48 * 1024) e2 = cudaFuncSetAttribute(k_align_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e2 != cudaSuccess) return e2;
+                k_align_block<0><<<a.nscans, BLOCK_ALIGN_THREADS, smem, c.stream>>>(a);
+            }
+            return cudaGetLastError();
+        }
+    }
     if (a.pairs) {
         if (a.prm.overlap) return staged ? launch_align_t<1, true, false, true>(c, a) : launch_align_t<1, false, false, true>(c, a);
         return staged ? launch_align_t<0, true, false, true>(c, a) : launch_align_t<0, false, false, true>(c, a);

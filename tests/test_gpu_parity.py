@@ -304,6 +304,29 @@ def test_sweep_matches_oracle(mods, small_world, overlap):
     assert list(bi2[5:]) == [-1, -1, -1] and sorted(bi2[:5]) == [0, 1, 2, 3, 4]
 
 
+@pytest.mark.parametrize("cfg", [dict(res=[0.5]), dict(res=[2.0, 1.0, 0.5]), dict(res=[1.0, 0.5], overlap=1)])
+def test_block_and_warp_align_kernels_agree(mods, small_world, cfg, monkeypatch):
+    """Calls with few scans run one BLOCK per scan (low latency), large batches one WARP per scan (throughput). Both
+    must give the same bytes, and the oracle's: the same ragged batch through a handle forced to each kernel."""
+    from gtsam_ndt_b200 import synth
+    g, oracle = mods
+    scans = [s[:: 1 + i % 3][: len(s) - 7 * i] for i, s in enumerate(small_world["scans"])] + [np.zeros((0, 2), np.float32), small_world["scans"][0][:5]]
+    init = np.vstack([small_world["init"], small_world["init"][:2]])
+    xy, off = synth.pack(scans)
+    out = {}
+    for mode, env in (("warp", "0"), ("block", "100000")):
+        monkeypatch.setenv("NDT2D_BLOCK_ALIGN_MAX", env)
+        m = g.NdtMatcher2D(cfg["res"], overlap=cfg.get("overlap", 0))
+        m.set_target(small_world["map_xy"])
+        out[mode] = m.align_batch(xy, off, init)
+        one = m.align(scans[3], init[3])
+        assert one.tobytes() == out[mode][3].tobytes()
+    o = oracle.Oracle(cfg["res"], overlap=cfg.get("overlap", 0))
+    o.set_target(small_world["map_xy"])
+    ro = o.align_batch(xy, off, init)
+    assert out["warp"].tobytes() == out["block"].tobytes() == ro.tobytes()
+
+
 def _between(a, b):
     c, s_ = math.cos(a[2]), math.sin(a[2])
     dx, dy = b[0] - a[0], b[1] - a[1]
