@@ -277,6 +277,27 @@ def test_solve_matches_numpy():
     assert not ok
 
 
+def test_sincos_spec_is_accurate_and_exact_at_special_angles():
+    """SPEC 4.2: the specified f64 sin/cos sequence is within 1 ulp(1) of libm on the pose range, rounds to the same f32
+    as libm on a dense sample, and is exact where it has to be (0, NaN, infinities, quadrant boundaries' signs)."""
+    rng = np.random.default_rng(9)
+    th = np.concatenate([rng.uniform(-10, 10, 20000), rng.uniform(-1e4, 1e4, 5000), np.arange(-40, 41) * math.pi / 4])
+    worst, bad32 = 0.0, 0
+    for t in th:
+        s, c = oracle.sincos(float(t))
+        worst = max(worst, abs(s - math.sin(t)), abs(c - math.cos(t)))
+        bad32 += np.float32(s) != np.float32(math.sin(t)) or np.float32(c) != np.float32(math.cos(t))
+    assert worst <= 2.3e-16 and bad32 == 0
+    assert oracle.sincos(0.0) == (0.0, 1.0)
+    s, c = oracle.sincos(math.pi / 2)
+    assert s == 1.0 and abs(c) < 1e-16
+    s, c = oracle.sincos(-math.pi)
+    assert c == -1.0 and abs(s) < 2e-16
+    for t in (float("nan"), float("inf"), -float("inf")):
+        s, c = oracle.sincos(t)
+        assert math.isnan(s) and math.isnan(c)
+
+
 def test_align_identity_and_recovery():
     from gtsam_ndt_b200 import synth
     r, p = synth.scans(1, traj_len=1000, first=17, **synth.SCAN_360)
