@@ -21,12 +21,14 @@ def _config(rng, seed=0):
 
 
 @pytest.mark.parametrize("seed", range(10))
-def test_random_configuration_is_bit_identical(small_world, seed):
+def test_random_configuration_is_bit_identical(small_world, seed, monkeypatch):
     import gtsam_ndt_b200 as g
     import oracle
     from gtsam_ndt_b200 import synth
     rng = np.random.default_rng(1000 + seed)
     res, prm, grid = _config(rng, seed)
+    # small batches normally run the block-per-scan kernel; odd seeds force the one-warp-per-scan kernel instead
+    monkeypatch.setenv("NDT2D_BLOCK_ALIGN_MAX", "0" if seed % 2 else "100000")
     m, o = g.NdtMatcher2D(res, **prm), oracle.Oracle(res, **prm)
     if grid:
         m.set_grid(*grid); o.set_grid(*grid)
