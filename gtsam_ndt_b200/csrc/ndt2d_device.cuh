@@ -430,12 +430,6 @@ struct LatticePk {
 // slot of a cell key in a per-target hash table: Fibonacci hashing, bits 15.. of the product (tables have <= 2^16 slots)
 __device__ __forceinline__ unsigned hash_slot(unsigned key, unsigned mask) { return ((key * 0x9E3779B1u) >> 15) & mask; }
 
-// The record of cell `key`: the dense table is indexed directly; a hash table is probed linearly until the key or an empty
-// slot turns up (an empty slot is an all-zero, invalid record: a cell without target points). Outside the lattice: the
-// sentinel record either way.
-template <bool HASH>
-__device__ __forceinline__ Cell4 fetch_cell(const float4 *__restrict__ cells, const LatticePk &G, bool inside, unsigned key);
-
 // SPEC 2 in integers: for a finite f, (f >= 0 && f < (float)nh) == ((unsigned)floor_to_int(f) < nh), because the
 // conversion saturates (huge -> INT_MAX, very negative -> INT_MIN) and rounds (-1, 0) down to -1; inside the
 // lattice floor and SPEC 2's truncation agree. Points are sanitised, so f is never NaN here.
@@ -446,23 +440,6 @@ __device__ __forceinline__ bool cell_base(const LatticePk &G, u64 f, unsigned &b
     const unsigned ix = (unsigned)__float2int_rd(fx), iy = (unsigned)__float2int_rd(fy);
     base = iy * G.njx + ix;
     return (ix < G.nhx) && (iy < G.nhy);
-}
-
-template <bool HASH>
-__device__ __forceinline__ Cell4 fetch_cell(const float4 *__restrict__ cells, const LatticePk &G, bool inside, unsigned key)
-{
-    if (!HASH) return load_cell(cells, inside ? key : G.sentinel);
-    unsigned s = inside ? hash_slot(key, G.mask) : G.sentinel;
-    Cell4 r = load_cell(cells, s);
-    if (inside) {
-        for (;;) {
-            const unsigned k = (unsigned)__float_as_int(lo32(r.nv));
-            if (k == key || k == kEmptyKey) break;
-            s = (s + 1u) & G.mask;
-            r = load_cell(cells, s);
-        }
-    }
-    return r;
 }
 
 template <int OV, bool SMEM, bool HASH = false>
@@ -482,8 +459,8 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
 #pragma unroll
         for (int k = 0; k < Fetched<OV>::NC; ++k) {
             const unsigned o = (k & 1) + (k >> 1) * G.njx;
-            F.cA[k] = fetch_cell<false>(cells, G, inA, bA + o);
-            F.cB[k] = fetch_cell<false>(cells, G, inB, bB + o);
+            F.cA[k] = load_cell(cells, inA ? bA + o : G.sentinel);
+            F.cB[k] = load_cell(cells, inB ? bB + o : G.sentinel);
         }
     } else {
         // hash tables: the first probes of all cells go out together; only then are the (rare) collisions chased
@@ -530,7 +507,7 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
 template <bool FULL, bool TR>
 __device__ __forceinline__ void finish_partials(const Partials &S, int cnt, int lane, Eval &E);
 
-// HASH: L.cells is a per-target hash table (L.hash_mask), see fetch_cell().
+// HASH: L.cells is a per-target hash table (L.hash_mask), probed in fetch().
 template <int OV, bool FULL, bool SMEM, int PIPE, bool TR = false, bool HASH = false>
 __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E)
 {
