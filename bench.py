@@ -443,6 +443,18 @@ def run_build(args):
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / args.steps
     launches = m.kernel_launches - l0
+    # incremental update: one scan's 1080 points added to the finished map, device-resident
+    d_scan = d_maps[0][:1080].contiguous()
+    for _ in range(5):
+        m.add_target_device(d_scan, 1080)
+    torch.cuda.synchronize()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record(stream)
+    for _ in range(50):
+        m.add_target_device(d_scan, 1080)
+    eb.record(stream)
+    torch.cuda.synchronize()
+    add_us = ea.elapsed_time(eb) * 1e3 / 50
     # e2e: host points through ndt2d_set_target (pinned memory, copy in the timed region, host-synchronous)
     h_map = torch.from_numpy(map_xy).pin_memory()
     m.set_target(h_map.numpy())
@@ -471,6 +483,7 @@ def run_build(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                          "kernel": "k_accumulate + k_finalize (+ 3 clears) per level", "peak_source": peak_src, "bytes_per_build": per_build,
                          "convention": "points 8 B per level; per cell: clear 44 B, atomic read-modify-write 88 B, finalise read 44 B, record 32 B"},
+            "incremental_update_us": {"value": add_us, "what": "ndt2d_add_target_device of one 1080-point scan into the finished map (accumulate + finalise), per call"},
             "clocks": clocks}
     print(json.dumps(line), flush=True)
 

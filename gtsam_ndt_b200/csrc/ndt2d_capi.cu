@@ -48,13 +48,15 @@ struct LevelMem {
     float4 *cells = nullptr;
     uint32_t *cnt = nullptr;
     unsigned long long *sums = nullptr;
-    int64_t cap = 0; // cells the three allocations can hold (plus the sentinel record)
+    unsigned *dirty = nullptr; // incremental updates: one word per cell, zero between calls (allocated on the first ndt2d_add_target)
+    int64_t cap = 0; // cells the allocations can hold (plus the sentinel record)
     void release()
     {
         if (cells) cudaFree(cells);
         if (cnt) cudaFree(cnt);
         if (sums) cudaFree(sums);
-        cells = nullptr; cnt = nullptr; sums = nullptr;
+        if (dirty) cudaFree(dirty);
+        cells = nullptr; cnt = nullptr; sums = nullptr; dirty = nullptr;
         cap = 0;
     }
     // Grow-only: scan-to-scan odometry sets a new target of about the same size for every scan, and a
@@ -532,7 +534,23 @@ int ndt2d_add_target_device(ndt2d_matcher *m, const float *d_xy, int64_t n)
     if (!m->has_target) return ndt2d_set_target_device(m, d_xy, n);
     if (!m->sums_valid) return fail(m, NDT2D_EINVAL, "target was loaded with ndt2d_set_cells; it has no sums to extend");
     DeviceGuard g(m->device);
-    return accumulate_and_finalize(m, reinterpret_cast<const float2 *>(d_xy), n);
+    // small additions (a scan into a large map) finalise only the cells they touch; large ones take the dense pass
+    const int K = m->prm.overlap ? 4 : 1;
+    bool sparse = n > 0;
+    for (int l = 0; l < m->nlevels; ++l) sparse = sparse && n * K * 8 < (int64_t)m->lv[l].njx * m->lv[l].njy;
+    if (!sparse) return accumulate_and_finalize(m, reinterpret_cast<const float2 *>(d_xy), n);
+    CK(m, m->b_idx.ensure((size_t)n * K * 4 + 16));
+    for (int l = 0; l < m->nlevels; ++l) {
+        LevelMem &M = m->mem[l];
+        if (!M.dirty) {
+            CK(m, cudaMalloc(&M.dirty, (size_t)M.cap * 4));
+            CK(m, cudaMemsetAsync(M.dirty, 0, (size_t)M.cap * 4, m->cfg.stream));
+        }
+        unsigned *list = m->b_idx.as<unsigned>() + 4;
+        CK(m, launch_add_points(m->cfg, m->lv[l], M.cells, m->prm, reinterpret_cast<const float2 *>(d_xy), n, M.dirty, list,
+                                m->b_idx.as<unsigned>(), &m->launches));
+    }
+    return NDT2D_OK;
 }
 
 int ndt2d_set_target(ndt2d_matcher *m, const float *xy, int64_t n)

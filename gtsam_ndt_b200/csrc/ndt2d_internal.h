@@ -56,6 +56,8 @@ struct LaunchCfg {
 // all launchers return the cudaError_t of the launch; *launches is incremented per kernel launched
 cudaError_t launch_accumulate(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int64_t n, int64_t *launches);
 cudaError_t launch_finalize(const LaunchCfg &c, const LevelDev &L, float4 *cells_out, const ndt2d_params &p, int64_t *launches);
+cudaError_t launch_add_points(const LaunchCfg &c, const LevelDev &L, float4 *cells_out, const ndt2d_params &p, const float2 *d_xy,
+                              int64_t n, unsigned *dirty, unsigned *list, unsigned *nlist, int64_t *launches);
 cudaError_t launch_cell_index(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const double *d_pose,
                               int32_t *d_idx, int64_t *launches);
 cudaError_t launch_point_terms(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const double *d_pose,

@@ -21,8 +21,11 @@ static constexpr unsigned FULL_MASK = 0xffffffffu;
 // same cell in consecutive positions (laser scans are spatially coherent) are combined with a
 // segmented shuffle reduction and only the head of each run issues the integer atomics. Integer
 // sums are associative, so the result is independent of the order of points, warps and atomics.
-template <int OV>
-__global__ void __launch_bounds__(256) k_accumulate(const LevelDev L, const float2 *__restrict__ xy, int64_t n)
+// TOUCH (incremental update): the first run head to reach a cell since the last finalisation (an exchange on the cell's
+// dirty word) appends it to `list`, so that the finalisation can visit the touched cells only.
+template <int OV, bool TOUCH>
+__global__ void __launch_bounds__(256) k_accumulate(const LevelDev L, const float2 *__restrict__ xy, int64_t n, unsigned *__restrict__ dirty,
+                                                    unsigned *__restrict__ list, unsigned *__restrict__ nlist)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -71,6 +74,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const LevelDev L, const floa
                     }
                 }
                 if (head && key >= 0) {
+                    if (TOUCH && atomicExch(dirty + key, 1u) == 0u) list[atomicAdd(nlist, 1u)] = (unsigned)key;
                     atomicAdd(L.cnt + key, (unsigned)c);
                     unsigned long long *s = L.sums + 5 * (size_t)key;
                     atomicAdd(s + 0, (unsigned long long)sx);
@@ -95,6 +99,24 @@ __global__ void __launch_bounds__(256) k_finalize(const LevelDev L, float4 *__re
                         min_points, eig_ratio, ra, rb);
         cells[2 * c] = ra;
         cells[2 * c + 1] = rb;
+    }
+}
+
+// Finalisation of the touched cells only (incremental update): the list is consumed and the dirty words are cleared.
+__global__ void __launch_bounds__(256) k_finalize_list(const LevelDev L, float4 *__restrict__ cells, int min_points, double eig_ratio,
+                                                       unsigned *__restrict__ dirty, const unsigned *__restrict__ list,
+                                                       const unsigned *__restrict__ nlist)
+{
+    const unsigned len = *nlist;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < len; e += gridDim.x * blockDim.x) {
+        const unsigned c = list[e];
+        const long long *s = reinterpret_cast<const long long *>(L.sums) + 5 * (size_t)c;
+        float4 ra, rb;
+        finalize_record(L.cnt[c], s[0], s[1], s[2], s[3], s[4], (int)(c % (unsigned)L.njx), (int)(c / (unsigned)L.njx), L.ox, L.oy, L.st, L.res,
+                        L.ov, min_points, eig_ratio, ra, rb);
+        cells[2 * (size_t)c] = ra;
+        cells[2 * (size_t)c + 1] = rb;
+        dirty[c] = 0u;
     }
 }
 
@@ -893,9 +915,25 @@ cudaError_t launch_accumulate(const LaunchCfg &c, const LevelDev &L, const float
 {
     if (n <= 0) return cudaSuccess;
     int grid = grid_for(n, 256, c.sm_count, 8);
-    if (L.ov) k_accumulate<1><<<grid, 256, 0, c.stream>>>(L, d_xy, n);
-    else k_accumulate<0><<<grid, 256, 0, c.stream>>>(L, d_xy, n);
+    if (L.ov) k_accumulate<1, false><<<grid, 256, 0, c.stream>>>(L, d_xy, n, nullptr, nullptr, nullptr);
+    else k_accumulate<0, false><<<grid, 256, 0, c.stream>>>(L, d_xy, n, nullptr, nullptr, nullptr);
     ++*launches;
+    return cudaGetLastError();
+}
+
+// incremental update: accumulate n points and finalise only the cells they touched. dirty: one zeroed word per cell
+// (left zeroed), list: room for n * (ov ? 4 : 1) cell indices, nlist: one word (zeroed here)
+cudaError_t launch_add_points(const LaunchCfg &c, const LevelDev &L, float4 *cells_out, const ndt2d_params &p, const float2 *d_xy,
+                              int64_t n, unsigned *dirty, unsigned *list, unsigned *nlist, int64_t *launches)
+{
+    if (n <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(nlist, 0, 4, c.stream);
+    if (e != cudaSuccess) return e;
+    int grid = grid_for(n, 256, c.sm_count, 8);
+    if (L.ov) k_accumulate<1, true><<<grid, 256, 0, c.stream>>>(L, d_xy, n, dirty, list, nlist);
+    else k_accumulate<0, true><<<grid, 256, 0, c.stream>>>(L, d_xy, n, dirty, list, nlist);
+    k_finalize_list<<<grid_for(n * (L.ov ? 4 : 1), 256, c.sm_count, 8), 256, 0, c.stream>>>(L, cells_out, p.min_points, p.eig_ratio, dirty, list, nlist);
+    *launches += 2;
     return cudaGetLastError();
 }
 

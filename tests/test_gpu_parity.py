@@ -72,6 +72,27 @@ def test_grid_build_order_independent_and_incremental(mods, small_world):
     assert np.array_equal(m.sums()[1], o.sums()[1])
 
 
+@pytest.mark.parametrize("overlap", [0, 1])
+def test_scan_by_scan_mapping_equals_one_shot(mods, small_world, overlap):
+    """Incremental mapping as a SLAM front end does it: one scan at a time into a large fixed lattice (the sparse path of
+    ndt2d_add_target: only the touched cells are finalised), on a pyramid; every level must equal the oracle's one-shot
+    build from the union of the points, and a further dense rebuild must not be disturbed by the dirty words."""
+    from gtsam_ndt_b200 import synth
+    m, o = make_pair(mods, [1.0, 0.25], (-100.0, -100.0, 200.0, 200.0), overlap=overlap)
+    world = [synth.transform(s, p) for s, p in zip(small_world["scans"][:12], small_world["poses"][:12])]
+    m.set_target(world[0])
+    for w in world[1:]:
+        m.add_target(w)
+    o.set_target(np.concatenate(world))
+    for lv in (0, 1):
+        assert m.cells(lv).tobytes() == o.cells(lv).tobytes()
+        assert np.array_equal(m.sums(lv)[1], o.sums(lv)[1])
+    m.set_target(np.concatenate(world[:3])); m.add_target(world[3])
+    o.set_target(np.concatenate(world[:4]))
+    for lv in (0, 1):
+        assert m.cells(lv).tobytes() == o.cells(lv).tobytes()
+
+
 def test_grid_build_edge_inputs(mods):
     m, o = make_pair(mods, [1.0], min_points=3)
     pts = np.array([[np.nan, 1.0], [np.inf, 0.0], [0.2, 0.2], [0.3, 0.4], [0.5, 0.1], [1e30, 1e30]], np.float32)
