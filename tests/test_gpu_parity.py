@@ -389,6 +389,25 @@ def test_align_pairs_equals_set_target_plus_align(mods, cfg, monkeypatch):
         assert rg[p].tobytes() == ref.tobytes(), (p, t, s_, rg[p], ref)
 
 
+@pytest.mark.parametrize("overlap", [0, 1])
+def test_align_pairs_large_scans(mods, overlap):
+    """Targets with more occupied cells than the build warp's claimed-slot list holds (full-table finalisation) and
+    sources too long for the shared-memory slot (points read from global memory): still set_target + align, byte for byte."""
+    from gtsam_ndt_b200 import synth
+    m, o = make_pair(mods, [1.0], None, overlap=overlap)
+    rng = np.random.default_rng(21)
+    big = np.stack([rng.uniform(-60, 60, 4200), rng.uniform(-60, 60, 4200)], 1).astype(np.float32)      # ~3700 distinct 1 m cells
+    wall = np.stack([np.linspace(-40, 40, 4200), 5.0 + 0.02 * rng.normal(size=4200)], 1).astype(np.float32)
+    scans = [big, wall, (wall + np.float32([0.1, 0.05])).astype(np.float32), big[::2] + np.float32(0.2)]
+    pairs = [(0, 3), (1, 2), (2, 1), (0, 0), (3, 0)]
+    init = np.array([[0.1, 0.1, 0.0], [0.0, 0.0, 0.0], [0.05, 0.0, 0.001], [0.0, 0.0, 0.0], [-0.2, -0.2, 0.0]])
+    xy, off = synth.pack(scans)
+    rg = m.align_pairs(xy, off, pairs, init)
+    for p, (t, s_) in enumerate(pairs):
+        m.set_target(scans[t]); o.set_target(scans[t])
+        assert rg[p].tobytes() == m.align(scans[s_], init[p]).tobytes() == o.align(scans[s_], init[p]).tobytes(), p
+
+
 def test_sweep_publish_world1_equals_sweep(mods, small_world):
     """The peer-memory exchange with a single rank: the arg-max kernel publishes into the rank's own table and the host
     poll returns what ndt2d_sweep returns (index shifted by index_offset); slots are reused as the epochs grow."""
