@@ -2,18 +2,7 @@
 // kernel launches. No CPU compute path exists here: without a CUDA device ndt2d_create fails.
 // Reference interface: none citable (/root/reference/README.md:1 is the whole mount); the entry points
 // implement the matcher operations BASELINE.json's north_star names.
-#include <math.h>
-#include <stdarg.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include <algorithm>
-#include <chrono>
-#include <string>
-#include <vector>
-
-#include "ndt2d_internal.h"
+#include "ndt2d_host.h"
 
 using namespace ndt2d;
 
@@ -21,106 +10,10 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t bytes)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
-};
-
-struct LevelMem {
-    float4 *cells = nullptr;
-    uint32_t *cnt = nullptr;
-    unsigned long long *sums = nullptr;
-    unsigned *dirty = nullptr; // incremental updates: one word per cell, zero between calls (allocated on the first ndt2d_add_target)
-    int64_t cap = 0; // cells the allocations can hold (plus the sentinel record)
-    void release()
-    {
-        if (cells) cudaFree(cells);
-        if (cnt) cudaFree(cnt);
-        if (sums) cudaFree(sums);
-        if (dirty) cudaFree(dirty);
-        cells = nullptr; cnt = nullptr; sums = nullptr; dirty = nullptr;
-        cap = 0;
-    }
-    // Grow-only: scan-to-scan odometry sets a new target of about the same size for every scan, and a
-    // cudaFree/cudaMalloc pair per level and call costs more than building the grid.
-    cudaError_t ensure(int64_t nc)
-    {
-        if (nc <= cap) return cudaSuccess;
-        release();
-        const int64_t want = nc + nc / 4 + 1024;
-        cudaError_t e = cudaMalloc(&cells, (size_t)(want + 1) * 32);
-        if (e == cudaSuccess) e = cudaMalloc(&cnt, (size_t)want * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&sums, (size_t)want * 40);
-        if (e != cudaSuccess) { release(); return e; }
-        cap = want;
-        return cudaSuccess;
-    }
-};
-
 } // namespace
 
-struct ndt2d_matcher {
-    int device = 0;
-    bool own_stream = false;
-    LaunchCfg cfg{};
-    ndt2d_params prm{};
-    int nlevels = 1;
-    float res[NDT2D_MAX_LEVELS] = {1.0f};
-    bool explicit_grid = false;
-    float gox = 0, goy = 0, gex = 0, gey = 0;
-    bool has_target = false;
-    bool sums_valid = false;
-    LevelDev lv[NDT2D_MAX_LEVELS]{};
-    LevelMem mem[NDT2D_MAX_LEVELS];
-    DevBuf b_xy, b_off, b_init, b_res, b_pose, b_out, b_cnt, b_idx, b_terms, b_hyp, b_scores, b_tki, b_tkv, b_scratch,
-        b_counter, b_beams, b_ranges, b_box, b_ptab, b_pcnt, b_psums, b_pgeo, b_ptargets, b_ppairs, b_perr;
-    double beams_amin = 0, beams_ainc = 0;
-    int beams_n = 0;
-    // host-buffer batch calls are cut into chunks: chunk i+1 is copied on copy_stream while chunk i computes
-    static constexpr int MAX_CHUNKS = 16;
-    cudaStream_t copy_stream = nullptr;
-    cudaStream_t work_stream[2] = {nullptr, nullptr}; // chunk kernels alternate so one chunk's tail overlaps the next
-    cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
-    cudaEvent_t ev_begin = nullptr, ev_done[2] = {nullptr, nullptr};
-    // multi-GPU best-hypothesis exchange (ndt2d_exchange_*): own table, the peers' tables opened through CUDA IPC
-    int ex_world = 0, ex_rank = 0, ex_slots = 0;
-    ndt2d_best *ex_table[NDT2D_MAX_RANKS] = {};
-    bool ex_opened[NDT2D_MAX_RANKS] = {};
-    ndt2d_best *ex_host = nullptr; // pinned staging for the host-side poll: two snapshots of the whole table
-    std::vector<char> ex_verified_ok; // per row: the second snapshot holds a verified, complete row
-    int chunk_scans = 0; // NDT2D_CHUNK_SCANS override; 0 = choose by bytes (plan_chunks)
-    // low-latency path of small host-buffer calls (a single align is 3 CUDA calls): pinned staging for one packed upload,
-    // results written by the kernel straight into mapped pinned memory, work-queue counters from a pre-zeroed ring
-    static constexpr size_t FAST_BYTES = 256 << 10;
-    static constexpr int FAST_SCANS = 256, RING = 4096;
-    unsigned char *fast_host = nullptr;      // pinned, FAST_BYTES
-    ndt2d_result *fast_res = nullptr;        // pinned + mapped, FAST_SCANS records
-    ndt2d_result *fast_res_dev = nullptr;    // its device address
-    DevBuf b_fast, b_ring;
-    int ring_pos = 0;
-    int64_t launches = 0;
-    std::string err;
-};
-
-namespace {
+// helpers shared with the other host translation units are declared in ndt2d_host.h
+namespace ndt2d {
 
 int fail(ndt2d_matcher *m, int code, const char *fmt, ...)
 {
@@ -133,27 +26,6 @@ int fail(ndt2d_matcher *m, int code, const char *fmt, ...)
     return code;
 }
 
-#define CK(m, call)                                                                                        \
-    do {                                                                                                   \
-        cudaError_t e_ = (call);                                                                           \
-        if (e_ != cudaSuccess)                                                                             \
-            return fail(m, e_ == cudaErrorMemoryAllocation ? NDT2D_ENOMEM : NDT2D_ECUDA, "%s: %s", #call, \
-                        cudaGetErrorString(e_));                                                           \
-    } while (0)
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev)
-    {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard()
-    {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
 
 // forget the target; keep_memory: the per-level allocations stay for the next target (set_target after set_target)
 void drop_target(ndt2d_matcher *m, bool keep_memory = false)
@@ -326,7 +198,7 @@ int run_pipeline(ndt2d_matcher *m, int nscans, size_t total_bytes, ndt2d_result 
     return rc ? rc : rs;
 }
 
-} // namespace
+} // namespace ndt2d
 
 extern "C" {
 
@@ -938,162 +810,6 @@ int ndt2d_sweep(ndt2d_matcher *m, int level, const float *xy, int n, const float
     return ndt2d_synchronize(m);
 }
 
-// ---- batched scan-to-scan (north_star stage 3, "batched multi-scan"): many (target scan, source scan) pairs per call ----
-
-static unsigned next_pow2(unsigned v)
-{
-    unsigned p = 1;
-    while (p < v) p <<= 1;
-    return p;
-}
-
-// d_xy / d_offsets / d_init / d_res: device; h_offsets / pairs: host (the chunking and the target list are host work).
-// One chunk = as many pairs as fit the table budget. Asynchronous on the handle's stream apart from the uploads of the
-// small per-chunk index lists; *err_out (optional) receives the device error flag after a synchronisation.
-static int align_pairs_impl(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, const int64_t *h_offsets, int nscans,
-                            const int32_t *pairs, int npairs, const double *d_init, ndt2d_result *d_res)
-{
-    int64_t max_src = 0, max_tgt = 0;
-    for (int p = 0; p < npairs; ++p) {
-        const int t = pairs[2 * p], s = pairs[2 * p + 1];
-        if (t < 0 || t >= nscans || s < 0 || s >= nscans) return fail(m, NDT2D_EINVAL, "pair %d: scan index out of range", p);
-        max_tgt = std::max(max_tgt, h_offsets[t + 1] - h_offsets[t]);
-        max_src = std::max(max_src, h_offsets[s + 1] - h_offsets[s]);
-    }
-    const int K = m->prm.overlap ? 4 : 1, L = m->nlevels;
-    // slots per table: 1.5 x the most cells a target can occupy (every point in cells of its own), rounded up to a power
-    // of two: at most 2/3 full in that worst case, typically a quarter (a 1080-beam scan occupies ~500 cells)
-    const uint64_t want = 3ull * (uint64_t)std::max<int64_t>(max_tgt, 16) * K / 2;
-    if (want > 65536) return fail(m, NDT2D_EINVAL, "align_pairs: target scans of %lld points need more than 65536 table slots",
-                                  (long long)max_tgt);
-    const unsigned cap = next_pow2((unsigned)want);
-    const size_t per_target = (size_t)L * (((size_t)cap + 1) * 32 + (size_t)cap * 44 + sizeof(LevelDev));
-    size_t budget = (size_t)8 << 30;
-    if (const char *e = getenv("NDT2D_PAIRS_BYTES")) budget = (size_t)strtoull(e, nullptr, 10);
-    const int tmax = (int)std::max<size_t>(1, std::min<size_t>(budget / per_target, (size_t)nscans));
-    CK(m, m->b_perr.ensure(4));
-    int rc;
-    CK(m, cudaMemsetAsync(m->b_perr.p, 0, 4, m->cfg.stream));
-    std::vector<int32_t> slot((size_t)nscans, -1), targets, resolved;
-    int p0 = 0;
-    while (p0 < npairs) {
-        // the next chunk: pairs in order until the chunk's distinct targets would exceed the budget
-        targets.clear();
-        resolved.clear();
-        int p1 = p0;
-        for (; p1 < npairs; ++p1) {
-            const int t = pairs[2 * p1];
-            if (slot[t] < 0) {
-                if ((int)targets.size() == tmax) break;
-                slot[t] = (int32_t)targets.size();
-                targets.push_back(t);
-            }
-            resolved.push_back(slot[t]);
-            resolved.push_back(pairs[2 * p1 + 1]);
-        }
-        const size_t T = targets.size(), TL = T * (size_t)L;
-        CK(m, m->b_ptab.ensure(TL * ((size_t)cap + 1) * 32));
-        // the accumulators are zero between builds (every finalisation zeroes what it consumed): clear them when they are (re)allocated
-        if (m->b_pcnt.cap < TL * cap * 4 || m->b_psums.cap < TL * cap * 40) {
-            CK(m, cudaStreamSynchronize(m->cfg.stream));
-            CK(m, m->b_pcnt.ensure(TL * cap * 4));
-            CK(m, m->b_psums.ensure(TL * cap * 40));
-            CK(m, cudaMemsetAsync(m->b_pcnt.p, 0, m->b_pcnt.cap, m->cfg.stream));
-            CK(m, cudaMemsetAsync(m->b_psums.p, 0, m->b_psums.cap, m->cfg.stream));
-        }
-        CK(m, m->b_pgeo.ensure(TL * sizeof(LevelDev)));
-        if ((rc = upload(m, m->b_ptargets, targets.data(), T * 4))) return rc;
-        if ((rc = upload(m, m->b_ppairs, resolved.data(), resolved.size() * 4))) return rc;
-        CK(m, cudaStreamSynchronize(m->cfg.stream)); // the vectors are reused by the next chunk
-        PairBuildArgs b;
-        memset(&b, 0, sizeof(b));
-        b.xy = reinterpret_cast<const float2 *>(d_xy);
-        b.offsets = d_offsets;
-        b.targets = m->b_ptargets.as<int32_t>();
-        b.ntargets = (int)T; b.nlevels = L; b.ov = m->prm.overlap; b.explicit_grid = m->explicit_grid ? 1 : 0;
-        for (int l = 0; l < L; ++l) b.res[l] = m->res[l];
-        b.gox = m->gox; b.goy = m->goy; b.gex = m->gex; b.gey = m->gey;
-        b.min_points = m->prm.min_points; b.eig_ratio = m->prm.eig_ratio;
-        b.cap = cap;
-        b.tab = m->b_ptab.as<float4>(); b.cnt = m->b_pcnt.as<uint32_t>(); b.sums = m->b_psums.as<unsigned long long>();
-        b.geo = m->b_pgeo.as<LevelDev>();
-        b.error = m->b_perr.as<int>();
-        CK(m, launch_pairs_build(m->cfg, b, &m->launches));
-        AlignArgs a;
-        fill_align_args(m, a);
-        a.xy = reinterpret_cast<const float2 *>(d_xy);
-        if (!a.xy) a.xy = m->b_counter.as<float2>();
-        a.offsets = d_offsets;
-        a.pairs = m->b_ppairs.as<int32_t>();
-        a.geo = m->b_pgeo.as<LevelDev>();
-        a.init = d_init + 3 * (size_t)p0;
-        a.res = d_res + p0;
-        a.nscans = p1 - p0;
-        a.cap_points = align_cap_points(m, (int)max_src);
-        CK(m, launch_align(m->cfg, a, &m->launches));
-        for (int32_t t : targets) slot[t] = -1;
-        p0 = p1;
-    }
-    return NDT2D_OK;
-}
-
-static int align_pairs_check(ndt2d_matcher *m)
-{
-    int err = 0;
-    CK(m, cudaMemcpyAsync(&err, m->b_perr.p, 4, cudaMemcpyDeviceToHost, m->cfg.stream));
-    int rc = ndt2d_synchronize(m);
-    if (rc) return rc;
-    if (err) return fail(m, NDT2D_EINVAL, "align_pairs: the auto-fitted lattice of a target scan exceeds 2^31 cells "
-                                          "(a point far from the rest?); its pairs were returned with status NO_OVERLAP");
-    return NDT2D_OK;
-}
-
-static int align_pairs_validate(ndt2d_matcher *m, const int64_t *offsets, int nscans, const int32_t *pairs, int npairs)
-{
-    if (nscans < 0 || npairs < 0 || (nscans > 0 && !offsets) || (npairs > 0 && !pairs)) return fail(m, NDT2D_EINVAL, "bad arguments");
-    if (m->nlevels < 1) return fail(m, NDT2D_EINVAL, "no resolution set");
-    for (int b = 0; b < nscans; ++b) {
-        int64_t nb = offsets[b + 1] - offsets[b];
-        if (nb < 0 || nb > 0x7fffffff) return fail(m, NDT2D_EINVAL, "offsets not monotone at scan %d", b);
-    }
-    if (nscans > 0 && offsets[0] < 0) return fail(m, NDT2D_EINVAL, "bad offsets");
-    return NDT2D_OK;
-}
-
-int ndt2d_align_pairs_device(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, const int64_t *offsets, int nscans,
-                             const int32_t *pairs, int npairs, const double *d_init, ndt2d_result *d_res)
-{
-    if (!m) return NDT2D_EINVAL;
-    int rc = align_pairs_validate(m, offsets, nscans, pairs, npairs);
-    if (rc) return rc;
-    if (npairs == 0) return NDT2D_OK;
-    if (!d_offsets || !d_init || !d_res) return fail(m, NDT2D_EINVAL, "bad arguments");
-    DeviceGuard g(m->device);
-    return align_pairs_impl(m, d_xy, d_offsets, offsets, nscans, pairs, npairs, d_init, d_res);
-}
-
-int ndt2d_align_pairs(ndt2d_matcher *m, const float *xy, const int64_t *offsets, int nscans, const int32_t *pairs, int npairs,
-                      const double *init, ndt2d_result *res)
-{
-    if (!m) return NDT2D_EINVAL;
-    int rc = align_pairs_validate(m, offsets, nscans, pairs, npairs);
-    if (rc) return rc;
-    if (npairs == 0) return NDT2D_OK;
-    if (!init || !res) return fail(m, NDT2D_EINVAL, "bad arguments");
-    const int64_t total = offsets[nscans];
-    if (total > 0 && !xy) return fail(m, NDT2D_EINVAL, "bad offsets / xy");
-    DeviceGuard g(m->device);
-    if ((rc = upload(m, m->b_xy, xy, (size_t)total * 8))) return rc;
-    if ((rc = upload(m, m->b_off, offsets, (size_t)(nscans + 1) * 8))) return rc;
-    if ((rc = upload(m, m->b_init, init, (size_t)npairs * 24))) return rc;
-    CK(m, m->b_res.ensure((size_t)npairs * sizeof(ndt2d_result)));
-    rc = align_pairs_impl(m, m->b_xy.as<float>(), m->b_off.as<int64_t>(), offsets, nscans, pairs, npairs, m->b_init.as<double>(),
-                          m->b_res.as<ndt2d_result>());
-    if (rc) return rc;
-    CK(m, cudaMemcpyAsync(res, m->b_res.p, (size_t)npairs * sizeof(ndt2d_result), cudaMemcpyDeviceToHost, m->cfg.stream));
-    return align_pairs_check(m);
-}
-
 int ndt2d_relocalize(ndt2d_matcher *m, int level, const float *xy, int n, const float *hyp, int64_t nhyp, int k,
                      int64_t *best_idx, ndt2d_result *res)
 {
@@ -1119,164 +835,6 @@ int ndt2d_relocalize(ndt2d_matcher *m, int level, const float *xy, int n, const 
         memset(res + j, 0, sizeof(ndt2d_result));
         res[j].status = NDT2D_NO_OVERLAP;
     }
-    return NDT2D_OK;
-}
-
-// ---- multi-GPU best-hypothesis exchange over peer memory -------------------------------------------------------
-
-int ndt2d_exchange_close(ndt2d_matcher *m)
-{
-    if (!m) return NDT2D_EINVAL;
-    if (m->ex_world == 0) return NDT2D_OK;
-    DeviceGuard g(m->device);
-    cudaStreamSynchronize(m->cfg.stream);
-    for (int r = 0; r < m->ex_world; ++r) {
-        if (r != m->ex_rank && m->ex_opened[r]) cudaIpcCloseMemHandle(m->ex_table[r]);
-        m->ex_opened[r] = false;
-        if (r != m->ex_rank) m->ex_table[r] = nullptr;
-    }
-    if (m->ex_table[m->ex_rank]) cudaFree(m->ex_table[m->ex_rank]);
-    m->ex_table[m->ex_rank] = nullptr;
-    if (m->ex_host) cudaFreeHost(m->ex_host);
-    m->ex_host = nullptr;
-    m->ex_world = m->ex_rank = m->ex_slots = 0;
-    return NDT2D_OK;
-}
-
-int ndt2d_exchange_create(ndt2d_matcher *m, int world, int rank, int nslots, unsigned char *handle)
-{
-    if (!m || !handle) return NDT2D_EINVAL;
-    if (world < 1 || world > NDT2D_MAX_RANKS || rank < 0 || rank >= world || nslots < 1 || nslots > 4096)
-        return fail(m, NDT2D_EINVAL, "exchange: world %d (max %d), rank %d, nslots %d", world, NDT2D_MAX_RANKS, rank, nslots);
-    static_assert(sizeof(cudaIpcMemHandle_t) == NDT2D_IPC_HANDLE_BYTES, "CUDA IPC handle size");
-    static_assert(sizeof(ndt2d_best) == 32, "ndt2d_best is 32 bytes");
-    ndt2d_exchange_close(m);
-    DeviceGuard g(m->device);
-    const size_t bytes = (size_t)nslots * world * sizeof(ndt2d_best);
-    ndt2d_best *own = nullptr;
-    CK(m, cudaMalloc(reinterpret_cast<void **>(&own), bytes)); // its own allocation: IPC handles name whole allocations
-    cudaError_t e = cudaMemset(own, 0, bytes);                 // epoch 0 = nothing published
-    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&m->ex_host), 2 * bytes, cudaHostAllocDefault);
-    cudaIpcMemHandle_t h;
-    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, own);
-    if (e != cudaSuccess) {
-        cudaFree(own);
-        if (m->ex_host) cudaFreeHost(m->ex_host);
-        m->ex_host = nullptr;
-        return fail(m, NDT2D_ECUDA, "exchange_create: %s", cudaGetErrorString(e));
-    }
-    memcpy(handle, &h, sizeof(h));
-    m->ex_world = world; m->ex_rank = rank; m->ex_slots = nslots;
-    m->ex_table[rank] = own;
-    m->ex_verified_ok.assign((size_t)nslots, 0);
-    return NDT2D_OK;
-}
-
-int ndt2d_exchange_open(ndt2d_matcher *m, const unsigned char *handles)
-{
-    if (!m || !handles) return NDT2D_EINVAL;
-    if (m->ex_world == 0) return fail(m, NDT2D_EINVAL, "exchange_open before exchange_create");
-    DeviceGuard g(m->device);
-    for (int r = 0; r < m->ex_world; ++r) {
-        if (r == m->ex_rank || m->ex_opened[r]) continue;
-        cudaIpcMemHandle_t h;
-        memcpy(&h, handles + (size_t)r * NDT2D_IPC_HANDLE_BYTES, sizeof(h));
-        void *p = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) return fail(m, NDT2D_ECUDA, "exchange_open: rank %d's table: %s", r, cudaGetErrorString(e));
-        m->ex_table[r] = static_cast<ndt2d_best *>(p);
-        m->ex_opened[r] = true;
-    }
-    return NDT2D_OK;
-}
-
-int ndt2d_sweep_publish(ndt2d_matcher *m, int level, const float *d_xy, int n, const float *d_hyp, int64_t nhyp,
-                        double *d_scores, int64_t index_offset, uint64_t query)
-{
-    int rc = check_level(m, level);
-    if (rc) return rc;
-    if (m->ex_world == 0) return fail(m, NDT2D_EINVAL, "sweep_publish before exchange_create");
-    for (int r = 0; r < m->ex_world; ++r)
-        if (!m->ex_table[r]) return fail(m, NDT2D_EINVAL, "sweep_publish: rank %d's table is not open (ndt2d_exchange_open)", r);
-    if (n < 0 || nhyp < 0 || (nhyp > 0 && !d_hyp)) return fail(m, NDT2D_EINVAL, "bad arguments");
-    DeviceGuard g(m->device);
-    if (!d_scores) {
-        CK(m, m->b_scores.ensure((size_t)(nhyp ? nhyp : 1) * 8));
-        d_scores = m->b_scores.as<double>();
-    }
-    CK(m, m->b_tki.ensure(8));
-    CK(m, m->b_tkv.ensure(8));
-    CK(m, launch_eval_poses(m->cfg, m->lv[level], reinterpret_cast<const float2 *>(d_xy), n, d_hyp, 1, nhyp, 0, d_scores, 1,
-                            nullptr, &m->launches));
-    PublishArgs pub;
-    memset(&pub, 0, sizeof(pub));
-    for (int r = 0; r < m->ex_world; ++r) pub.table[r] = m->ex_table[r];
-    pub.world = m->ex_world; pub.rank = m->ex_rank; pub.row = (int)(query % (uint64_t)m->ex_slots);
-    pub.index_offset = index_offset;
-    pub.epoch = query + 1;
-    CK(m, launch_topk(m->cfg, d_scores, nhyp, 1, m->b_tki.as<int64_t>(), m->b_tkv.as<double>(), m->b_scratch.as<unsigned long long>(),
-                      &m->launches, &pub));
-    return NDT2D_OK;
-}
-
-// best of one complete row by (-score, index), SPEC 6
-static void exchange_pick(const ndt2d_best *row, int W, int64_t *best_index, double *best_score)
-{
-    int64_t bi = -1;
-    double bs = 0.0;
-    for (int r = 0; r < W; ++r) {
-        const ndt2d_best &b = row[r];
-        if (b.index < 0 || b.score != b.score) continue;
-        if (bi < 0 || b.score > bs || (b.score == bs && b.index < bi)) { bi = b.index; bs = b.score; }
-    }
-    *best_index = bi;
-    *best_score = bs;
-}
-
-// The poll copies the WHOLE table (nslots x world x 32 B, a few KB) to pinned memory on the copy stream, so that it never
-// waits for kernels queued on the handle's stream. A row is trusted only from a snapshot taken after an earlier snapshot
-// already showed all its epochs (record, system fence, epoch: a complete epoch guarantees the record was written before
-// the later copy started). The verified snapshot is kept, so waiting for several finished queries costs two copies in all.
-int ndt2d_exchange_wait(ndt2d_matcher *m, uint64_t query, int timeout_ms, int64_t *best_index, double *best_score)
-{
-    if (!m || !best_index || !best_score) return NDT2D_EINVAL;
-    if (m->ex_world == 0) return fail(m, NDT2D_EINVAL, "exchange_wait before exchange_create");
-    DeviceGuard g(m->device);
-    const int W = m->ex_world;
-    const size_t rows = (size_t)m->ex_slots, bytes = rows * W * sizeof(ndt2d_best);
-    const size_t row = (size_t)(query % (uint64_t)m->ex_slots);
-    ndt2d_best *probe = m->ex_host, *verified = m->ex_host + rows * W;
-    auto complete = [&](const ndt2d_best *t) {
-        for (int r = 0; r < W; ++r)
-            if (t[row * W + r].epoch != query + 1) return false;
-        return true;
-    };
-    if (m->ex_verified_ok[row] && complete(verified)) {
-        exchange_pick(verified + row * W, W, best_index, best_score);
-        return NDT2D_OK;
-    }
-    const auto t0 = std::chrono::steady_clock::now();
-    for (;;) {
-        CK(m, cudaMemcpyAsync(probe, m->ex_table[m->ex_rank], bytes, cudaMemcpyDeviceToHost, m->copy_stream));
-        CK(m, cudaStreamSynchronize(m->copy_stream));
-        if (complete(probe)) break;
-        const auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
-        if (ms > timeout_ms) return fail(m, NDT2D_ETIMEOUT, "exchange_wait: query %llu not published by every rank within %d ms",
-                                         (unsigned long long)query, timeout_ms);
-    }
-    CK(m, cudaMemcpyAsync(verified, m->ex_table[m->ex_rank], bytes, cudaMemcpyDeviceToHost, m->copy_stream));
-    CK(m, cudaStreamSynchronize(m->copy_stream));
-    for (size_t q = 0; q < rows; ++q) {   // a row of the second snapshot is verified if the first one already showed it complete
-        bool same = true;
-        for (int r = 0; r < W; ++r)
-            same = same && probe[q * W + r].epoch == verified[q * W + r].epoch && probe[q * W + r].epoch == probe[q * W].epoch &&
-                   probe[q * W].epoch != 0;
-        m->ex_verified_ok[q] = same;
-    }
-    if (!m->ex_verified_ok[row] || !complete(verified))   // the row moved on between the two copies: slot discipline broken
-        return fail(m, NDT2D_EINVAL, "exchange_wait: row of query %llu was overwritten while waiting (see the slot discipline in ndt2d.h)",
-                    (unsigned long long)query);
-    exchange_pick(verified + row * W, W, best_index, best_score);
     return NDT2D_OK;
 }
 

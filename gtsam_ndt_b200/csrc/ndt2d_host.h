@@ -1,0 +1,151 @@
+// Host-side internals shared by the C-ABI translation units (ndt2d_capi.cu, ndt2d_pairs.cu, ndt2d_exchange.cu):
+// the handle, its device buffers, error reporting and the helpers every entry point uses. Not part of the ABI.
+#pragma once
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "ndt2d_internal.h"
+
+namespace ndt2d {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct LevelMem {
+    float4 *cells = nullptr;
+    uint32_t *cnt = nullptr;
+    unsigned long long *sums = nullptr;
+    unsigned *dirty = nullptr; // incremental updates: one word per cell, zero between calls (allocated on the first ndt2d_add_target)
+    int64_t cap = 0; // cells the allocations can hold (plus the sentinel record)
+    void release()
+    {
+        if (cells) cudaFree(cells);
+        if (cnt) cudaFree(cnt);
+        if (sums) cudaFree(sums);
+        if (dirty) cudaFree(dirty);
+        cells = nullptr; cnt = nullptr; sums = nullptr; dirty = nullptr;
+        cap = 0;
+    }
+    // Grow-only: scan-to-scan odometry sets a new target of about the same size for every scan, and a
+    // cudaFree/cudaMalloc pair per level and call costs more than building the grid.
+    cudaError_t ensure(int64_t nc)
+    {
+        if (nc <= cap) return cudaSuccess;
+        release();
+        const int64_t want = nc + nc / 4 + 1024;
+        cudaError_t e = cudaMalloc(&cells, (size_t)(want + 1) * 32);
+        if (e == cudaSuccess) e = cudaMalloc(&cnt, (size_t)want * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&sums, (size_t)want * 40);
+        if (e != cudaSuccess) { release(); return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+};
+
+
+} // namespace ndt2d
+
+struct ndt2d_matcher {
+    int device = 0;
+    bool own_stream = false;
+    ndt2d::LaunchCfg cfg{};
+    ndt2d_params prm{};
+    int nlevels = 1;
+    float res[NDT2D_MAX_LEVELS] = {1.0f};
+    bool explicit_grid = false;
+    float gox = 0, goy = 0, gex = 0, gey = 0;
+    bool has_target = false;
+    bool sums_valid = false;
+    ndt2d::LevelDev lv[NDT2D_MAX_LEVELS]{};
+    ndt2d::LevelMem mem[NDT2D_MAX_LEVELS];
+    ndt2d::DevBuf b_xy, b_off, b_init, b_res, b_pose, b_out, b_cnt, b_idx, b_terms, b_hyp, b_scores, b_tki, b_tkv, b_scratch,
+        b_counter, b_beams, b_ranges, b_box, b_ptab, b_pcnt, b_psums, b_pgeo, b_ptargets, b_ppairs, b_perr;
+    double beams_amin = 0, beams_ainc = 0;
+    int beams_n = 0;
+    // host-buffer batch calls are cut into chunks: chunk i+1 is copied on copy_stream while chunk i computes
+    static constexpr int MAX_CHUNKS = 16;
+    cudaStream_t copy_stream = nullptr;
+    cudaStream_t work_stream[2] = {nullptr, nullptr}; // chunk kernels alternate so one chunk's tail overlaps the next
+    cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
+    cudaEvent_t ev_begin = nullptr, ev_done[2] = {nullptr, nullptr};
+    // multi-GPU best-hypothesis exchange (ndt2d_exchange_*): own table, the peers' tables opened through CUDA IPC
+    int ex_world = 0, ex_rank = 0, ex_slots = 0;
+    ndt2d_best *ex_table[NDT2D_MAX_RANKS] = {};
+    bool ex_opened[NDT2D_MAX_RANKS] = {};
+    ndt2d_best *ex_host = nullptr; // pinned staging for the host-side poll: two snapshots of the whole table
+    std::vector<char> ex_verified_ok; // per row: the second snapshot holds a verified, complete row
+    int chunk_scans = 0; // NDT2D_CHUNK_SCANS override; 0 = choose by bytes (plan_chunks)
+    // low-latency path of small host-buffer calls (a single align is 3 CUDA calls): pinned staging for one packed upload,
+    // results written by the kernel straight into mapped pinned memory, work-queue counters from a pre-zeroed ring
+    static constexpr size_t FAST_BYTES = 256 << 10;
+    static constexpr int FAST_SCANS = 256, RING = 4096;
+    unsigned char *fast_host = nullptr;      // pinned, FAST_BYTES
+    ndt2d_result *fast_res = nullptr;        // pinned + mapped, FAST_SCANS records
+    ndt2d_result *fast_res_dev = nullptr;    // its device address
+    ndt2d::DevBuf b_fast, b_ring;
+    int ring_pos = 0;
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace ndt2d {
+
+// records the message (ndt2d_last_error) and returns `code`
+int fail(ndt2d_matcher *m, int code, const char *fmt, ...);
+
+#define CK(m, call)                                                                                        \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(m, e_ == cudaErrorMemoryAllocation ? NDT2D_ENOMEM : NDT2D_ECUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e_));                                                           \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int check_level(ndt2d_matcher *m, int level);
+int upload(ndt2d_matcher *m, DevBuf &b, const void *src, size_t bytes);
+int align_cap_points(const ndt2d_matcher *m, int max_points);
+void fill_align_args(ndt2d_matcher *m, AlignArgs &a);
+
+} // namespace ndt2d

@@ -121,197 +121,6 @@ __global__ void __launch_bounds__(256) k_finalize_list(const LevelDev L, float4 
 }
 
 // ------------------------------------------------------------------------------------------------
-// (1b) batched scan-to-scan: one grid per target scan, one warp per (target, level)
-// ------------------------------------------------------------------------------------------------
-
-// Same arithmetic as the dense build (SPEC 2 auto-fit lattice, SPEC 3 integer sums and finalisation), so every record
-// equals the one ndt2d_set_target(scan) would produce; only the container differs: a scan touches a few hundred of
-// the cells of its bounding box, so the cells live in an open-addressing hash table keyed by the dense cell index.
-static constexpr int PAIRS_LIST_CAP = 2304; // claimed-slot list per warp (u16 entries, 36 KB per block); longer: full-table scan
-
-template <int OV>
-__global__ void __launch_bounds__(256) k_pairs_build(const PairBuildArgs a)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wid >= (int64_t)a.ntargets * a.nlevels) return;
-    const int t = (int)(wid / a.nlevels), l = (int)(wid % a.nlevels);
-    // slots this warp claimed, so that the finalisation visits the few hundred occupied slots instead of the whole table
-    __shared__ unsigned short s_list[8][PAIRS_LIST_CAP];
-    __shared__ int s_nlist[8];
-    const int w = threadIdx.x >> 5;
-    if (lane == 0) s_nlist[w] = 0;
-    const int scan = __ldg(a.targets + t);
-    const int64_t o0 = __ldg(a.offsets + scan), o1 = __ldg(a.offsets + scan + 1);
-    const int n = (int)(o1 - o0);
-    const float2 *__restrict__ src = a.xy + o0;
-
-    // SPEC 2 auto-fit: bounding box of the finite points (min and max are order independent)
-    float xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY;
-    if (!a.explicit_grid) {
-        for (int i = lane; i < n; i += 32) {
-            float2 p = __ldg(src + i);
-            if (!isfinite(p.x) || !isfinite(p.y)) continue;
-            xmin = fminf(xmin, p.x); xmax = fmaxf(xmax, p.x);
-            ymin = fminf(ymin, p.y); ymax = fmaxf(ymax, p.y);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            xmin = fminf(xmin, __shfl_xor_sync(FULL_MASK, xmin, o));
-            ymin = fminf(ymin, __shfl_xor_sync(FULL_MASK, ymin, o));
-            xmax = fmaxf(xmax, __shfl_xor_sync(FULL_MASK, xmax, o));
-            ymax = fmaxf(ymax, __shfl_xor_sync(FULL_MASK, ymax, o));
-        }
-    }
-    // geometry, the f32 expressions of setup_level() in ndt2d_capi.cu (every lane computes the same values)
-    LevelDev L;
-    L.res = a.res[l];
-    L.ov = a.ov;
-    L.st = L.ov ? __fmul_rn(L.res, 0.5f) : L.res;
-    L.inv_st = __fdiv_rn(1.0f, L.st);
-    if (a.explicit_grid) {
-        L.ox = a.gox; L.oy = a.goy;
-        L.nhx = (int)ceilf(__fdiv_rn(a.gex, L.st));
-        L.nhy = (int)ceilf(__fdiv_rn(a.gey, L.st));
-    } else {
-        if (!(xmin <= xmax)) { xmin = xmax = ymin = ymax = 0.0f; }
-        L.ox = __fsub_rn(__fmul_rn(floorf(__fdiv_rn(xmin, L.res)), L.res), L.res);
-        L.oy = __fsub_rn(__fmul_rn(floorf(__fdiv_rn(ymin, L.res)), L.res), L.res);
-        L.nhx = (int)ceilf(__fdiv_rn(__fsub_rn(xmax, L.ox), L.st)) + 2;
-        L.nhy = (int)ceilf(__fdiv_rn(__fsub_rn(ymax, L.oy), L.st)) + 2;
-    }
-    bool too_big = L.nhx < 1 || L.nhy < 1 || (int64_t)(L.nhx + L.ov) * (int64_t)(L.nhy + L.ov) >= ((int64_t)1 << 31);
-    if (too_big) { L.nhx = L.nhy = 0; }      // nothing is inside: every align against this target ends NO_OVERLAP
-    L.njx = L.nhx + L.ov;
-    L.njy = L.nhy + L.ov;
-    L.nhxf = (float)L.nhx;
-    L.nhyf = (float)L.nhy;
-    L.hash_mask = a.cap - 1u;
-    float4 *rec = a.tab + (size_t)wid * ((size_t)a.cap + 1) * 2;
-    uint32_t *cnt = a.cnt + (size_t)wid * a.cap;
-    unsigned long long *sums = a.sums + (size_t)wid * a.cap * 5;
-    L.cells = rec;
-    L.cnt = cnt;
-    L.sums = sums;
-    if (lane == 0) {
-        a.geo[wid] = L;
-        if (too_big) atomicMax(a.error, t + 1);
-    }
-
-    // clear the records: empty key in every slot's `n` word; the sentinel record after the last slot
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 empty = make_float4(0.f, 0.f, __int_as_float((int)kEmptyKey), 0.f);
-    for (unsigned s = lane; s <= a.cap; s += 32) {
-        rec[2 * (size_t)s] = zero;
-        rec[2 * (size_t)s + 1] = s < a.cap ? empty : zero;
-    }
-    // (cnt and sums are zero on entry: they are zeroed when allocated and every finalisation zeroes what it consumed)
-    __syncwarp();
-
-    // SPEC 3 accumulation, as k_accumulate: runs of equal cells are combined in the warp, run heads find or claim the
-    // cell's slot (compare-and-swap on the key word) and add into its integer sums
-    unsigned *keyword = reinterpret_cast<unsigned *>(rec);   // key of slot s = word 8 s + 6
-    constexpr int K = OV ? 2 : 1;
-    float2 pnext = lane < n ? __ldg(src + lane) : make_float2(0.f, 0.f);   // the next window's point is requested one window ahead
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const float2 p = pnext;
-        if (i + 32 < n) pnext = __ldg(src + i + 32);
-        float X = 0.0f, Y = 0.0f;
-        bool inside = false;
-        int hx = 0, hy = 0;
-        if (i < n) {
-            X = p.x;
-            Y = p.y;
-            inside = lattice(L, X, Y, hx, hy);
-        }
-#pragma unroll
-        for (int b = 0; b < K; ++b) {
-#pragma unroll
-            for (int aa = 0; aa < K; ++aa) {
-                int jx = hx + aa, jy = hy + b;
-                int key = inside ? jy * L.njx + jx : -1;
-                double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
-                double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
-                double dx = (double)X - cx, dy = (double)Y - cy;
-                long long qx = inside ? __double2ll_rn(dx * 1048576.0) : 0;
-                long long qy = inside ? __double2ll_rn(dy * 1048576.0) : 0;
-                int c = inside ? 1 : 0;
-                long long sx = qx, sy = qy, sxx = qx * qx, sxy = qx * qy, syy = qy * qy;
-                int prev = __shfl_up_sync(FULL_MASK, key, 1);
-                bool head = (lane == 0) || (prev != key);
-                unsigned heads = __ballot_sync(FULL_MASK, head);
-                int rid = __popc(heads & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int rid2 = __shfl_down_sync(FULL_MASK, rid, d);
-                    int c2 = __shfl_down_sync(FULL_MASK, c, d);
-                    long long sx2 = __shfl_down_sync(FULL_MASK, sx, d);
-                    long long sy2 = __shfl_down_sync(FULL_MASK, sy, d);
-                    long long sxx2 = __shfl_down_sync(FULL_MASK, sxx, d);
-                    long long sxy2 = __shfl_down_sync(FULL_MASK, sxy, d);
-                    long long syy2 = __shfl_down_sync(FULL_MASK, syy, d);
-                    if (lane + d < 32 && rid2 == rid) {
-                        c += c2; sx += sx2; sy += sy2; sxx += sxx2; sxy += sxy2; syy += syy2;
-                    }
-                }
-                if (head && key >= 0) {
-                    unsigned s = hash_slot((unsigned)key, L.hash_mask);
-                    bool placed = false;
-                    // the table is at most 2/3 full by construction; the probe count is bounded all the same, so that
-                    // inconsistent arguments (offsets on the device that differ from the host copy) cannot hang the GPU
-                    for (unsigned probes = 0; probes <= L.hash_mask; ++probes) {
-                        unsigned was = atomicCAS(keyword + 8 * (size_t)s + 6, kEmptyKey, (unsigned)key);
-                        if (was == kEmptyKey) {
-                            const int pos = atomicAdd(&s_nlist[w], 1);
-                            if (pos < PAIRS_LIST_CAP) s_list[w][pos] = (unsigned short)s;
-                            placed = true;
-                            break;
-                        }
-                        if (was == (unsigned)key) { placed = true; break; }
-                        s = (s + 1u) & L.hash_mask;
-                    }
-                    if (!placed) { atomicMax(a.error, t + 1); continue; }
-                    atomicAdd(cnt + s, (unsigned)c);
-                    unsigned long long *q = sums + 5 * (size_t)s;
-                    atomicAdd(q + 0, (unsigned long long)sx);
-                    atomicAdd(q + 1, (unsigned long long)sy);
-                    atomicAdd(q + 2, (unsigned long long)sxx);
-                    atomicAdd(q + 3, (unsigned long long)sxy);
-                    atomicAdd(q + 4, (unsigned long long)syy);
-                }
-            }
-        }
-    }
-    __threadfence();
-    __syncwarp();
-
-    // SPEC 3 finalisation of the occupied slots; the key stays in the record's `n` word for the probing reader, and the
-    // slot's sums go back to zero for the next build that uses this memory
-    auto finish = [&](unsigned s) {
-        const unsigned key = *(volatile unsigned *)(keyword + 8 * (size_t)s + 6);
-        if (key == kEmptyKey) return;
-        const unsigned nn = *(volatile uint32_t *)(cnt + s);
-        volatile long long *q = reinterpret_cast<volatile long long *>(sums + 5 * (size_t)s);
-        const long long q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
-        float4 ra, rb;
-        finalize_record(nn, q0, q1, q2, q3, q4, (int)(key % (unsigned)L.njx), (int)(key / (unsigned)L.njx), L.ox, L.oy, L.st, L.res,
-                        L.ov, a.min_points, a.eig_ratio, ra, rb);
-        rb.z = __int_as_float((int)key);
-        rec[2 * (size_t)s] = ra;
-        rec[2 * (size_t)s + 1] = rb;
-        cnt[s] = 0u;
-        q[0] = 0; q[1] = 0; q[2] = 0; q[3] = 0; q[4] = 0;
-    };
-    const int nlist = s_nlist[w];
-    if (nlist <= PAIRS_LIST_CAP) {
-        for (int e = lane; e < nlist; e += 32) finish(s_list[w][e]);
-    } else {
-        for (unsigned s = lane; s < a.cap; s += 32) finish(s);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // (2a) small per-point kernels used by the API's diagnostic entry points
 // ------------------------------------------------------------------------------------------------
 
@@ -1034,17 +843,6 @@ static cudaError_t launch_align_t(const LaunchCfg &c, const AlignArgs &a)
 #endif
     int grid = grid_for(a.nscans, ALIGN_THREADS / 32, c.sm_count, per_sm);
     kern<<<grid, ALIGN_THREADS, smem, c.stream>>>(a);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_pairs_build(const LaunchCfg &c, const PairBuildArgs &a, int64_t *launches)
-{
-    const int64_t warps = (int64_t)a.ntargets * a.nlevels;
-    if (warps <= 0) return cudaSuccess;
-    const int grid = (int)((warps + 7) / 8);
-    if (a.ov) k_pairs_build<1><<<grid, 256, 0, c.stream>>>(a);
-    else k_pairs_build<0><<<grid, 256, 0, c.stream>>>(a);
-    ++*launches;
     return cudaGetLastError();
 }
 
