@@ -62,8 +62,9 @@ int setup_level(ndt2d_matcher *m, int l, const float bbox[4])
     if (L.nhx < 1 || L.nhy < 1) return fail(m, NDT2D_EINVAL, "level %d: empty lattice (%d x %d)", l, L.nhx, L.nhy);
     L.njx = L.nhx + L.ov;
     L.njy = L.nhy + L.ov;
-    L.nhxf = (float)L.nhx;
-    L.nhyf = (float)L.nhy;
+    L.inv_std = 1.0 / (double)L.st;
+    L.qs = 4194304.0 / (double)L.res;
+    L.qu = (double)L.res * (1.0 / 4194304.0);
     int64_t nc = (int64_t)L.njx * L.njy;
     if (nc >= (int64_t)1 << 31) return fail(m, NDT2D_EINVAL, "level %d: %lld cells exceed 2^31", l, (long long)nc);
     LevelMem &M = m->mem[l];

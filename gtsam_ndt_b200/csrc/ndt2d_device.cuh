@@ -1,4 +1,4 @@
-// Device-side building blocks of the 2D NDT path: lattice index (SPEC 2), per-pair terms (SPEC 4),
+// Device-side building blocks of the 2D NDT path: lattice index (SPEC 2, f64), per-pair terms (SPEC 4, cell-local f32),
 // expneg (SPEC 4.1), the warp evaluation with SPEC 4's fixed summation order, and the damped closed-form 3x3 solve
 // (SPEC 5). Compiled with -fmad=false: only the explicit fma calls below fuse, exactly as SPEC.md writes them.
 // Reference file:line: none exists (/root/reference/README.md:1 is the whole mount).
@@ -47,26 +47,40 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f3
 // lo + hi of a packed product pair: the "a*b + c*d" of SPEC 4 (two rounded products, one add)
 __device__ __forceinline__ float hsum(u64 v) { float a, b; upk(v, a, b); return __fadd_rn(a, b); }
 
-// ---- SPEC 2: lattice index (scalar form, used by the small kernels) -----------------------------------
-__device__ __forceinline__ bool lattice(const LevelDev &L, float X, float Y, int &hx, int &hy)
+// ---- SPEC 2 (v4): lattice index in f64 -------------------------------------------------------------------
+// f: a coordinate in cell units relative to the lattice origin. h = floor(f) comes from the "magic number" sum
+// t = f + 1.5 * 2^52 rounded towards -infinity: for 0 <= floor(f) < 2^32 the high word of t is the magic constant's and
+// the low word is floor(f), so the lattice test is two integer compares and NaN, infinities and huge values fail it.
+// df = (float)(f - h): the position inside the lattice square, in [0, 1] (the subtraction is exact).
+__device__ __forceinline__ bool node_of(double f, unsigned nh, unsigned &h, float &df)
 {
-    float fx = __fmul_rn(__fsub_rn(X, L.ox), L.inv_st);
-    float fy = __fmul_rn(__fsub_rn(Y, L.oy), L.inv_st);
-    bool inside = (fx >= 0.0f) && (fx < L.nhxf) && (fy >= 0.0f) && (fy < L.nhyf);
-    hx = (int)fx;
-    hy = (int)fy;
-    return inside;
+    const double MAGIC = 6755399441055744.0; // 1.5 * 2^52
+    const double t = __dadd_rd(f, MAGIC);
+    const double n = __dadd_rn(t, -MAGIC);
+    df = __double2float_rn(__dsub_rn(f, n));
+    h = (unsigned)__double2loint(t);
+    return (__double2hiint(t) == 0x43380000) && (h < nh);
+}
+
+// a target point (no pose): f = ((double)X - (double)origin) * inv_st
+__device__ __forceinline__ bool lattice_of_point(const LevelDev &L, float X, float Y, int &hx, int &hy)
+{
+    unsigned ux, uy;
+    float dfx, dfy;
+    const bool inx = node_of(__dmul_rn(__dsub_rn((double)X, (double)L.ox), L.inv_std), (unsigned)L.nhx, ux, dfx);
+    const bool iny = node_of(__dmul_rn(__dsub_rn((double)Y, (double)L.oy), L.inv_std), (unsigned)L.nhy, uy, dfy);
+    hx = (int)ux;
+    hy = (int)uy;
+    return inx && iny;
 }
 
 // ---- SPEC 3: finalisation of one cell from its integer sums; f64, operations in the order the spec lists ----
 __device__ __forceinline__ void finalize_record(unsigned n, long long s0, long long s1, long long s2, long long s3, long long s4,
-                                                int jx, int jy, float ox, float oy, float st, float res, int ov, int min_points,
-                                                double eig_ratio, float4 &ra, float4 &rb)
+                                                double U, int min_points, double eig_ratio, float4 &ra, float4 &rb)
 {
     ra = make_float4(0.f, 0.f, 0.f, 0.f);
     rb = ra;
     if (n < (unsigned)min_points) return;
-    const double U = 1.0 / 1048576.0;
     double N = (double)n;
     double mx = (double)s0 / N, my = (double)s1 / N;
     double cxx = ((double)s2 - (double)s0 * mx) / (N - 1.0);
@@ -85,10 +99,8 @@ __device__ __forceinline__ void finalize_record(unsigned n, long long s0, long l
         cyy = l2n + dl * (vy * vy) / nn;
     }
     double det = cxx * cyy - cxy * cxy;
-    double cx = (double)ox + ((double)(jx - ov)) * (double)st + 0.5 * (double)res;
-    double cy = (double)oy + ((double)(jy - ov)) * (double)st + 0.5 * (double)res;
     const float b01 = (float)(-(cxy / det));
-    ra = make_float4((float)(cx + mx), (float)(cy + my), (float)(cyy / det), b01);
+    ra = make_float4((float)mx, (float)my, (float)(cyy / det), b01); // the mean relative to the cell centre
     rb = make_float4(b01, (float)(cxx / det), (float)n, 1.0f);
 }
 
@@ -136,8 +148,11 @@ __device__ __forceinline__ u64 expneg2(u64 nh)
 }
 
 // ---- SPEC 4: pose and point -----------------------------------------------------------------------------
+// The pose as one evaluation on one level uses it (SPEC 4, v4): the point-to-cell geometry runs in f64 and in cell
+// units relative to the lattice origin (ci, si, txi, tyi); the derivative terms use the f32 roundings (c, s).
 struct Pose32 {
-    float c, s, tx, ty;
+    double ci, si, txi, tyi;
+    float c, s;
 };
 
 // SPEC 4.2: sin and cos of the pose angle as a fixed sequence of f64 operations (two-constant Cody-Waite reduction,
@@ -169,15 +184,17 @@ __device__ __forceinline__ void sincos_spec(double th, double &sn_out, double &c
     cs_out = ((q + 1) & 2) ? -c4 : c4;
 }
 
-__device__ __forceinline__ Pose32 pose_to_f32(double tx, double ty, double th)
+__device__ __forceinline__ Pose32 pose_for_level(double tx, double ty, double th, const LevelDev &L)
 {
     double sn, cs;
     sincos_spec(th, sn, cs);
     Pose32 q;
     q.c = (float)cs;
     q.s = (float)sn;
-    q.tx = (float)tx;
-    q.ty = (float)ty;
+    q.ci = __dmul_rn(cs, L.inv_std);
+    q.si = __dmul_rn(sn, L.inv_std);
+    q.txi = __dmul_rn(__dsub_rn(tx, (double)L.ox), L.inv_std);
+    q.tyi = __dmul_rn(__dsub_rn(ty, (double)L.oy), L.inv_std);
     return q;
 }
 
@@ -189,7 +206,8 @@ __device__ __forceinline__ float2 sanitize(float2 p)
 }
 
 struct PosePk {
-    u64 cs, nsc, ncns, t; // (c,s) (-s,c) (-c,-s) (tx,ty)
+    u64 cs, nsc, ncns;        // (c,s) (-s,c) (-c,-s): f32, for r = R x and j = dr/dtheta
+    double ci, si, txi, tyi;  // f64, cell units: the lattice coordinates of the transformed point
 };
 __device__ __forceinline__ PosePk pose_pack(const Pose32 &q)
 {
@@ -197,27 +215,40 @@ __device__ __forceinline__ PosePk pose_pack(const Pose32 &q)
     P.cs = pk(q.c, q.s);
     P.nsc = pk(-q.s, q.c);
     P.ncns = pk(-q.c, -q.s);
-    P.t = pk(q.tx, q.ty);
+    P.ci = q.ci; P.si = q.si; P.txi = q.txi; P.tyi = q.tyi;
     return P;
 }
 
 struct PointPk {
-    u64 r, j, XY; // (rx,ry) (jx,jy) (X,Y)
+    u64 r, j;      // (rx,ry) (jx,jy), f32
+    u64 XY;        // the point relative to the centre of the cell being evaluated (lx, ly), metres, f32
+    u64 df;        // position inside the lattice square, in [0,1]^2
 };
 // JR: take j from r instead of computing it. SPEC 4: jx = fma(ns,x,nc*y) = -ry and jy = fma(c,x,ns*y) = rx bit for bit
 // (round-to-nearest is symmetric under negation), so j is r with its halves swapped and one sign flipped; ptxas folds
-// that into operand modifiers (.HI_LO.NP) and four packed instructions per step disappear. Measured: +2.3 % at K = 4,
-// where j is used by four cells, but -2 % at K = 1 (the swizzled operands issue more slowly than the two extra FFMA2
-// they replace), so only the K = 4 kernels use it.
+// that into operand modifiers (.HI_LO.NP) and four packed instructions per step disappear. Measured (v3): +2.3 % at K = 4,
+// where j is used by four cells, but -2 % at K = 1, so only the K = 4 kernels use it.
 template <bool JR = false>
-__device__ __forceinline__ PointPk transform_point(const PosePk &P, float x, float y)
+__device__ __forceinline__ void rotate_point(const PosePk &P, float x, float y, PointPk &p)
 {
-    PointPk p;
     p.r = fma2(P.cs, bc(x), mul2(P.nsc, bc(y)));   // rx = fma(c,x,ns*y), ry = fma(s,x,c*y)
     if (JR) p.j = pk(-hi32(p.r), lo32(p.r));
     else p.j = fma2(P.nsc, bc(x), mul2(P.ncns, bc(y))); // jx = fma(ns,x,nc*y), jy = fma(c,x,ns*y)
-    p.XY = add2(p.r, P.t);
-    return p;
+}
+
+// SPEC 4 (v4): lattice coordinates of the transformed point in f64, f = R x / st + (t - origin) / st; the lattice square
+// (hx, hy) and the f32 position inside it. Returns false outside the lattice (hx, hy are then meaningless).
+__device__ __forceinline__ bool locate_point(const PosePk &P, float x, float y, unsigned nhx, unsigned nhy, unsigned &hx, unsigned &hy,
+                                             u64 &df)
+{
+    const double xd = (double)x, yd = (double)y;
+    const double fx = __fma_rn(P.ci, xd, __fma_rn(-P.si, yd, P.txi));
+    const double fy = __fma_rn(P.si, xd, __fma_rn(P.ci, yd, P.tyi));
+    float dfx, dfy;
+    const bool inx = node_of(fx, nhx, hx, dfx);
+    const bool iny = node_of(fy, nhy, hy, dfy);
+    df = pk(dfx, dfy);
+    return inx && iny;
 }
 
 // ---- cell record: four f32 pairs in one 256-bit load ------------------------------------------------------
@@ -421,26 +452,37 @@ struct Fetched {
 };
 
 struct LatticePk {
-    u64 org, inv;
     unsigned nhx, nhy, njx;
     unsigned sentinel; // index of the all-zero record that follows the cells of the table
     unsigned mask;     // hash tables only: slots - 1
+    float st;          // stride in metres: local coordinate = fma(df, st, off)
+    u64 off[4];        // per cell of the point: minus the cell centre relative to node (hx, hy): (-st/2, -st/2) for one
+                       // grid; (-a st, -b st) for cell (a, b) of the four half-shifted grids
 };
+
+template <int OV>
+__device__ __forceinline__ LatticePk lattice_pack(const LevelDev &L, bool hash)
+{
+    LatticePk G;
+    G.nhx = (unsigned)L.nhx; G.nhy = (unsigned)L.nhy; G.njx = (unsigned)L.njx;
+    G.mask = L.hash_mask;
+    G.sentinel = hash ? L.hash_mask + 1u : (unsigned)L.njx * (unsigned)L.njy;
+    G.st = L.st;
+    if (OV) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) G.off[k] = pk(-__fmul_rn((float)(k & 1), L.st), -__fmul_rn((float)(k >> 1), L.st));
+    } else {
+        const float h2 = __fmul_rn(0.5f, L.st);
+        G.off[0] = G.off[1] = G.off[2] = G.off[3] = pk(-h2, -h2);
+    }
+    return G;
+}
 
 // slot of a cell key in a per-target hash table: Fibonacci hashing, bits 15.. of the product (tables have <= 2^16 slots)
 __device__ __forceinline__ unsigned hash_slot(unsigned key, unsigned mask) { return ((key * 0x9E3779B1u) >> 15) & mask; }
 
-// SPEC 2 in integers: for a finite f, (f >= 0 && f < (float)nh) == ((unsigned)floor_to_int(f) < nh), because the
-// conversion saturates (huge -> INT_MAX, very negative -> INT_MIN) and rounds (-1, 0) down to -1; inside the
-// lattice floor and SPEC 2's truncation agree. Points are sanitised, so f is never NaN here.
-__device__ __forceinline__ bool cell_base(const LatticePk &G, u64 f, unsigned &base)
-{
-    float fx, fy;
-    upk(f, fx, fy);
-    const unsigned ix = (unsigned)__float2int_rd(fx), iy = (unsigned)__float2int_rd(fy);
-    base = iy * G.njx + ix;
-    return (ix < G.nhx) && (iy < G.nhy);
-}
+// the point relative to the centre of its cell k (SPEC 4, v4): one f32 fma per coordinate
+__device__ __forceinline__ u64 local_xy(const LatticePk &G, u64 df, int k) { return fma2(df, bc(G.st), G.off[k]); }
 
 template <int OV, bool SMEM, bool HASH = false>
 __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const LatticePk &G, const PosePk &P, const float2 *pts,
@@ -448,11 +490,12 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
 {
     float2 a, b;
     load_two<SMEM>(pts, n, i, a, b);
-    F.A = transform_point<OV != 0>(P, a.x, a.y);
-    F.B = transform_point<OV != 0>(P, b.x, b.y);
-    unsigned bA, bB;
-    const bool inA = cell_base(G, mul2(sub2(F.A.XY, G.org), G.inv), bA);
-    const bool inB = cell_base(G, mul2(sub2(F.B.XY, G.org), G.inv), bB);
+    rotate_point<OV != 0>(P, a.x, a.y, F.A);
+    rotate_point<OV != 0>(P, b.x, b.y, F.B);
+    unsigned axh, ayh, bxh, byh;
+    const bool inA = locate_point(P, a.x, a.y, G.nhx, G.nhy, axh, ayh, F.A.df);
+    const bool inB = locate_point(P, b.x, b.y, G.nhx, G.nhy, bxh, byh, F.B.df);
+    const unsigned bA = ayh * G.njx + axh, bB = byh * G.njx + bxh;
     // K = 1: one record per point. K = 4: two rows of two adjacent records (64 contiguous bytes per row).
     // Outside the lattice: the sentinel record (all zero = invalid), so the gather needs no predicate.
     if (!HASH) {
@@ -499,6 +542,18 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
     }
 }
 
+// one step's cells for the lane's two points, accumulated in cell order (SPEC 4)
+template <int OV, bool FULL>
+__device__ __forceinline__ void accumulate_step(const LatticePk &G, Fetched<OV> &F, Partials &S, int &cnt)
+{
+#pragma unroll
+    for (int k = 0; k < Fetched<OV>::NC; ++k) {
+        F.A.XY = local_xy(G, F.A.df, k);
+        F.B.XY = local_xy(G, F.B.df, k);
+        accumulate_cell<FULL>(F.cA[k], F.cB[k], F.A, F.B, S, cnt);
+    }
+}
+
 // SPEC 4 for one warp. Lane l owns points 64 j + l (A) and 64 j + 32 + l (B), i.e. partials l and l + 32: each of the
 // two gather requests of an iteration then covers 32 consecutive beams (few distinct cache lines per request).
 // PIPE: software pipelining, the records of step j+1 are requested before step j is computed, so the L2 round
@@ -519,10 +574,7 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
     int cnt = 0;
     const float4 *__restrict__ cells = L.cells;
     const PosePk P = pose_pack(q);
-    LatticePk G;
-    G.org = pk(L.ox, L.oy); G.inv = bc(L.inv_st); G.nhx = (unsigned)L.nhx; G.nhy = (unsigned)L.nhy; G.njx = (unsigned)L.njx;
-    G.mask = L.hash_mask;
-    G.sentinel = HASH ? L.hash_mask + 1u : (unsigned)L.njx * (unsigned)L.njy;
+    const LatticePk G = lattice_pack<OV>(L, HASH);
     const int npad = (n + 63) & ~63;
     if (PIPE == 1 && OV == 0) {
         // Software pipeline over registers, two steps per trip: the records of the next step are requested before
@@ -534,7 +586,7 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
         if ((npad >> 6) & 1) {
             Fetched<OV> cur;
             fetch<OV, SMEM, HASH>(cells, G, P, pts, n, i, cur);
-            accumulate_cell<FULL>(cur.cA[0], cur.cB[0], cur.A, cur.B, S, cnt);
+            accumulate_step<OV, FULL>(G, cur, S, cnt);
             i += 64;
         }
         if (i < npad) {
@@ -544,9 +596,9 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
 #pragma unroll 1
             for (; i < npad; i += 128) {
                 fetch<OV, SMEM, HASH>(cells, G, P, pts, n, i + 64, F1);
-                accumulate_cell<FULL>(F0.cA[0], F0.cB[0], F0.A, F0.B, S, cnt);
+                accumulate_step<OV, FULL>(G, F0, S, cnt);
                 fetch<OV, SMEM, HASH>(cells, G, P, pts, n, min(i + 128, last), F0);
-                accumulate_cell<FULL>(F1.cA[0], F1.cB[0], F1.A, F1.B, S, cnt);
+                accumulate_step<OV, FULL>(G, F1, S, cnt);
             }
         }
     } else {
@@ -554,8 +606,7 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
         for (int i = lane; i < npad; i += 64) {
             Fetched<OV> cur;
             fetch<OV, SMEM, HASH>(cells, G, P, pts, n, i, cur);
-#pragma unroll
-            for (int k = 0; k < Fetched<OV>::NC; ++k) accumulate_cell<FULL>(cur.cA[k], cur.cB[k], cur.A, cur.B, S, cnt);
+            accumulate_step<OV, FULL>(G, cur, S, cnt);
         }
     }
     finish_partials<FULL, TR>(S, cnt, lane, E);

@@ -13,8 +13,9 @@ struct LevelDev {
     uint32_t *cnt;            // njx*njy
     unsigned long long *sums; // njx*njy*5, two's-complement i64
     float res, st, inv_st, ox, oy;
-    float nhxf, nhyf;         // (float)nhx, (float)nhy
     int nhx, nhy, njx, njy, ov;
+    double inv_std;           // SPEC 2: 1.0 / (double)st, the f64 scale of the lattice index
+    double qs, qu;            // SPEC 3: fixed-point scale 2^22 / res and its unit res * 2^-22
     // 0: `cells` is the dense table indexed by jy*njx+jx. Otherwise `cells` is an open-addressing hash table of
     // hash_mask+1 records keyed by that index (the key sits in the record's `n` word, 0xffffffff = empty slot), with the
     // sentinel record at index hash_mask+1: the per-target tables of the batched scan-to-scan path (ndt2d_align_pairs).

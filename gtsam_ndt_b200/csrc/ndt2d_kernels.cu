@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const LevelDev L, const floa
             float2 p = __ldg(xy + i);
             X = p.x;
             Y = p.y;
-            inside = lattice(L, X, Y, hx, hy);
+            inside = lattice_of_point(L, X, Y, hx, hy);
         }
 #pragma unroll
         for (int b = 0; b < K; ++b) {
@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(256) k_accumulate(const LevelDev L, const floa
                 double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
                 double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
                 double dx = (double)X - cx, dy = (double)Y - cy;
-                long long qx = inside ? __double2ll_rn(dx * 1048576.0) : 0;
-                long long qy = inside ? __double2ll_rn(dy * 1048576.0) : 0;
+                long long qx = inside ? __double2ll_rn(dx * L.qs) : 0;
+                long long qy = inside ? __double2ll_rn(dy * L.qs) : 0;
                 int c = inside ? 1 : 0;
                 long long sx = qx, sy = qy, sxx = qx * qx, sxy = qx * qy, syy = qy * qy;
                 // run id: number of run heads at or below this lane
@@ -95,8 +95,7 @@ __global__ void __launch_bounds__(256) k_finalize(const LevelDev L, float4 *__re
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
         const long long *s = reinterpret_cast<const long long *>(L.sums) + 5 * c;
         float4 ra, rb;
-        finalize_record(L.cnt[c], s[0], s[1], s[2], s[3], s[4], (int)(c % L.njx), (int)(c / L.njx), L.ox, L.oy, L.st, L.res, L.ov,
-                        min_points, eig_ratio, ra, rb);
+        finalize_record(L.cnt[c], s[0], s[1], s[2], s[3], s[4], L.qu, min_points, eig_ratio, ra, rb);
         cells[2 * c] = ra;
         cells[2 * c + 1] = rb;
     }
@@ -112,8 +111,7 @@ __global__ void __launch_bounds__(256) k_finalize_list(const LevelDev L, float4 
         const unsigned c = list[e];
         const long long *s = reinterpret_cast<const long long *>(L.sums) + 5 * (size_t)c;
         float4 ra, rb;
-        finalize_record(L.cnt[c], s[0], s[1], s[2], s[3], s[4], (int)(c % (unsigned)L.njx), (int)(c / (unsigned)L.njx), L.ox, L.oy, L.st, L.res,
-                        L.ov, min_points, eig_ratio, ra, rb);
+        finalize_record(L.cnt[c], s[0], s[1], s[2], s[3], s[4], L.qu, min_points, eig_ratio, ra, rb);
         cells[2 * (size_t)c] = ra;
         cells[2 * (size_t)c + 1] = rb;
         dirty[c] = 0u;
@@ -130,15 +128,20 @@ __global__ void k_cell_index(const LevelDev L, const float2 *__restrict__ xy, in
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float2 p = xy[i];
-    float X = p.x, Y = p.y;
-    if (pose) {
-        Pose32 q = pose_to_f32(pose[0], pose[1], pose[2]);
-        float2 ps = sanitize(p);
-        PointPk t = transform_point(pose_pack(q), ps.x, ps.y);
-        upk(t.XY, X, Y);
-    }
     int hx, hy;
-    idx[i] = lattice(L, X, Y, hx, hy) ? hy * L.nhx + hx : -1;
+    bool in;
+    if (pose) {
+        const PosePk P = pose_pack(pose_for_level(pose[0], pose[1], pose[2], L));
+        float2 ps = sanitize(p);
+        unsigned ux, uy;
+        u64 df;
+        in = locate_point(P, ps.x, ps.y, (unsigned)L.nhx, (unsigned)L.nhy, ux, uy, df);
+        hx = (int)ux;
+        hy = (int)uy;
+    } else {
+        in = lattice_of_point(L, p.x, p.y, hx, hy);
+    }
+    idx[i] = in ? hy * L.nhx + hx : -1;
 }
 
 template <int OV>
@@ -148,18 +151,19 @@ __global__ void k_point_terms(const LevelDev L, const float2 *__restrict__ xy, i
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     constexpr int K = OV ? 4 : 1;
-    Pose32 q = pose_to_f32(pose[0], pose[1], pose[2]);
+    const PosePk P = pose_pack(pose_for_level(pose[0], pose[1], pose[2], L));
+    const LatticePk G = lattice_pack<OV>(L, false);
     float2 p = sanitize(xy[i]);
-    PointPk pt = transform_point(pose_pack(q), p.x, p.y);
-    float X, Y;
-    upk(pt.XY, X, Y);
+    PointPk pt;
+    rotate_point(P, p.x, p.y, pt);
     float *out = terms + (size_t)i * K * 10;
     for (int t = 0; t < K * 10; ++t) out[t] = 0.0f;
-    int hx, hy;
-    if (!lattice(L, X, Y, hx, hy)) return;
+    unsigned hx, hy;
+    if (!locate_point(P, p.x, p.y, G.nhx, G.nhy, hx, hy, pt.df)) return;
     for (int k = 0; k < K; ++k) {
-        unsigned cidx = (unsigned)(hy + (k >> 1)) * (unsigned)L.njx + (unsigned)(hx + (k & 1));
+        unsigned cidx = (hy + (k >> 1)) * (unsigned)L.njx + (hx + (k & 1));
         Cell4 rec = load_cell(L.cells, cidx);
+        pt.XY = local_xy(G, pt.df, k);
         float T[10];
         if (pair_terms_scalar(rec, pt, T))
             for (int t = 0; t < 10; ++t) out[k * 10 + t] = T[t];
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, FULL ? EVAL_BLOCKS_FULL : NDT2D_
             const double *h = reinterpret_cast<const double *>(poses) + 3 * j;
             tx = __ldg(h); ty = __ldg(h + 1); th = __ldg(h + 2);
         }
-        Pose32 q = pose_to_f32(tx, ty, th);
+        Pose32 q = pose_for_level(tx, ty, th, L);
         Eval E;
         // FULL: the transposed reduction leaves sum number E.slot in every lane (lanes with the same slot hold the same bits)
         if (STAGED) eval_warp<OV, FULL, true, OV == 0 ? EVAL_PIPE : 0, FULL>(L, sp, n, q, lane, E);
@@ -265,7 +269,7 @@ __device__ __noinline__ void eval_to_smem(const LevelDev *L, const float2 *pts, 
     const int lane = threadIdx.x & 31;
     const double *pose = trial ? ws->pn : ws->p;
     Eval E;
-    eval_warp<OV, true, STAGED, (STAGED && OV == 0 && !HASH) ? NDT2D_PIPE : 0, true, HASH>(*L, pts, n, pose_to_f32(pose[0], pose[1], pose[2]), lane, E);
+    eval_warp<OV, true, STAGED, (STAGED && OV == 0 && !HASH) ? NDT2D_PIPE : 0, true, HASH>(*L, pts, n, pose_for_level(pose[0], pose[1], pose[2], *L), lane, E);
     __syncwarp();
     double *out = trial ? ws->t : ws->v;
     out[E.slot] = E.v[0]; // lanes holding the same sum store the same bits
@@ -362,11 +366,8 @@ __device__ __forceinline__ void eval_block(const LevelDev *L, const float2 *pts,
     constexpr int NC = OV ? 4 : 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double *pose = trial ? ws->pn : ws->p;
-    const PosePk P = pose_pack(pose_to_f32(pose[0], pose[1], pose[2]));
-    LatticePk G;
-    G.org = pk(L->ox, L->oy); G.inv = bc(L->inv_st); G.nhx = (unsigned)L->nhx; G.nhy = (unsigned)L->nhy; G.njx = (unsigned)L->njx;
-    G.mask = 0;
-    G.sentinel = (unsigned)L->njx * (unsigned)L->njy;
+    const PosePk P = pose_pack(pose_for_level(pose[0], pose[1], pose[2], *L));
+    const LatticePk G = lattice_pack<OV>(*L, false);
     const float4 *__restrict__ cells = L->cells;
     const int nsteps = (n + 63) >> 6;
     for (int step = warp; step < nsteps; step += BLOCK_ALIGN_THREADS / 32) {
@@ -376,6 +377,8 @@ __device__ __forceinline__ void eval_block(const LevelDev *L, const float2 *pts,
         for (int k = 0; k < NC; ++k) {
             Factors X;
             int c = 0;
+            F.A.XY = local_xy(G, F.A.df, k);
+            F.B.XY = local_xy(G, F.B.df, k);
             cell_factors<true>(F.cA[k], F.cB[k], F.A, F.B, X, c);
             u64 *o = fac + ((size_t)(step * NC + k) * FACTOR_WORDS) * 32 + lane;
             o[0 * 32] = X.e;

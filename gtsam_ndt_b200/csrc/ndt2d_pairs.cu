@@ -69,8 +69,9 @@ __global__ void __launch_bounds__(256) k_pairs_build(const PairBuildArgs a)
     if (too_big) { L.nhx = L.nhy = 0; }      // nothing is inside: every align against this target ends NO_OVERLAP
     L.njx = L.nhx + L.ov;
     L.njy = L.nhy + L.ov;
-    L.nhxf = (float)L.nhx;
-    L.nhyf = (float)L.nhy;
+    L.inv_std = __ddiv_rn(1.0, (double)L.st);
+    L.qs = __ddiv_rn(4194304.0, (double)L.res);
+    L.qu = __dmul_rn((double)L.res, 1.0 / 4194304.0);
     L.hash_mask = a.cap - 1u;
     float4 *rec = a.tab + (size_t)wid * ((size_t)a.cap + 1) * 2;
     uint32_t *cnt = a.cnt + (size_t)wid * a.cap;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) k_pairs_build(const PairBuildArgs a)
         if (i < n) {
             X = p.x;
             Y = p.y;
-            inside = lattice(L, X, Y, hx, hy);
+            inside = lattice_of_point(L, X, Y, hx, hy);
         }
 #pragma unroll
         for (int b = 0; b < K; ++b) {
@@ -119,8 +120,8 @@ __global__ void __launch_bounds__(256) k_pairs_build(const PairBuildArgs a)
                 double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
                 double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
                 double dx = (double)X - cx, dy = (double)Y - cy;
-                long long qx = inside ? __double2ll_rn(dx * 1048576.0) : 0;
-                long long qy = inside ? __double2ll_rn(dy * 1048576.0) : 0;
+                long long qx = inside ? __double2ll_rn(dx * L.qs) : 0;
+                long long qy = inside ? __double2ll_rn(dy * L.qs) : 0;
                 int c = inside ? 1 : 0;
                 long long sx = qx, sy = qy, sxx = qx * qx, sxy = qx * qy, syy = qy * qy;
                 int prev = __shfl_up_sync(FULL_MASK, key, 1);
@@ -180,8 +181,7 @@ __global__ void __launch_bounds__(256) k_pairs_build(const PairBuildArgs a)
         volatile long long *q = reinterpret_cast<volatile long long *>(sums + 5 * (size_t)s);
         const long long q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
         float4 ra, rb;
-        finalize_record(nn, q0, q1, q2, q3, q4, (int)(key % (unsigned)L.njx), (int)(key / (unsigned)L.njx), L.ox, L.oy, L.st, L.res,
-                        L.ov, a.min_points, a.eig_ratio, ra, rb);
+        finalize_record(nn, q0, q1, q2, q3, q4, L.qu, a.min_points, a.eig_ratio, ra, rb);
         rb.z = __int_as_float((int)key);
         rec[2 * (size_t)s] = ra;
         rec[2 * (size_t)s + 1] = rb;

@@ -18,6 +18,8 @@
 
 typedef struct {
     float res, st, inv_st, ox, oy;
+    double inv_std;      /* SPEC 2 (v4): 1.0 / (double)st */
+    double qs, qu;       /* SPEC 3 (v4): fixed-point scale 2^22 / res and its unit res * 2^-22 */
     int ov, nhx, nhy, njx, njy;
     uint32_t *n;  /* per cell */
     int64_t *s;   /* 5 per cell: sx sy sxx sxy syy */
@@ -113,6 +115,9 @@ static int level_setup(oracle_matcher *m, int l, const float *xy, int n)
     L->ov = m->prm.overlap;
     L->st = L->ov ? L->res * 0.5f : L->res;
     L->inv_st = 1.0f / L->st;
+    L->inv_std = 1.0 / (double)L->st;
+    L->qs = 4194304.0 / (double)L->res;
+    L->qu = (double)L->res * (1.0 / 4194304.0);
     if (m->explicit_grid) {
         L->ox = m->gox; L->oy = m->goy;
         L->nhx = (int)ceilf(m->gex / L->st);
@@ -143,14 +148,22 @@ static int level_setup(oracle_matcher *m, int l, const float *xy, int n)
     return (L->n && L->s && L->cells) ? 0 : 2;
 }
 
-/* SPEC 2: lattice index; returns 0 when outside */
-static int lattice(const level_t *L, float X, float Y, int *hx, int *hy)
+/* SPEC 2 (v4): lattice index of a coordinate pair given in CELL UNITS relative to the lattice origin, f64; returns 0
+ * when outside. h = floor(f); the fraction f - h (exact in f64) is rounded once to f32 (dfx, dfy in [0, 1]): the
+ * per-point algebra of SPEC 4 works on such cell-local coordinates, never on map-frame f32 coordinates. */
+static int lattice(const level_t *L, double fx, double fy, int *hx, int *hy, float *dfx, float *dfy)
 {
-    float fx = (X - L->ox) * L->inv_st;
-    float fy = (Y - L->oy) * L->inv_st;
-    if (!((fx >= 0.0f) && (fx < (float)L->nhx) && (fy >= 0.0f) && (fy < (float)L->nhy))) return 0;
-    *hx = (int)fx; *hy = (int)fy;
+    double nx = floor(fx), ny = floor(fy);
+    if (!((nx >= 0.0) && (nx < (double)L->nhx) && (ny >= 0.0) && (ny < (double)L->nhy))) return 0; /* NaN is outside */
+    *hx = (int)nx; *hy = (int)ny;
+    if (dfx) { *dfx = (float)(fx - nx); *dfy = (float)(fy - ny); }
     return 1;
+}
+
+/* SPEC 2 (v4): a target point (no pose): f = ((double)X - (double)origin) * inv_st */
+static int lattice_of_point(const level_t *L, float X, float Y, int *hx, int *hy)
+{
+    return lattice(L, ((double)X - (double)L->ox) * L->inv_std, ((double)Y - (double)L->oy) * L->inv_std, hx, hy, NULL, NULL);
 }
 
 /* SPEC 3: integer accumulation of one point into its K cells */
@@ -160,13 +173,13 @@ static void accumulate(level_t *L, const float *xy, int n)
     for (int i = 0; i < n; ++i) {
         float X = xy[2 * i], Y = xy[2 * i + 1];
         int hx, hy;
-        if (!lattice(L, X, Y, &hx, &hy)) continue;
+        if (!lattice_of_point(L, X, Y, &hx, &hy)) continue;
         for (int b = 0; b < K; ++b) for (int a = 0; a < K; ++a) {
             int jx = hx + a, jy = hy + b;
             double cx = (double)L->ox + ((double)(jx - L->ov)) * (double)L->st + 0.5 * (double)L->res;
             double cy = (double)L->oy + ((double)(jy - L->ov)) * (double)L->st + 0.5 * (double)L->res;
             double dx = (double)X - cx, dy = (double)Y - cy;
-            int64_t qx = llrint(dx * 1048576.0), qy = llrint(dy * 1048576.0);
+            int64_t qx = llrint(dx * L->qs), qy = llrint(dy * L->qs);
             size_t c = (size_t)jy * (size_t)L->njx + (size_t)jx;
             L->n[c] += 1;
             int64_t *s = L->s + 5 * c;
@@ -178,7 +191,7 @@ static void accumulate(level_t *L, const float *xy, int n)
 /* SPEC 3: finalisation of every cell */
 static void finalize(level_t *L, const oracle_params *P)
 {
-    const double U = 1.0 / 1048576.0;
+    const double U = L->qu;
     for (int jy = 0; jy < L->njy; ++jy) for (int jx = 0; jx < L->njx; ++jx) {
         size_t c = (size_t)jy * (size_t)L->njx + (size_t)jx;
         float *rec = L->cells + 8 * c;
@@ -204,9 +217,7 @@ static void finalize(level_t *L, const oracle_params *P)
             cyy = l2n + dl * (vy * vy) / nn;
         }
         double det = cxx * cyy - cxy * cxy;
-        double cx = (double)L->ox + ((double)(jx - L->ov)) * (double)L->st + 0.5 * (double)L->res;
-        double cy = (double)L->oy + ((double)(jy - L->ov)) * (double)L->st + 0.5 * (double)L->res;
-        rec[0] = (float)(cx + mx); rec[1] = (float)(cy + my);
+        rec[0] = (float)mx; rec[1] = (float)my;   /* the mean RELATIVE TO THE CELL CENTRE (v4) */
         rec[2] = (float)(cyy / det); rec[3] = (float)(-(cxy / det));
         rec[4] = rec[3]; rec[5] = (float)(cxx / det);
         rec[6] = (float)n; rec[7] = 1.0f;
@@ -301,30 +312,37 @@ void oracle_sincos(double th, double *sn_out, double *cs_out)
     *cs_out = ((q + 1) & 2) ? -c4 : c4;
 }
 
-/* SPEC 4: pose to f32 */
-typedef struct { float c, s, tx, ty; } pose32;
-static pose32 pose_to_f32(const double p[3])
+/* SPEC 4 (v4): the pose as the evaluation uses it. The point-to-cell geometry is f64: (c, s) from SPEC 4.2 and the
+ * translation relative to the level's lattice origin; the derivative terms use the f32 roundings (cf, sf). */
+typedef struct { double ci, si, txi, tyi; float cf, sf; } pose_t;
+static pose_t pose_for_level(const double p[3], const level_t *L)
 {
-    pose32 q;
+    pose_t q;
     double sn, cs;
     oracle_sincos(p[2], &sn, &cs);
-    q.c = (float)cs; q.s = (float)sn;
-    q.tx = (float)p[0]; q.ty = (float)p[1];
+    q.cf = (float)cs; q.sf = (float)sn;
+    q.ci = cs * L->inv_std; q.si = sn * L->inv_std;              /* rotation and translation in cell units */
+    q.txi = (p[0] - (double)L->ox) * L->inv_std; q.tyi = (p[1] - (double)L->oy) * L->inv_std;
     return q;
 }
 
-/* SPEC 4: the per-point quantities shared by its K cells */
-typedef struct { float rx, ry, jx, jy, X, Y; } point_t;
+/* SPEC 4: the per-point quantities shared by its K cells: r = R x and j = dr/dtheta in f32 (derivative terms),
+ * the lattice square (hx, hy) and the position (dfx, dfy) in [0, 1] inside it, from the f64 transform */
+typedef struct { float rx, ry, jx, jy, dfx, dfy; int hx, hy, inside; } point_t;
 
-static point_t transform_point(const pose32 *q, float x, float y)
+static point_t transform_point(const pose_t *q, const level_t *L, float x, float y)
 {
     /* SPEC 4: points that cannot lie in any lattice are replaced by a finite far-away point */
     if (!isfinite(x) || !isfinite(y) || fabsf(x) > 1e18f || fabsf(y) > 1e18f) { x = 1e18f; y = 1e18f; }
-    const float nc = -q->c, ns = -q->s;
+    const float nc = -q->cf, ns = -q->sf;
     point_t p;
-    p.rx = fmaf(q->c, x, ns * y); p.ry = fmaf(q->s, x, q->c * y);
-    p.jx = fmaf(ns, x, nc * y);   p.jy = fmaf(q->c, x, ns * y);
-    p.X = p.rx + q->tx; p.Y = p.ry + q->ty;
+    p.rx = fmaf(q->cf, x, ns * y); p.ry = fmaf(q->sf, x, q->cf * y);
+    p.jx = fmaf(ns, x, nc * y);    p.jy = fmaf(q->cf, x, ns * y);
+    const double xd = (double)x, yd = (double)y;
+    const double fx = fma(q->ci, xd, fma(-q->si, yd, q->txi));
+    const double fy = fma(q->si, xd, fma(q->ci, yd, q->tyi));
+    p.hx = p.hy = 0; p.dfx = p.dfy = 0.0f;
+    p.inside = lattice(L, fx, fy, &p.hx, &p.hy, &p.dfx, &p.dfy);
     return p;
 }
 
@@ -333,16 +351,18 @@ int oracle_cell_index(const oracle_matcher *m, int level, const float *xy, int n
 {
     const level_t *L = get_level(m, level);
     if (!L) return 1;
-    pose32 q = {1.0f, 0.0f, 0.0f, 0.0f};
-    if (pose) q = pose_to_f32(pose);
+    pose_t q;
+    if (pose) q = pose_for_level(pose, L);
     for (int i = 0; i < n; ++i) {
-        float x = xy[2 * i], y = xy[2 * i + 1], X = x, Y = y;
+        float x = xy[2 * i], y = xy[2 * i + 1];
+        int hx, hy, in;
         if (pose) {
-            point_t p = transform_point(&q, x, y);
-            X = p.X; Y = p.Y;
+            point_t p = transform_point(&q, L, x, y);
+            in = p.inside; hx = p.hx; hy = p.hy;
+        } else {
+            in = lattice_of_point(L, x, y, &hx, &hy);
         }
-        int hx, hy;
-        idx[i] = lattice(L, X, Y, &hx, &hy) ? hy * L->nhx + hx : -1;
+        idx[i] = in ? hy * L->nhx + hx : -1;
     }
     return 0;
 }
@@ -367,11 +387,12 @@ float oracle_expneg(float h)
 }
 
 /* SPEC 4: the ten f32 factors (e, c1..c9) of one (point, cell) pair; returns 0 when skipped */
-static int pair_terms(const float *rec, const point_t *p, float T[10])
+/* (lx, ly): the point relative to the centre of this cell (SPEC 4 v4), f32 */
+static int pair_terms(const float *rec, const point_t *p, float lx, float ly, float T[10])
 {
     if (rec[7] == 0.0f) return 0;
     float mux = rec[0], muy = rec[1], B00 = rec[2], B01 = rec[3], B11 = rec[5];
-    float qx = p->X - mux, qy = p->Y - muy;
+    float qx = lx - mux, qy = ly - muy;
     float ux = fmaf(B00, qx, B01 * qy), uy = fmaf(B01, qx, B11 * qy);
     float m1 = qx * ux, m2 = qy * uy;
     float mm = m1 + m2, h = 0.5f * mm;
@@ -399,21 +420,26 @@ static int pair_terms(const float *rec, const point_t *p, float T[10])
 static void evaluate_level(const level_t *L, const float *xy, int n, const double pose[3],
                            double out[10], int32_t *count, float *terms_out)
 {
-    pose32 q = pose_to_f32(pose);
+    pose_t q = pose_for_level(pose, L);
     const int K = L->ov ? 2 : 1;
+    const float h2 = 0.5f * L->st;
     float part[64][10];
     memset(part, 0, sizeof(part));
     int32_t cnt = 0;
     if (terms_out) memset(terms_out, 0, (size_t)n * K * K * 10 * sizeof(float));
     for (int i = 0; i < n; ++i) {
-        point_t p = transform_point(&q, xy[2 * i], xy[2 * i + 1]);
-        int hx, hy;
-        if (!lattice(L, p.X, p.Y, &hx, &hy)) continue;
+        point_t p = transform_point(&q, L, xy[2 * i], xy[2 * i + 1]);
+        if (!p.inside) continue;
+        const int hx = p.hx, hy = p.hy;
         float *acc = part[i & 63];
         for (int b = 0; b < K; ++b) for (int a = 0; a < K; ++a) {
             const float *rec = L->cells + 8 * ((size_t)(hy + b) * L->njx + (size_t)(hx + a));
+            /* the cell's centre relative to node (hx, hy): (st/2, st/2) for one grid; node (hx+a, hy+b) itself for the
+             * four half-shifted grids */
+            const float lx = fmaf(p.dfx, L->st, L->ov ? -((float)a * L->st) : -h2);
+            const float ly = fmaf(p.dfy, L->st, L->ov ? -((float)b * L->st) : -h2);
             float T[10];
-            if (!pair_terms(rec, &p, T)) continue;
+            if (!pair_terms(rec, &p, lx, ly, T)) continue;
             acc[0] = acc[0] + T[0];
             for (int t = 1; t < 10; ++t) acc[t] = fmaf(T[0], T[t], acc[t]);
             if (terms_out) memcpy(terms_out + ((size_t)i * K * K + (size_t)(b * K + a)) * 10, T, sizeof(T));

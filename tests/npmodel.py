@@ -38,12 +38,19 @@ def score_terms(xy, pose, mu, B):
     return S, g, H
 
 
+def cell_centre(geom, jx, jy, overlap=0):
+    """SPEC 2: centre of table entry (jx, jy) in the map frame, f64."""
+    ov = 1 if overlap else 0
+    st, res = float(geom["st"]), float(geom["res"])
+    return np.array([float(geom["ox"]) + (jx - ov) * st + 0.5 * res, float(geom["oy"]) + (jy - ov) * st + 0.5 * res])
+
+
 def gather(cells, geom, xy, pose, overlap=0):
-    """Per-(point, cell) pairs of a pose: returns (xy_rep, mu, B) for valid pairs. f32 index as SPEC 2."""
+    """Per-(point, cell) pairs of a pose: returns (xy_rep, mu, B) for valid pairs; mu in the map frame (the records
+    carry the mean relative to the cell centre since SPEC v4; the centre is added back here in f64)."""
     xy = np.asarray(xy, np.float32)
-    c = np.float32(np.cos(pose[2])); s = np.float32(np.sin(pose[2]))
     x64 = xy.astype(np.float64)
-    # the lattice index is taken with f64 math here; tests avoid points within 1e-4 of a cell edge
+    # the lattice index is plain f64 math here (SPEC 2 is f64 as well; points closer than 1e-9 cells to an edge could differ)
     X = np.cos(pose[2]) * x64[:, 0] - np.sin(pose[2]) * x64[:, 1] + pose[0]
     Y = np.sin(pose[2]) * x64[:, 0] + np.cos(pose[2]) * x64[:, 1] + pose[1]
     fx = (X - float(geom["ox"])) / float(geom["st"])
@@ -59,7 +66,8 @@ def gather(cells, geom, xy, pose, overlap=0):
                 rec = cells[hy[i] + b, hx[i] + a].astype(np.float64)
                 if rec[7] == 0:
                     continue
-                pts.append(x64[i]); mus.append(rec[0:2]); Bs.append([[rec[2], rec[3]], [rec[4], rec[5]]])
+                ctr = cell_centre(geom, hx[i] + a, hy[i] + b, overlap)
+                pts.append(x64[i]); mus.append(ctr + rec[0:2]); Bs.append([[rec[2], rec[3]], [rec[4], rec[5]]])
     if not pts:
         return np.zeros((0, 2)), np.zeros((0, 2)), np.zeros((0, 2, 2)), edge
     return np.array(pts), np.array(mus), np.array(Bs), edge
