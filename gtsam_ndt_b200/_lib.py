@@ -43,7 +43,9 @@ SIGNATURES = {
     "ndt2d_get_cells": (C.c_int, [_V, C.c_int, _V]),
     "ndt2d_get_sums": (C.c_int, [_V, C.c_int, _V, _V]),
     "ndt2d_cells_device": (_V, [_V, C.c_int]),
-    "ndt2d_set_cells": (C.c_int, [_V, C.c_int, _V]),
+    "ndt2d_set_cells": (C.c_int, [_V, C.c_int, _V, C.c_int64]),
+    "ndt2d_save_map": (C.c_int, [_V, C.c_char_p, C.c_int]),
+    "ndt2d_load_map": (C.c_int, [_V, C.c_char_p]),
     "ndt2d_cell_index": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, _V]),
     "ndt2d_evaluate": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, C.c_int, _V, _V]),
     "ndt2d_evaluate_device": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, C.c_int, _V, _V]),

@@ -38,6 +38,38 @@ void drop_target(ndt2d_matcher *m, bool keep_memory = false)
     m->sums_valid = false;
 }
 
+// the quantities SPEC 2 and 3 derive from a level's cell size and overlap mode
+static void derive_strides(LevelDev &L)
+{
+    L.st = L.ov ? L.res * 0.5f : L.res;
+    L.inv_st = 1.0f / L.st;
+    L.inv_std = 1.0 / (double)L.st;
+    L.qs = 4194304.0 / (double)L.res;
+    L.qu = (double)L.res * (1.0 / 4194304.0);
+}
+
+// device memory of level l for the lattice in m->lv[l] (nhx, nhy set): tables allocated and cleared
+static int install_level(ndt2d_matcher *m, int l)
+{
+    LevelDev &L = m->lv[l];
+    if (L.nhx < 1 || L.nhy < 1) return fail(m, NDT2D_EINVAL, "level %d: empty lattice (%d x %d)", l, L.nhx, L.nhy);
+    L.njx = L.nhx + L.ov;
+    L.njy = L.nhy + L.ov;
+    int64_t nc = (int64_t)L.njx * L.njy;
+    if (nc >= (int64_t)1 << 31) return fail(m, NDT2D_EINVAL, "level %d: %lld cells exceed 2^31", l, (long long)nc);
+    LevelMem &M = m->mem[l];
+    const int64_t pad = LevelMem::zero_pad(L.njx);
+    CK(m, M.ensure(nc, pad));
+    // all-zero records after the table: the gather targets of points outside the lattice (never written again)
+    CK(m, cudaMemsetAsync(M.cells, 0, (size_t)(nc + pad) * 32, m->cfg.stream));
+    CK(m, cudaMemsetAsync(M.cnt, 0, (size_t)nc * 4, m->cfg.stream));
+    CK(m, cudaMemsetAsync(M.sums, 0, (size_t)nc * 40, m->cfg.stream));
+    L.cells = M.cells;
+    L.cnt = M.cnt;
+    L.sums = M.sums;
+    return NDT2D_OK;
+}
+
 // SPEC 2: geometry of level l. bbox = {xmin, ymin, xmax, ymax}, used for auto-fit only.
 int setup_level(ndt2d_matcher *m, int l, const float bbox[4])
 {
@@ -45,8 +77,7 @@ int setup_level(ndt2d_matcher *m, int l, const float bbox[4])
     L = LevelDev{};
     L.res = m->res[l];
     L.ov = m->prm.overlap;
-    L.st = L.ov ? L.res * 0.5f : L.res;
-    L.inv_st = 1.0f / L.st;
+    derive_strides(L);
     if (m->explicit_grid) {
         L.ox = m->gox; L.oy = m->goy;
         L.nhx = (int)ceilf(m->gex / L.st);
@@ -59,24 +90,7 @@ int setup_level(ndt2d_matcher *m, int l, const float bbox[4])
         L.nhx = (int)ceilf((xmax - L.ox) / L.st) + 2;
         L.nhy = (int)ceilf((ymax - L.oy) / L.st) + 2;
     }
-    if (L.nhx < 1 || L.nhy < 1) return fail(m, NDT2D_EINVAL, "level %d: empty lattice (%d x %d)", l, L.nhx, L.nhy);
-    L.njx = L.nhx + L.ov;
-    L.njy = L.nhy + L.ov;
-    L.inv_std = 1.0 / (double)L.st;
-    L.qs = 4194304.0 / (double)L.res;
-    L.qu = (double)L.res * (1.0 / 4194304.0);
-    int64_t nc = (int64_t)L.njx * L.njy;
-    if (nc >= (int64_t)1 << 31) return fail(m, NDT2D_EINVAL, "level %d: %lld cells exceed 2^31", l, (long long)nc);
-    LevelMem &M = m->mem[l];
-    CK(m, M.ensure(nc));
-    // one extra all-zero record after the table: the gather target of points outside the lattice (never written again)
-    CK(m, cudaMemsetAsync(M.cells, 0, (size_t)(nc + 1) * 32, m->cfg.stream));
-    CK(m, cudaMemsetAsync(M.cnt, 0, (size_t)nc * 4, m->cfg.stream));
-    CK(m, cudaMemsetAsync(M.sums, 0, (size_t)nc * 40, m->cfg.stream));
-    L.cells = M.cells;
-    L.cnt = M.cnt;
-    L.sums = M.sums;
-    return NDT2D_OK;
+    return install_level(m, l);
 }
 
 int accumulate_and_finalize(ndt2d_matcher *m, const float2 *d_xy, int64_t n)
@@ -486,7 +500,7 @@ const float *ndt2d_cells_device(const ndt2d_matcher *m, int level)
     return reinterpret_cast<const float *>(m->lv[level].cells);
 }
 
-int ndt2d_set_cells(ndt2d_matcher *m, int level, const float *cells)
+int ndt2d_set_cells(ndt2d_matcher *m, int level, const float *cells, int64_t nrecords)
 {
     if (!m || !cells) return NDT2D_EINVAL;
     DeviceGuard g(m->device);
@@ -503,10 +517,139 @@ int ndt2d_set_cells(ndt2d_matcher *m, int level, const float *cells)
         m->has_target = true;
     }
     if (level < 0 || level >= m->nlevels) return fail(m, NDT2D_EINVAL, "level %d out of range", level);
-    m->sums_valid = false;
     const LevelDev &L = m->lv[level];
+    if (nrecords != (int64_t)L.njx * L.njy)
+        return fail(m, NDT2D_EINVAL, "set_cells: level %d holds %d x %d = %lld records, caller passed %lld", level, L.njx, L.njy,
+                    (long long)((int64_t)L.njx * L.njy), (long long)nrecords);
+    m->sums_valid = false;
     CK(m, cudaMemcpyAsync(m->mem[level].cells, cells, (size_t)L.njx * L.njy * 32, cudaMemcpyHostToDevice, m->cfg.stream));
     return ndt2d_synchronize(m);
+}
+
+// ---- map files. Layout: MapFileHeader, nlevels x MapFileLevel, then per level the cell records
+// (njx*njy*32 B) and, when has_sums, the counts (u32) and the five i64 sums of every cell. Little endian, no padding games:
+// both structs are made of 4- and 8-byte fields in natural alignment.
+namespace {
+struct MapFileHeader {
+    char magic[8];          // "NDT2DMAP"
+    uint32_t version;       // file layout, 1
+    uint32_t spec_version;  // SPEC.md version of the records (4): records of another version are not interchangeable
+    int32_t nlevels, overlap, min_points, explicit_grid;
+    double eig_ratio;
+    float gox, goy, gex, gey;
+    uint32_t has_sums, reserved;
+};
+struct MapFileLevel {
+    float res, ox, oy, reserved;
+    int32_t nhx, nhy, njx, njy;
+};
+constexpr uint32_t kMapFileVersion = 1, kSpecVersion = 4;
+} // namespace
+
+int ndt2d_save_map(ndt2d_matcher *m, const char *path, int with_sums)
+{
+    if (!m || !path) return NDT2D_EINVAL;
+    if (!m->has_target) return fail(m, NDT2D_ENOTARGET, "no target set");
+    if (with_sums && !m->sums_valid) return fail(m, NDT2D_EINVAL, "save_map: the target has no sums (it was loaded without them)");
+    DeviceGuard g(m->device);
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(m, NDT2D_EINVAL, "save_map: cannot open %s for writing", path);
+    MapFileHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "NDT2DMAP", 8);
+    h.version = kMapFileVersion; h.spec_version = kSpecVersion;
+    h.nlevels = m->nlevels; h.overlap = m->prm.overlap; h.min_points = m->prm.min_points; h.explicit_grid = m->explicit_grid ? 1 : 0;
+    h.eig_ratio = m->prm.eig_ratio;
+    h.gox = m->gox; h.goy = m->goy; h.gex = m->gex; h.gey = m->gey;
+    h.has_sums = with_sums ? 1u : 0u;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    for (int l = 0; l < m->nlevels && ok; ++l) {
+        const LevelDev &L = m->lv[l];
+        MapFileLevel v = {L.res, L.ox, L.oy, 0.0f, L.nhx, L.nhy, L.njx, L.njy};
+        ok = fwrite(&v, sizeof(v), 1, f) == 1;
+    }
+    std::vector<unsigned char> buf;
+    for (int l = 0; l < m->nlevels && ok; ++l) {
+        const LevelDev &L = m->lv[l];
+        const size_t nc = (size_t)L.njx * L.njy;
+        const void *src[3] = {L.cells, L.cnt, L.sums};
+        const size_t bytes[3] = {nc * 32, nc * 4, nc * 40};
+        for (int part = 0; part < (with_sums ? 3 : 1) && ok; ++part) {
+            buf.resize(bytes[part]);
+            cudaError_t e = cudaMemcpyAsync(buf.data(), src[part], bytes[part], cudaMemcpyDeviceToHost, m->cfg.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(m->cfg.stream);
+            if (e != cudaSuccess) {
+                fclose(f);
+                return fail(m, NDT2D_ECUDA, "save_map: %s", cudaGetErrorString(e));
+            }
+            ok = fwrite(buf.data(), 1, bytes[part], f) == bytes[part];
+        }
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? NDT2D_OK : fail(m, NDT2D_EINVAL, "save_map: short write to %s", path);
+}
+
+int ndt2d_load_map(ndt2d_matcher *m, const char *path)
+{
+    if (!m || !path) return NDT2D_EINVAL;
+    DeviceGuard g(m->device);
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(m, NDT2D_EINVAL, "load_map: cannot open %s", path);
+    MapFileHeader h;
+    MapFileLevel lv[NDT2D_MAX_LEVELS];
+    bool ok = fread(&h, sizeof(h), 1, f) == 1 && memcmp(h.magic, "NDT2DMAP", 8) == 0;
+    if (!ok || h.version != kMapFileVersion || h.spec_version != kSpecVersion || h.nlevels < 1 || h.nlevels > NDT2D_MAX_LEVELS ||
+        (h.overlap != 0 && h.overlap != 1) || h.min_points < 2) {
+        fclose(f);
+        return fail(m, NDT2D_EINVAL, "load_map: %s is not an NDT2DMAP file of layout %u / SPEC v%u", path, kMapFileVersion, kSpecVersion);
+    }
+    ok = fread(lv, sizeof(MapFileLevel), (size_t)h.nlevels, f) == (size_t)h.nlevels;
+    for (int l = 0; l < h.nlevels && ok; ++l)
+        ok = lv[l].res > 0.0f && lv[l].res <= 8.0f && lv[l].nhx >= 1 && lv[l].nhy >= 1 && lv[l].njx == lv[l].nhx + h.overlap &&
+             lv[l].njy == lv[l].nhy + h.overlap && (int64_t)lv[l].njx * lv[l].njy < ((int64_t)1 << 31);
+    if (!ok) {
+        fclose(f);
+        return fail(m, NDT2D_EINVAL, "load_map: %s: bad level table", path);
+    }
+    cudaStreamSynchronize(m->cfg.stream);
+    drop_target(m, /*keep_memory=*/true);
+    m->prm.overlap = h.overlap; m->prm.min_points = h.min_points; m->prm.eig_ratio = h.eig_ratio;
+    m->nlevels = h.nlevels;
+    m->explicit_grid = h.explicit_grid != 0;
+    m->gox = h.gox; m->goy = h.goy; m->gex = h.gex; m->gey = h.gey;
+    std::vector<unsigned char> buf;
+    int rc = NDT2D_OK;
+    for (int l = 0; l < h.nlevels && rc == NDT2D_OK; ++l) {
+        m->res[l] = lv[l].res;
+        LevelDev &L = m->lv[l];
+        L = LevelDev{};
+        L.res = lv[l].res; L.ov = h.overlap;
+        derive_strides(L);
+        L.ox = lv[l].ox; L.oy = lv[l].oy; L.nhx = lv[l].nhx; L.nhy = lv[l].nhy;   // the saved lattice, exactly (auto-fitted or explicit)
+        rc = install_level(m, l);
+        if (rc) break;
+        const size_t nc = (size_t)L.njx * L.njy;
+        void *dst[3] = {m->mem[l].cells, m->mem[l].cnt, m->mem[l].sums};
+        const size_t bytes[3] = {nc * 32, nc * 4, nc * 40};
+        for (int part = 0; part < (h.has_sums ? 3 : 1) && rc == NDT2D_OK; ++part) {
+            buf.resize(bytes[part]);
+            if (fread(buf.data(), 1, bytes[part], f) != bytes[part]) {
+                rc = fail(m, NDT2D_EINVAL, "load_map: %s is truncated (level %d)", path, l);
+                break;
+            }
+            cudaError_t e = cudaMemcpyAsync(dst[part], buf.data(), bytes[part], cudaMemcpyHostToDevice, m->cfg.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(m->cfg.stream);
+            if (e != cudaSuccess) rc = fail(m, NDT2D_ECUDA, "load_map: %s", cudaGetErrorString(e));
+        }
+    }
+    fclose(f);
+    if (rc) {
+        drop_target(m);
+        return rc;
+    }
+    m->has_target = true;
+    m->sums_valid = h.has_sums != 0;
+    return NDT2D_OK;
 }
 
 int ndt2d_cell_index(ndt2d_matcher *m, int level, const float *xy, int n, const double *pose, int32_t *idx)
@@ -612,14 +755,15 @@ static int align_batch_device_impl(ndt2d_matcher *m, const float *d_xy, const in
 static int align_batch_fast(ndt2d_matcher *m, const float *xy, const int64_t *offsets, int nscans, int64_t total, int64_t maxn,
                             const double *init, ndt2d_result *res)
 {
-    if (!m->fast_host) {
-        CK(m, cudaHostAlloc(reinterpret_cast<void **>(&m->fast_host), ndt2d_matcher::FAST_BYTES, cudaHostAllocDefault));
-        CK(m, cudaHostAlloc(reinterpret_cast<void **>(&m->fast_res), ndt2d_matcher::FAST_SCANS * sizeof(ndt2d_result), cudaHostAllocMapped));
+    if (!m->fast_ready) {   // set only after every allocation below has succeeded: a failed attempt is simply repeated
+        if (!m->fast_host) CK(m, cudaHostAlloc(reinterpret_cast<void **>(&m->fast_host), ndt2d_matcher::FAST_BYTES, cudaHostAllocDefault));
+        if (!m->fast_res) CK(m, cudaHostAlloc(reinterpret_cast<void **>(&m->fast_res), ndt2d_matcher::FAST_SCANS * sizeof(ndt2d_result), cudaHostAllocMapped));
         CK(m, cudaHostGetDevicePointer(reinterpret_cast<void **>(&m->fast_res_dev), m->fast_res, 0));
         CK(m, m->b_fast.ensure(ndt2d_matcher::FAST_BYTES));
         CK(m, m->b_ring.ensure(ndt2d_matcher::RING * 4));
         CK(m, cudaMemsetAsync(m->b_ring.p, 0, ndt2d_matcher::RING * 4, m->cfg.stream));
         m->ring_pos = 0;
+        m->fast_ready = true;
     }
     if (m->ring_pos == ndt2d_matcher::RING) {   // every slot used once: zero the ring again (stream-ordered after its last user)
         CK(m, cudaMemsetAsync(m->b_ring.p, 0, ndt2d_matcher::RING * 4, m->cfg.stream));

@@ -18,6 +18,9 @@
 #ifndef NDT2D_UNROLL
 #define NDT2D_UNROLL 1
 #endif
+#ifndef NDT2D_JR1
+#define NDT2D_JR1 0 // 1: K = 1 kernels also take j from r by operand modifiers (see rotate_point)
+#endif
 #ifndef NDT2D_LDMODE
 #define NDT2D_LDMODE 4 // cell gather instruction variant; 4 = ld.global.nc.L1::no_allocate, one 256-bit load (measured best:
                        // a gathered record is rarely reused before L1 evicts it, and not allocating spares the fill bandwidth)
@@ -52,14 +55,41 @@ __device__ __forceinline__ float hsum(u64 v) { float a, b; upk(v, a, b); return 
 // t = f + 1.5 * 2^52 rounded towards -infinity: for 0 <= floor(f) < 2^32 the high word of t is the magic constant's and
 // the low word is floor(f), so the lattice test is two integer compares and NaN, infinities and huge values fail it.
 // df = (float)(f - h): the position inside the lattice square, in [0, 1] (the subtraction is exact).
-__device__ __forceinline__ bool node_of(double f, unsigned nh, unsigned &h, float &df)
+// Returns hi(t), which equals hi(magic) = 0x43380000 iff 0 <= floor(f) < 2^32.
+__device__ __forceinline__ unsigned node_of(double f, unsigned &h, float &df)
 {
     const double MAGIC = 6755399441055744.0; // 1.5 * 2^52
     const double t = __dadd_rd(f, MAGIC);
     const double n = __dadd_rn(t, -MAGIC);
     df = __double2float_rn(__dsub_rn(f, n));
     h = (unsigned)__double2loint(t);
-    return (__double2hiint(t) == 0x43380000) && (h < nh);
+    return (unsigned)__double2hiint(t);
+}
+
+// Index of table entry (hx, hy) if both coordinates are inside the lattice, else `outside`. Written in PTX so that the
+// test stays one LOP3 ((wx ^ C) | (wy ^ C)), three chained ISETP, one IMAD and one SEL: the compiler's own expansion of the
+// same expression is four compares feeding four dependent selects per point.
+__device__ __forceinline__ unsigned lattice_base(unsigned wx, unsigned wy, unsigned hx, unsigned hy, unsigned nhx, unsigned nhy,
+                                                 unsigned njx, unsigned outside)
+{
+    unsigned r;
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 bad, idx;\n\t"
+        "lop3.b32 bad, %1, %2, 0x43380000, 0x7e;\n\t"
+        "setp.eq.u32 p, bad, 0;\n\t"
+        "setp.lt.and.u32 p, %3, %5, p;\n\t"
+        "setp.lt.and.u32 p, %4, %6, p;\n\t"
+        "mad.lo.u32 idx, %4, %7, %3;\n\t"
+        "selp.u32 %0, idx, %8, p;\n\t}"
+        : "=r"(r)
+        : "r"(wx), "r"(wy), "r"(hx), "r"(hy), "r"(nhx), "r"(nhy), "r"(njx), "r"(outside));
+    return r;
+}
+
+__device__ __forceinline__ bool lattice_of(double fx, double fy, unsigned nhx, unsigned nhy, unsigned &hx, unsigned &hy, float &dfx,
+                                           float &dfy)
+{
+    const unsigned wx = node_of(fx, hx, dfx), wy = node_of(fy, hy, dfy);
+    return (wx == 0x43380000u) & (wy == 0x43380000u) & (hx < nhx) & (hy < nhy);
 }
 
 // a target point (no pose): f = ((double)X - (double)origin) * inv_st
@@ -67,11 +97,11 @@ __device__ __forceinline__ bool lattice_of_point(const LevelDev &L, float X, flo
 {
     unsigned ux, uy;
     float dfx, dfy;
-    const bool inx = node_of(__dmul_rn(__dsub_rn((double)X, (double)L.ox), L.inv_std), (unsigned)L.nhx, ux, dfx);
-    const bool iny = node_of(__dmul_rn(__dsub_rn((double)Y, (double)L.oy), L.inv_std), (unsigned)L.nhy, uy, dfy);
+    const bool in = lattice_of(__dmul_rn(__dsub_rn((double)X, (double)L.ox), L.inv_std), __dmul_rn(__dsub_rn((double)Y, (double)L.oy), L.inv_std),
+                               (unsigned)L.nhx, (unsigned)L.nhy, ux, uy, dfx, dfy);
     hx = (int)ux;
     hy = (int)uy;
-    return inx && iny;
+    return in;
 }
 
 // ---- SPEC 3: finalisation of one cell from its integer sums; f64, operations in the order the spec lists ----
@@ -245,11 +275,14 @@ __device__ __forceinline__ bool locate_point(const PosePk &P, float x, float y, 
     const double fx = __fma_rn(P.ci, xd, __fma_rn(-P.si, yd, P.txi));
     const double fy = __fma_rn(P.si, xd, __fma_rn(P.ci, yd, P.tyi));
     float dfx, dfy;
-    const bool inx = node_of(fx, nhx, hx, dfx);
-    const bool iny = node_of(fy, nhy, hy, dfy);
+    const bool in = lattice_of(fx, fy, nhx, nhy, hx, hy, dfx, dfy);
     df = pk(dfx, dfy);
-    return inx && iny;
+    return in;
 }
+
+// The same for the gather path: the index of the point's first cell in the table, or G.sentinel outside the lattice.
+struct LatticePk;
+__device__ __forceinline__ unsigned locate_base(const PosePk &P, float x, float y, const LatticePk &G, u64 &df);
 
 // ---- cell record: four f32 pairs in one 256-bit load ------------------------------------------------------
 struct Cell4 {
@@ -377,7 +410,7 @@ __device__ __forceinline__ void cell_factors(const Cell4 &cA, const Cell4 &cB, c
     u64 e = expneg2(nh);
     // skipped pairs get e = 0: fma(0, c, acc) == acc bit for bit (every c is finite, see sanitize())
     F.e = pk(okA ? lo32(e) : 0.0f, okB ? hi32(e) : 0.0f);
-    cnt += (okA ? 1 : 0) + (okB ? 1 : 0);
+    if (FULL) cnt += (okA ? 1 : 0) + (okB ? 1 : 0);   // the score-only sweep reports no count
     if (FULL) {
         float a2A = hsum(mul2(uA, A.j)), a2B = hsum(mul2(uB, B.j));
         u64 vA = fma2(cA.B0, bc(lo32(A.j)), mul2(cA.B1, bc(hi32(A.j))));
@@ -453,7 +486,9 @@ struct Fetched {
 
 struct LatticePk {
     unsigned nhx, nhy, njx;
-    unsigned sentinel; // index of the all-zero record that follows the cells of the table
+    unsigned sentinel; // dense tables: index of the first of the njx + 2 all-zero records that follow the cells (the gather target of
+                       // a point outside the lattice; sentinel + {0, 1, njx, njx + 1} are all zero records, so the four cells
+                       // of an outside point need no test of their own). Hash tables: the one zero record after the slots.
     unsigned mask;     // hash tables only: slots - 1
     float st;          // stride in metres: local coordinate = fma(df, st, off)
     u64 off[4];        // per cell of the point: minus the cell centre relative to node (hx, hy): (-st/2, -st/2) for one
@@ -478,34 +513,59 @@ __device__ __forceinline__ LatticePk lattice_pack(const LevelDev &L, bool hash)
     return G;
 }
 
+__device__ __forceinline__ unsigned locate_base(const PosePk &P, double xd, double yd, const LatticePk &G, u64 &df);
+__device__ __forceinline__ unsigned locate_base(const PosePk &P, float x, float y, const LatticePk &G, u64 &df)
+{
+    return locate_base(P, (double)x, (double)y, G, df);
+}
+// (xd, yd): the point already widened to f64 (the sweep kernel stages the scan that way: the conversions are done once)
+__device__ __forceinline__ unsigned locate_base(const PosePk &P, double xd, double yd, const LatticePk &G, u64 &df)
+{
+    const double fx = __fma_rn(P.ci, xd, __fma_rn(-P.si, yd, P.txi));
+    const double fy = __fma_rn(P.si, xd, __fma_rn(P.ci, yd, P.tyi));
+    float dfx, dfy;
+    unsigned hx, hy;
+    const unsigned wx = node_of(fx, hx, dfx), wy = node_of(fy, hy, dfy);
+    df = pk(dfx, dfy);
+    return lattice_base(wx, wy, hx, hy, G.nhx, G.nhy, G.njx, G.sentinel);
+}
+
 // slot of a cell key in a per-target hash table: Fibonacci hashing, bits 15.. of the product (tables have <= 2^16 slots)
 __device__ __forceinline__ unsigned hash_slot(unsigned key, unsigned mask) { return ((key * 0x9E3779B1u) >> 15) & mask; }
 
 // the point relative to the centre of its cell k (SPEC 4, v4): one f32 fma per coordinate
 __device__ __forceinline__ u64 local_xy(const LatticePk &G, u64 df, int k) { return fma2(df, bc(G.st), G.off[k]); }
 
-template <int OV, bool SMEM, bool HASH = false>
+// P64 (score-only kernels with the scan staged in shared memory): pts holds double2 per point, r and j are not needed
+template <int OV, bool SMEM, bool HASH = false, bool P64 = false>
 __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const LatticePk &G, const PosePk &P, const float2 *pts,
                                       int n, int i, Fetched<OV> &F)
 {
-    float2 a, b;
-    load_two<SMEM>(pts, n, i, a, b);
-    rotate_point<OV != 0>(P, a.x, a.y, F.A);
-    rotate_point<OV != 0>(P, b.x, b.y, F.B);
-    unsigned axh, ayh, bxh, byh;
-    const bool inA = locate_point(P, a.x, a.y, G.nhx, G.nhy, axh, ayh, F.A.df);
-    const bool inB = locate_point(P, b.x, b.y, G.nhx, G.nhy, bxh, byh, F.B.df);
-    const unsigned bA = ayh * G.njx + axh, bB = byh * G.njx + bxh;
+    unsigned bA, bB;
+    if (P64) {
+        const double2 a = reinterpret_cast<const double2 *>(pts)[i], b = reinterpret_cast<const double2 *>(pts)[i + 32];
+        F.A.r = F.A.j = F.B.r = F.B.j = 0ull;
+        bA = locate_base(P, a.x, a.y, G, F.A.df);
+        bB = locate_base(P, b.x, b.y, G, F.B.df);
+    } else {
+        float2 a, b;
+        load_two<SMEM>(pts, n, i, a, b);
+        rotate_point<OV != 0 || NDT2D_JR1>(P, a.x, a.y, F.A);
+        rotate_point<OV != 0 || NDT2D_JR1>(P, b.x, b.y, F.B);
+        bA = locate_base(P, a.x, a.y, G, F.A.df);
+        bB = locate_base(P, b.x, b.y, G, F.B.df);
+    }
     // K = 1: one record per point. K = 4: two rows of two adjacent records (64 contiguous bytes per row).
-    // Outside the lattice: the sentinel record (all zero = invalid), so the gather needs no predicate.
+    // Outside the lattice: the zero records behind the table (invalid), so the gather needs no predicate.
     if (!HASH) {
 #pragma unroll
         for (int k = 0; k < Fetched<OV>::NC; ++k) {
             const unsigned o = (k & 1) + (k >> 1) * G.njx;
-            F.cA[k] = load_cell(cells, inA ? bA + o : G.sentinel);
-            F.cB[k] = load_cell(cells, inB ? bB + o : G.sentinel);
+            F.cA[k] = load_cell(cells, bA + o);
+            F.cB[k] = load_cell(cells, bB + o);
         }
     } else {
+        const bool inA = bA != G.sentinel, inB = bB != G.sentinel;
         // hash tables: the first probes of all cells go out together; only then are the (rare) collisions chased
         unsigned sA[Fetched<OV>::NC], sB[Fetched<OV>::NC];
 #pragma unroll
@@ -563,7 +623,7 @@ template <bool FULL, bool TR>
 __device__ __forceinline__ void finish_partials(const Partials &S, int cnt, int lane, Eval &E);
 
 // HASH: L.cells is a per-target hash table (L.hash_mask), probed in fetch().
-template <int OV, bool FULL, bool SMEM, int PIPE, bool TR = false, bool HASH = false>
+template <int OV, bool FULL, bool SMEM, int PIPE, bool TR = false, bool HASH = false, bool P64 = false>
 __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E)
 {
     Partials S;
@@ -585,19 +645,19 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
         int i = lane;
         if ((npad >> 6) & 1) {
             Fetched<OV> cur;
-            fetch<OV, SMEM, HASH>(cells, G, P, pts, n, i, cur);
+            fetch<OV, SMEM, HASH, P64>(cells, G, P, pts, n, i, cur);
             accumulate_step<OV, FULL>(G, cur, S, cnt);
             i += 64;
         }
         if (i < npad) {
             const int last = npad - 64 + lane;
             Fetched<OV> F0, F1;
-            fetch<OV, SMEM, HASH>(cells, G, P, pts, n, i, F0);
+            fetch<OV, SMEM, HASH, P64>(cells, G, P, pts, n, i, F0);
 #pragma unroll 1
             for (; i < npad; i += 128) {
-                fetch<OV, SMEM, HASH>(cells, G, P, pts, n, i + 64, F1);
+                fetch<OV, SMEM, HASH, P64>(cells, G, P, pts, n, i + 64, F1);
                 accumulate_step<OV, FULL>(G, F0, S, cnt);
-                fetch<OV, SMEM, HASH>(cells, G, P, pts, n, min(i + 128, last), F0);
+                fetch<OV, SMEM, HASH, P64>(cells, G, P, pts, n, min(i + 128, last), F0);
                 accumulate_step<OV, FULL>(G, F1, S, cnt);
             }
         }
@@ -605,7 +665,7 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
 #pragma unroll kUnroll
         for (int i = lane; i < npad; i += 64) {
             Fetched<OV> cur;
-            fetch<OV, SMEM, HASH>(cells, G, P, pts, n, i, cur);
+            fetch<OV, SMEM, HASH, P64>(cells, G, P, pts, n, i, cur);
             accumulate_step<OV, FULL>(G, cur, S, cnt);
         }
     }

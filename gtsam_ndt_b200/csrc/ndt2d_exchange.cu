@@ -3,6 +3,8 @@
 // Reference interface: none citable (/root/reference/README.md:1 is the whole mount).
 #include "ndt2d_host.h"
 
+#include <time.h>
+
 using namespace ndt2d;
 
 extern "C" {
@@ -31,8 +33,10 @@ int ndt2d_exchange_close(ndt2d_matcher *m)
 int ndt2d_exchange_create(ndt2d_matcher *m, int world, int rank, int nslots, unsigned char *handle)
 {
     if (!m || !handle) return NDT2D_EINVAL;
-    if (world < 1 || world > NDT2D_MAX_RANKS || rank < 0 || rank >= world || nslots < 1 || nslots > 4096)
-        return fail(m, NDT2D_EINVAL, "exchange: world %d (max %d), rank %d, nslots %d", world, NDT2D_MAX_RANKS, rank, nslots);
+    // the slot discipline (wait for q - nslots/2 before publishing q) needs at least two rows as soon as there is a peer
+    if (world < 1 || world > NDT2D_MAX_RANKS || rank < 0 || rank >= world || nslots < (world > 1 ? 2 : 1) || nslots > 4096)
+        return fail(m, NDT2D_EINVAL, "exchange: world %d (max %d), rank %d, nslots %d (2..4096 when world > 1)", world, NDT2D_MAX_RANKS, rank,
+                    nslots);
     static_assert(sizeof(cudaIpcMemHandle_t) == NDT2D_IPC_HANDLE_BYTES, "CUDA IPC handle size");
     static_assert(sizeof(ndt2d_best) == 32, "ndt2d_best is 32 bytes");
     ndt2d_exchange_close(m);
@@ -51,6 +55,7 @@ int ndt2d_exchange_create(ndt2d_matcher *m, int world, int rank, int nslots, uns
         return fail(m, NDT2D_ECUDA, "exchange_create: %s", cudaGetErrorString(e));
     }
     memcpy(handle, &h, sizeof(h));
+    memset(m->ex_host, 0, 2 * bytes);   // both host snapshots start as "nothing published"
     m->ex_world = world; m->ex_rank = rank; m->ex_slots = nslots;
     m->ex_table[rank] = own;
     m->ex_verified_ok.assign((size_t)nslots, 0);
@@ -118,17 +123,18 @@ static void exchange_pick(const ndt2d_best *row, int W, int64_t *best_index, dou
     *best_score = bs;
 }
 
-// The poll copies the WHOLE table (nslots x world x 32 B, a few KB) to pinned memory on the copy stream, so that it never
-// waits for kernels queued on the handle's stream. A row is trusted only from a snapshot taken after an earlier snapshot
-// already showed all its epochs (record, system fence, epoch: a complete epoch guarantees the record was written before
-// the later copy started). The verified snapshot is kept, so waiting for several finished queries costs two copies in all.
+// The poll copies the row of the query (world x 32 B) to pinned memory on the copy stream, so that it never waits for
+// kernels queued on the handle's stream, and backs off between polls. A row is trusted only from a snapshot taken after
+// an earlier snapshot showed all its epochs (record, system fence, epoch: a complete epoch guarantees the record was
+// written before the later copy started). The verifying snapshot copies the whole table once, so that waiting for
+// several finished queries in a row costs one more small copy each at most.
 int ndt2d_exchange_wait(ndt2d_matcher *m, uint64_t query, int timeout_ms, int64_t *best_index, double *best_score)
 {
     if (!m || !best_index || !best_score) return NDT2D_EINVAL;
     if (m->ex_world == 0) return fail(m, NDT2D_EINVAL, "exchange_wait before exchange_create");
     DeviceGuard g(m->device);
     const int W = m->ex_world;
-    const size_t rows = (size_t)m->ex_slots, bytes = rows * W * sizeof(ndt2d_best);
+    const size_t rows = (size_t)m->ex_slots, bytes = rows * W * sizeof(ndt2d_best), row_bytes = (size_t)W * sizeof(ndt2d_best);
     const size_t row = (size_t)(query % (uint64_t)m->ex_slots);
     ndt2d_best *probe = m->ex_host, *verified = m->ex_host + rows * W;
     auto complete = [&](const ndt2d_best *t) {
@@ -141,21 +147,33 @@ int ndt2d_exchange_wait(ndt2d_matcher *m, uint64_t query, int timeout_ms, int64_
         return NDT2D_OK;
     }
     const auto t0 = std::chrono::steady_clock::now();
-    for (;;) {
-        CK(m, cudaMemcpyAsync(probe, m->ex_table[m->ex_rank], bytes, cudaMemcpyDeviceToHost, m->copy_stream));
+    for (int polls = 0;; ++polls) {
+        CK(m, cudaMemcpyAsync(probe + row * W, m->ex_table[m->ex_rank] + row * W, row_bytes, cudaMemcpyDeviceToHost, m->copy_stream));
         CK(m, cudaStreamSynchronize(m->copy_stream));
         if (complete(probe)) break;
-        const auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
-        if (ms > timeout_ms) return fail(m, NDT2D_ETIMEOUT, "exchange_wait: query %llu not published by every rank within %d ms",
-                                         (unsigned long long)query, timeout_ms);
+        const auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        if (us > (long long)timeout_ms * 1000)
+            return fail(m, NDT2D_ETIMEOUT, "exchange_wait: query %llu not published by every rank within %d ms", (unsigned long long)query,
+                        timeout_ms);
+        if (polls > 64) {   // a sweep takes 0.3-2 ms: after the first polls sleep a little instead of hammering the copy engine
+            struct timespec ts = {0, polls > 1024 ? 200000 : 20000};
+            nanosleep(&ts, nullptr);
+        }
     }
+    // the verifying snapshot: the whole table, so that rows of other finished queries are verified in passing. A row of it
+    // is verified if the polled row (this query) or the previous whole snapshot already showed the same complete epochs.
+    std::vector<uint64_t> before(rows);
+    for (size_t q = 0; q < rows; ++q) {
+        bool full = verified[q * W].epoch != 0;
+        for (int r = 1; r < W; ++r) full = full && verified[q * W + r].epoch == verified[q * W].epoch;
+        before[q] = full ? verified[q * W].epoch : 0;
+    }
+    before[row] = query + 1;   // shown complete by the poll above
     CK(m, cudaMemcpyAsync(verified, m->ex_table[m->ex_rank], bytes, cudaMemcpyDeviceToHost, m->copy_stream));
     CK(m, cudaStreamSynchronize(m->copy_stream));
-    for (size_t q = 0; q < rows; ++q) {   // a row of the second snapshot is verified if the first one already showed it complete
-        bool same = true;
-        for (int r = 0; r < W; ++r)
-            same = same && probe[q * W + r].epoch == verified[q * W + r].epoch && probe[q * W + r].epoch == probe[q * W].epoch &&
-                   probe[q * W].epoch != 0;
+    for (size_t q = 0; q < rows; ++q) {
+        bool same = before[q] != 0;
+        for (int r = 0; r < W; ++r) same = same && verified[q * W + r].epoch == before[q];
         m->ex_verified_ok[q] = same;
     }
     if (!m->ex_verified_ok[row] || !complete(verified))   // the row moved on between the two copies: slot discipline broken

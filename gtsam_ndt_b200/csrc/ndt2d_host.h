@@ -44,7 +44,9 @@ struct LevelMem {
     uint32_t *cnt = nullptr;
     unsigned long long *sums = nullptr;
     unsigned *dirty = nullptr; // incremental updates: one word per cell, zero between calls (allocated on the first ndt2d_add_target)
-    int64_t cap = 0; // cells the allocations can hold (plus the sentinel record)
+    int64_t cap = 0; // cells the allocations can hold (plus the zero records behind the table, see ZERO_PAD)
+    // all-zero records behind a dense table: a point outside the lattice gathers records sentinel + {0, 1, njx, njx + 1}
+    static int64_t zero_pad(int64_t njx) { return njx + 2; }
     void release()
     {
         if (cells) cudaFree(cells);
@@ -56,12 +58,12 @@ struct LevelMem {
     }
     // Grow-only: scan-to-scan odometry sets a new target of about the same size for every scan, and a
     // cudaFree/cudaMalloc pair per level and call costs more than building the grid.
-    cudaError_t ensure(int64_t nc)
+    cudaError_t ensure(int64_t nc, int64_t pad)
     {
-        if (nc <= cap) return cudaSuccess;
+        if (nc + pad <= cap) return cudaSuccess;
         release();
-        const int64_t want = nc + nc / 4 + 1024;
-        cudaError_t e = cudaMalloc(&cells, (size_t)(want + 1) * 32);
+        const int64_t want = nc + pad + nc / 4 + 1024;
+        cudaError_t e = cudaMalloc(&cells, (size_t)want * 32);
         if (e == cudaSuccess) e = cudaMalloc(&cnt, (size_t)want * 4);
         if (e == cudaSuccess) e = cudaMalloc(&sums, (size_t)want * 40);
         if (e != cudaSuccess) { release(); return e; }
@@ -107,6 +109,7 @@ struct ndt2d_matcher {
     // results written by the kernel straight into mapped pinned memory, work-queue counters from a pre-zeroed ring
     static constexpr size_t FAST_BYTES = 256 << 10;
     static constexpr int FAST_SCANS = 256, RING = 4096;
+    bool fast_ready = false;                 // every allocation of the fast path exists and the ring is zeroed
     unsigned char *fast_host = nullptr;      // pinned, FAST_BYTES
     ndt2d_result *fast_res = nullptr;        // pinned + mapped, FAST_SCANS records
     ndt2d_result *fast_res_dev = nullptr;    // its device address

@@ -201,9 +201,14 @@ __global__ void __launch_bounds__(EVAL_THREADS, FULL ? EVAL_BLOCKS_FULL : NDT2D_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int npad = (n + 63) & ~63;
     float2 *sp = reinterpret_cast<float2 *>(smem_raw);
+    constexpr bool P64 = STAGED && !FULL;   // the score-only sweep needs the points in f64 only: widen them once, here
     if (STAGED) {
         // sanitised points, padded with the far-away point to a multiple of 64 (SPEC 4)
-        for (int i = threadIdx.x; i < npad; i += blockDim.x) sp[i] = i < n ? sanitize(__ldg(xy + i)) : make_float2(1e18f, 1e18f);
+        for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+            const float2 p = i < n ? sanitize(__ldg(xy + i)) : make_float2(1e18f, 1e18f);
+            if (P64) reinterpret_cast<double2 *>(smem_raw)[i] = make_double2((double)p.x, (double)p.y);
+            else sp[i] = p;
+        }
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, FULL ? EVAL_BLOCKS_FULL : NDT2D_
         Pose32 q = pose_for_level(tx, ty, th, L);
         Eval E;
         // FULL: the transposed reduction leaves sum number E.slot in every lane (lanes with the same slot hold the same bits)
-        if (STAGED) eval_warp<OV, FULL, true, OV == 0 ? EVAL_PIPE : 0, FULL>(L, sp, n, q, lane, E);
+        if (STAGED) eval_warp<OV, FULL, true, OV == 0 ? EVAL_PIPE : 0, FULL, false, P64>(L, sp, n, q, lane, E);
         else eval_warp<OV, FULL, false, 0, FULL>(L, xy, n, q, lane, E);
         if (FULL) out[(size_t)j * out_stride + E.slot] = E.v[0];
         else if (lane == 0) out[(size_t)j * out_stride] = E.v[0];
@@ -780,7 +785,7 @@ template <int OV, bool FULL, bool F32POSE>
 static cudaError_t launch_eval_t(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const void *d_poses,
                                  int64_t npose, double *d_out, int out_stride, int32_t *d_count)
 {
-    size_t smem = (size_t)((n + 63) & ~63) * sizeof(float2);
+    size_t smem = (size_t)((n + 63) & ~63) * (FULL ? sizeof(float2) : sizeof(double2));   // score only: points staged as f64
     int grid = grid_for(npose, EVAL_THREADS / 32, c.sm_count, FULL ? EVAL_BLOCKS_FULL : NDT2D_EVAL_BLOCKS);
     if (smem <= (size_t)c.max_smem_optin - 1024) {
         auto kern = k_eval_poses<OV, FULL, F32POSE, true>;

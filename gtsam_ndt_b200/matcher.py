@@ -120,8 +120,14 @@ class NdtMatcher2D:
         return out
 
     def set_cells(self, cells, level=0):
+        """Load a cell table (njy, njx, 8) for `level`; the lattice must exist (set_grid or a target)."""
         cells = np.ascontiguousarray(cells, np.float32)
-        self._ck(self._L.ndt2d_set_cells(self._h, level, _ptr(cells)))
+        if cells.ndim != 3 or cells.shape[2] != 8:
+            raise ValueError("cells must have shape (njy, njx, 8)")
+        self._ck(self._L.ndt2d_set_cells(self._h, level, _ptr(cells), cells.shape[0] * cells.shape[1]))
+        g = self.geometry(level)
+        if cells.shape[:2] != (g["njy"], g["njx"]):     # same record count, other shape: rows would be sheared
+            raise ValueError(f"cells has shape {cells.shape[:2]}, level {level} is ({g['njy']}, {g['njx']})")
 
     def sums(self, level=0):
         g = self.geometry(level)
@@ -133,26 +139,21 @@ class NdtMatcher2D:
     def cells_device(self, level=0):
         return self._L.ndt2d_cells_device(self._h, level)
 
-    def save_map(self, path):
-        """Persist the target (geometry, parameters that shape the cells, every level's cell table) as .npz."""
-        g0 = self.geometry(0)
-        levels = [self.cells(l) for l in range(self.nlevels)]
-        res = np.array([self.geometry(l)["res"] for l in range(self.nlevels)], np.float32)
-        ext = np.array([g0["ox"], g0["oy"], g0["nhx"] * g0["st"], g0["nhy"] * g0["st"]], np.float32)
-        np.savez_compressed(path, format=np.int32(2), res=res, grid=ext, overlap=np.int32(self.params.overlap),
-                            min_points=np.int32(self.params.min_points), eig_ratio=np.float64(self.params.eig_ratio),
-                            **{f"cells{l}": c for l, c in enumerate(levels)})
+    def save_map(self, path, with_sums=True):
+        """Persist the target through the C ABI (ndt2d_save_map): every level's lattice exactly as built, the parameters that
+        shaped the cells, the records and (with_sums) the integer sums, so add_target continues the loaded map bit for bit."""
+        self._ck(self._L.ndt2d_save_map(self._h, str(path).encode(), 1 if with_sums else 0))
 
     def load_map(self, path):
-        """Inverse of save_map: restores the grid and cell tables (no point sums, so add_target is unavailable)."""
-        z = np.load(path)
-        if int(z["format"]) != 2:
-            raise NdtError("unknown map file format")
-        self.set_params(overlap=int(z["overlap"]), min_points=int(z["min_points"]), eig_ratio=float(z["eig_ratio"]))
-        self.set_resolutions(z["res"])
-        self.set_grid(*[float(v) for v in z["grid"]])
-        for l in range(self.nlevels):
-            self.set_cells(z[f"cells{l}"], level=l)
+        """Inverse of save_map (ndt2d_load_map): replaces resolutions, grid, overlap/min_points/eig_ratio and the target."""
+        self._ck(self._L.ndt2d_load_map(self._h, str(path).encode()))
+        self._ck(self._L.ndt2d_get_params(self._h, C.byref(self.params)))
+        n = 0
+        g = np.zeros(5, np.float32)
+        d = np.zeros(4, np.int32)
+        while n < 8 and self._L.ndt2d_level_geometry(self._h, n, g.ctypes.data_as(_lib.c_f32p), d.ctypes.data_as(_lib.c_i32p)) == 0:
+            n += 1
+        self.nlevels = n
 
     # -- evaluation ------------------------------------------------------------------------------
     def cell_index(self, xy, pose=None, level=0):
@@ -185,6 +186,13 @@ class NdtMatcher2D:
         return out
 
     # -- align -----------------------------------------------------------------------------------
+    @staticmethod
+    def _check_out(out, n):
+        """A caller-supplied result buffer is written by the C side as n x 144 bytes: refuse anything else."""
+        if not (isinstance(out, np.ndarray) and out.dtype == RESULT_DTYPE and out.flags.c_contiguous and out.size >= n):
+            raise ValueError(f"out must be a C-contiguous array of RESULT_DTYPE with at least {n} entries")
+        return out
+
     def align(self, xy, init):
         """align(scan, initial pose) -> record with pose, score, hessian (+ grad, iterations, status, count)."""
         xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
@@ -198,9 +206,9 @@ class NdtMatcher2D:
         offsets = np.ascontiguousarray(offsets, np.int64)
         init = np.ascontiguousarray(init, np.float64).reshape(-1, 3)
         nb = len(offsets) - 1
-        if len(init) != nb or (nb and offsets[-1] > len(xy)):
+        if nb < 0 or len(init) != nb or (nb and (offsets[0] < 0 or offsets[-1] > len(xy))):
             raise ValueError("offsets / init / xy sizes disagree")
-        r = np.zeros(nb, RESULT_DTYPE) if out is None else out
+        r = np.zeros(nb, RESULT_DTYPE) if out is None else self._check_out(out, nb)
         self._ck(self._L.ndt2d_align_batch(self._h, _ptr(xy), _ptr(offsets), nb, _ptr(init), _ptr(r)))
         return r
 
@@ -215,7 +223,9 @@ class NdtMatcher2D:
             r = r.astype(np.float32)
         r = np.atleast_2d(r)
         init = np.ascontiguousarray(init, np.float64).reshape(-1, 3)
-        res = np.zeros(len(r), RESULT_DTYPE) if out is None else out
+        if r.ndim != 2 or len(init) != r.shape[0]:
+            raise ValueError("ranges must be (nscans, nbeams) with one initial pose per scan")
+        res = np.zeros(len(r), RESULT_DTYPE) if out is None else self._check_out(out, len(r))
         self._ck(self._L.ndt2d_align_batch_ranges(self._h, _ptr(r), int(r.dtype == np.uint16), r.shape[0], r.shape[1],
                                                   angle_min, angle_inc, range_scale, range_min, range_max, _ptr(init), _ptr(res)))
         return res
@@ -247,7 +257,9 @@ class NdtMatcher2D:
         offsets = np.ascontiguousarray(offsets, np.int64)
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         init = np.ascontiguousarray(init, np.float64).reshape(-1, 3)
-        assert len(init) == len(pairs)
+        nb = len(offsets) - 1
+        if nb < 0 or len(init) != len(pairs) or (nb and (offsets[0] < 0 or offsets[-1] > len(xy))):
+            raise ValueError("offsets / pairs / init / xy sizes disagree")
         res = np.zeros(len(pairs), RESULT_DTYPE)
         self._ck(self._L.ndt2d_align_pairs(self._h, _ptr(xy), _ptr(offsets), len(offsets) - 1, _ptr(pairs), len(pairs), _ptr(init), _ptr(res)))
         return res

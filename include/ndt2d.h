@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NDT2D_VERSION 100
+#define NDT2D_VERSION 200      /* 200: SPEC.md v4 (f64 point-to-cell geometry, cell-local records) */
 #define NDT2D_MAX_LEVELS 8
 
 enum {
@@ -120,14 +120,22 @@ int ndt2d_add_target(ndt2d_matcher *m, const float *xy, int64_t n);
 int ndt2d_add_target_device(ndt2d_matcher *m, const float *d_xy, int64_t n);
 /* geom = {res, st, inv_st, ox, oy}; dims = {nhx, nhy, njx, njy} */
 int ndt2d_level_geometry(const ndt2d_matcher *m, int level, float geom[5], int32_t dims[4]);
-/* cell table: njx*njy records of 8 floats {mux, muy, B00, B01, B01, B11, n, valid} */
+/* cell table: njx*njy records of 8 floats {mux, muy, B00, B01, B01, B11, n, valid}; (mux, muy) is the mean RELATIVE TO THE
+ * CELL CENTRE ox + (jx - ov) * st + res / 2 (SPEC.md section 3, v4) */
 int ndt2d_get_cells(ndt2d_matcher *m, int level, float *cells);
-/* raw accumulators: n[njx*njy] and sums[njx*njy*5] = {sx, sy, sxx, sxy, syy} in 2^-20 m units */
+/* raw accumulators: n[njx*njy] and sums[njx*njy*5] = {sx, sy, sxx, sxy, syy} about the cell centre, in res * 2^-22 m units */
 int ndt2d_get_sums(ndt2d_matcher *m, int level, uint32_t *n, int64_t *sums);
 /* device pointer to the cell table of a level (valid until the target changes) */
 const float *ndt2d_cells_device(const ndt2d_matcher *m, int level);
-/* load a cell table computed elsewhere (e.g. saved by ndt2d_get_cells); geometry must be explicit */
-int ndt2d_set_cells(ndt2d_matcher *m, int level, const float *cells);
+/* load a cell table computed elsewhere (e.g. saved by ndt2d_get_cells); geometry must be explicit (ndt2d_set_grid) or
+ * already present; nrecords must equal the level's njx*njy. The target then has no sums (ndt2d_add_target is refused). */
+int ndt2d_set_cells(ndt2d_matcher *m, int level, const float *cells, int64_t nrecords);
+/* map files: every level's lattice exactly as built (auto-fitted or explicit), the parameters that
+ * shaped the cells (overlap, min_points, eig_ratio), the cell records and - with_sums != 0 - the integer sums, so that
+ * ndt2d_add_target continues a loaded map bit for bit. Versioned binary file ("NDT2DMAP"); ndt2d_load_map replaces the
+ * handle's resolutions, grid, those three parameters and the target. */
+int ndt2d_save_map(ndt2d_matcher *m, const char *path, int with_sums);
+int ndt2d_load_map(ndt2d_matcher *m, const char *path);
 
 /* ---- evaluation (kernel stage 2, the Newton-step unit of work, SPEC 2 and 4) ------------------ */
 /* lattice index hy*nhx+hx (or -1) of each point after the optional pose (NULL = none) */

@@ -75,6 +75,11 @@ class Matcher {
     void addToTarget(const Point2f *pts, std::int64_t n) { ck(ndt2d_add_target(h_, reinterpret_cast<const float *>(pts), n)); }
     void addToTarget(const std::vector<Point2f> &pts) { addToTarget(pts.data(), static_cast<std::int64_t>(pts.size())); }
 
+    // map files: every level's lattice, the cell records and (withSums) the integer sums behind them, so that addToTarget
+    // continues a loaded map bit for bit; loadMap replaces the resolutions, the grid and the target of this matcher
+    void saveMap(const std::string &path, bool withSums = true) { ck(ndt2d_save_map(h_, path.c_str(), withSums ? 1 : 0)); }
+    void loadMap(const std::string &path) { ck(ndt2d_load_map(h_, path.c_str())); }
+
     // ---- align(scan, initial pose) -> pose, score, Hessian -----------------------------------------
     Result align(const Point2f *scan, int n, const Pose2d &init)
     {
@@ -91,6 +96,7 @@ class Matcher {
     {
         const int nb = static_cast<int>(init.size());
         if (offsets.size() != init.size() + 1) throw std::invalid_argument("alignBatch: offsets.size() must be init.size() + 1");
+        if (offsets.front() < 0 || static_cast<size_t>(offsets.back()) > points.size()) throw std::invalid_argument("alignBatch: offsets overrun points");
         std::vector<Result> out(init.size());
         static_assert(sizeof(Pose2d) == 3 * sizeof(double), "Pose2d must be three packed doubles");
         ck(ndt2d_align_batch(h_, reinterpret_cast<const float *>(points.data()), offsets.data(), nb,
@@ -102,6 +108,8 @@ class Matcher {
     std::vector<Result> alignBatchRanges(const std::vector<float> &ranges, int nbeams, double angle_min, double angle_inc,
                                          float range_min, float range_max, const std::vector<Pose2d> &init)
     {
+        if (nbeams < 1 || ranges.size() != init.size() * static_cast<size_t>(nbeams))
+            throw std::invalid_argument("alignBatchRanges: ranges.size() must be init.size() * nbeams");
         std::vector<Result> out(init.size());
         ck(ndt2d_align_batch_ranges(h_, ranges.data(), 0, static_cast<int>(init.size()), nbeams, angle_min, angle_inc, 1.0f,
                                     range_min, range_max, reinterpret_cast<const double *>(init.data()), out.data()));
@@ -115,6 +123,7 @@ class Matcher {
     {
         if (pairs.size() != init.size()) throw std::invalid_argument("alignPairs: one initial pose per pair");
         if (offsets.empty()) throw std::invalid_argument("alignPairs: offsets must have nscans + 1 entries");
+        if (offsets.front() < 0 || static_cast<size_t>(offsets.back()) > points.size()) throw std::invalid_argument("alignPairs: offsets overrun points");
         static_assert(sizeof(std::pair<std::int32_t, std::int32_t>) == 2 * sizeof(std::int32_t), "pairs must be packed int32 pairs");
         std::vector<Result> out(pairs.size());
         ck(ndt2d_align_pairs(h_, reinterpret_cast<const float *>(points.data()), offsets.data(), static_cast<int>(offsets.size() - 1),
