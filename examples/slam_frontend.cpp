@@ -78,13 +78,16 @@ ndt2d::Pose2d between(const ndt2d::Pose2d &a, const ndt2d::Pose2d &b)   // a^-1 
 struct Edge { int i, j; ndt2d::Pose2d z; double info[6]; bool loop; };
 
 // The matcher's pose is the scan frame expressed in the target frame, so with target = scan i and source = scan j the
-// result IS the relative pose z_ij, and its Hessian (of f = -score, order x, y, theta) is the factor's information.
+// result IS the relative pose z_ij. Its Hessian (of f = -score, order x, y, theta) is taken in the target frame; EDGE_SE2
+// (like gtsam::BetweenFactor<Pose2>) measures the error in the local frame of the measurement, hence the rotation
+// J^T H J, J = blockdiag(R(theta), 1), done by ndt2d::informationInLocalFrame.
 Edge make_edge(int i, int j, const ndt2d::Result &r, bool loop)
 {
     Edge e{i, j, {r.pose[0], r.pose[1], r.pose[2]}, {}, loop};
-    const double *H = r.hessian;
-    e.info[0] = H[0]; e.info[1] = 0.5 * (H[1] + H[3]); e.info[2] = 0.5 * (H[2] + H[6]);
-    e.info[3] = H[4]; e.info[4] = 0.5 * (H[5] + H[7]); e.info[5] = H[8];
+    double H[9];
+    ndt2d::informationInLocalFrame(r, H);
+    e.info[0] = H[0]; e.info[1] = H[1]; e.info[2] = H[2];
+    e.info[3] = H[4]; e.info[4] = H[5]; e.info[5] = H[8];
     return e;
 }
 

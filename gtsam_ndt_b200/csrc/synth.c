@@ -16,7 +16,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
-#define SYNTH_MAX_BOXES 1024
+#define SYNTH_MAX_BOXES 32768
 #define WALL 95.0
 #define TRAJ_R 60.0
 
@@ -24,14 +24,23 @@ typedef struct { double x0, y0, x1, y1; } box_t;
 
 #define GRID_N 20          /* broad phase: 20 x 20 buckets of 10 m over [-100, 100]^2 */
 #define GRID_CELL 10.0
-#define GRID_MAX 64
+#define GRID_MAX 512
 
 typedef struct {
     int nboxes;
     box_t box[SYNTH_MAX_BOXES];
     int bucket_n[GRID_N][GRID_N];
-    short bucket[GRID_N][GRID_N][GRID_MAX];
+    int bucket[GRID_N][GRID_N][GRID_MAX];
 } world_t;
+
+/* Shape of the candidate boxes: half sizes U[h_min, h_min + h_span] m, kept `clear` m away from the trajectory. The
+ * defaults are the SURVEY 8(d) room (about 230 boxes survive of 400 candidates: 14 k occupied 0.25 m cells); the "dense"
+ * world of bench.py (--world dense) uses many small boxes so that a third of the 640 k map cells are occupied. */
+static double g_hmin = 1.0, g_hspan = 3.0, g_clear = 3.0;
+void synth_set_world(double h_min, double h_span, double clear)
+{
+    g_hmin = h_min; g_hspan = h_span; g_clear = clear;
+}
 
 static uint64_t splitmix64(uint64_t *s)
 {
@@ -49,9 +58,9 @@ static void build_world(world_t *w, uint64_t seed, int ncand)
     if (ncand > SYNTH_MAX_BOXES) ncand = SYNTH_MAX_BOXES;
     for (int i = 0; i < ncand; ++i) {
         double cx = -90.0 + 180.0 * u01(&s), cy = -90.0 + 180.0 * u01(&s);
-        double hx = 1.0 + 3.0 * u01(&s), hy = 1.0 + 3.0 * u01(&s);
+        double hx = g_hmin + g_hspan * u01(&s), hy = g_hmin + g_hspan * u01(&s);
         double dist = fabs(sqrt(cx * cx + cy * cy) - TRAJ_R);
-        if (dist < sqrt(hx * hx + hy * hy) + 3.0) continue;
+        if (dist < sqrt(hx * hx + hy * hy) + g_clear) continue;
         box_t b = {cx - hx, cy - hy, cx + hx, cy + hy};
         if (b.x0 < -WALL + 0.5 || b.x1 > WALL - 0.5 || b.y0 < -WALL + 0.5 || b.y1 > WALL - 0.5) continue;
         w->box[w->nboxes++] = b;
@@ -63,7 +72,7 @@ static void build_world(world_t *w, uint64_t seed, int ncand)
         int y0 = (int)floor((b->y0 + 100.0) / GRID_CELL), y1 = (int)floor((b->y1 + 100.0) / GRID_CELL);
         for (int gy = y0; gy <= y1; ++gy) for (int gx = x0; gx <= x1; ++gx)
             if (gx >= 0 && gx < GRID_N && gy >= 0 && gy < GRID_N && w->bucket_n[gy][gx] < GRID_MAX)
-                w->bucket[gy][gx][w->bucket_n[gy][gx]++] = (short)i;
+                w->bucket[gy][gx][w->bucket_n[gy][gx]++] = i;
     }
 }
 

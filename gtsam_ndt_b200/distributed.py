@@ -80,6 +80,47 @@ def all_gather_blobs(blob):
     return [bytes(t.cpu().numpy().tobytes()) for t in out]
 
 
+def all_gather_array(a):
+    """All-gather one equally shaped numpy array per rank (any dtype, sent as bytes); returns the list by rank."""
+    a = np.ascontiguousarray(a)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [a.copy()]
+    blobs = all_gather_blobs(a.tobytes()) if a.nbytes else [b""] * dist.get_world_size()
+    return [np.frombuffer(b, dtype=a.dtype).reshape(a.shape).copy() for b in blobs]
+
+
+def relocalize_sharded(matcher, xy, hyp, k=4, level=0):
+    """Multi-GPU relocalisation end to end: every rank sweeps its contiguous shard of `hyp` (the same array on every
+    rank) and keeps its top-k, the per-rank lists are combined into the global top-k (combine_topk: 16 B x k per rank),
+    the k candidates are dealt out over the ranks again, every rank refines its share with the full align
+    (ndt2d_align_batch) and the result records are all-gathered. Every rank returns (idx[k], res[k]) ordered like the
+    top-k - bit for bit what ndt2d_relocalize returns on one GPU (SPEC 6: ties to the smaller global index; an align does
+    not depend on the batch it runs in)."""
+    from .matcher import RESULT_DTYPE, NO_OVERLAP
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    hyp = np.ascontiguousarray(hyp, np.float32).reshape(-1, 3)
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    lo, hi = shard_range(len(hyp), rank, world)
+    _, li, ls = matcher.sweep(xy, hyp[lo:hi], k=k, level=level, want_scores=False)
+    li = np.asarray(li, np.int64).copy()
+    li[li >= 0] += lo
+    gi, _ = combine_topk(li, ls, k)
+    kk = int((gi >= 0).sum())
+    a, b = shard_range(kk, rank, world)
+    kmax = -(-k // world)                                   # records per rank in the gather (padded)
+    mine = np.zeros(kmax, RESULT_DTYPE)
+    if b > a:
+        scans, off = np.tile(xy, (b - a, 1)), np.arange(b - a + 1, dtype=np.int64) * len(xy)
+        mine[: b - a] = matcher.align_batch(scans, off, hyp[gi[a:b]].astype(np.float64))
+    res = np.zeros(k, RESULT_DTYPE)
+    res["status"][kk:] = NO_OVERLAP
+    for r, part in enumerate(all_gather_array(mine)):
+        ra, rb = shard_range(kk, r, world)
+        res[ra:rb] = part[: rb - ra]
+    return gi, res
+
+
 class PeerExchange:
     """Best-hypothesis combine of a sharded sweep through peer memory (include/ndt2d.h, ndt2d_exchange_*).
 
@@ -104,8 +145,10 @@ class PeerExchange:
         return self.m.exchange_wait(query, timeout_ms)
 
     def close(self):
+        # every kernel this rank queued has finished storing into the peers' tables before anybody frees a table
+        self.m.synchronize()
         if self.world > 1:
-            dist.barrier()          # nobody frees a table a peer may still be writing to
+            dist.barrier()
         self.m.exchange_close()
 
 

@@ -52,9 +52,38 @@ def uniform3(n, first=0, seed=PERTURB_SEED):
 
 
 def boxes(seed=WORLD_SEED, nboxes=NBOXES):
-    out = np.zeros((1024, 4), np.float64)
-    n = lib().synth_world_boxes(C.c_uint64(seed), C.c_int(nboxes), out.ctypes.data_as(C.POINTER(C.c_double)), 1024)
+    out = np.zeros((32768, 4), np.float64)
+    n = lib().synth_world_boxes(C.c_uint64(seed), C.c_int(nboxes), out.ctypes.data_as(C.POINTER(C.c_double)), 32768)
     return out[:n]
+
+
+DENSE_NBOXES = 30000
+
+
+def set_world(dense=False):
+    """Box shape of the synthetic world for every later call: the SURVEY 8(d) room (default), or the cluttered "dense"
+    world (pass nboxes=DENSE_NBOXES to scans / boxes): ~17 000 boxes of 0.6-2 m, 1.5 m clear of the trajectory."""
+    if dense:
+        lib().synth_set_world(C.c_double(0.3), C.c_double(0.7), C.c_double(1.5))
+    else:
+        lib().synth_set_world(C.c_double(1.0), C.c_double(3.0), C.c_double(3.0))
+
+
+def dense_map(seed=WORLD_SEED, nboxes=DENSE_NBOXES, spacing=0.04, sigma=0.01):
+    """Map cloud of the dense world: every box edge and the outer walls sampled every `spacing` m with Gaussian noise, as a
+    surveyed map would hold them (a lidar on the loop alone sees a few percent of the boxes). Call set_world(dense=True) first."""
+    bx = boxes(seed, nboxes)
+    rng = np.random.default_rng(seed)
+    segs = []
+    for x0, y0, x1, y1 in np.concatenate([bx, [[-95.0, -95.0, 95.0, 95.0]]]):
+        segs += [(x0, y0, x1, y0), (x1, y0, x1, y1), (x1, y1, x0, y1), (x0, y1, x0, y0)]
+    segs = np.array(segs)
+    ln = np.hypot(segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1])
+    cnt = np.maximum(2, np.ceil(ln / spacing).astype(np.int64))
+    t = np.concatenate([np.linspace(0.0, 1.0, c, endpoint=False) for c in cnt])
+    si = np.repeat(np.arange(len(segs)), cnt)
+    pts = segs[si, :2] + t[:, None] * (segs[si, 2:] - segs[si, :2])
+    return (pts + rng.normal(size=pts.shape) * sigma).astype(np.float32)
 
 
 def beam_table(nbeams, angle_min, angle_inc):

@@ -11,6 +11,7 @@
 #define NDT2D_HPP
 
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -31,6 +32,24 @@ struct Pose2d {
 
 using Result = ndt2d_result;   // pose[3], score, grad[3], hessian[9] (row-major), iterations, status, count
 using Params = ndt2d_params;
+
+// The Hessian align() returns is taken with respect to increments (dtx, dty, dtheta) of the pose IN THE TARGET FRAME
+// (x' = R(theta) x + t). Pose-graph back ends (gtsam::BetweenFactor<Pose2>, g2o EDGE_SE2) express the translation error
+// of a relative-pose measurement in the measurement's own (local) frame, dt_target = R(theta) dt_local, so the information
+// matrix of such a factor is J^T H J with J = blockdiag(R(theta), 1). Writes the symmetrised 3x3 result, row-major.
+// (For odometry theta is small and the two nearly coincide; for loop closures at large relative rotation they do not.)
+inline void informationInLocalFrame(const ndt2d_result &r, double info[9])
+{
+    const double c = std::cos(r.pose[2]), s = std::sin(r.pose[2]);
+    const double J[3][3] = {{c, -s, 0.0}, {s, c, 0.0}, {0.0, 0.0, 1.0}};
+    double H[3][3], T[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) H[i][j] = 0.5 * (r.hessian[3 * i + j] + r.hessian[3 * j + i]);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) T[i][j] = H[i][0] * J[0][j] + H[i][1] * J[1][j] + H[i][2] * J[2][j];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) info[3 * i + j] = J[0][i] * T[0][j] + J[1][i] * T[1][j] + J[2][i] * T[2][j];
+}
 
 class Matcher {
   public:

@@ -1,7 +1,8 @@
 // ndt2d_gtsam.hpp — glue from ndt2d results to GTSAM factors.
 //
 // Compiles to nothing unless GTSAM's headers are on the include path: GTSAM, Eigen and Boost are absent from
-// the build container, so this file is exercised only by its include guard there. The sparse incremental
+// the build container, so there it is compiled against a type stub only (tests/gtsam_stub/, tests/test_cpp_host.py:
+// the header parses, the factor receives the rotated information matrix). The sparse incremental
 // iSAM2 back end stays on the host in GTSAM, as BASELINE.json's north_star requires; nothing here replaces it.
 // Reference glue code replaced: none citable (/root/reference/README.md:1 is the whole mount).
 #ifndef NDT2D_GTSAM_HPP
@@ -25,13 +26,17 @@ namespace ndt2d {
 
 inline gtsam::Pose2 toPose2(const Result &r) { return gtsam::Pose2(r.pose[0], r.pose[1], r.pose[2]); }
 
-// The Hessian of f = -score at the optimum, symmetrised, as the information matrix of the relative pose.
-// `scale` maps the NDT score scale to the caller's noise scale (1 keeps it as returned).
+// The Hessian of f = -score at the optimum as the information matrix of the relative pose, in the frame the factor
+// uses: BetweenFactor<Pose2> measures the error in the local (measurement) frame, the matcher's Hessian is in the target
+// frame, so it is rotated by J = blockdiag(R(theta), 1) (informationInLocalFrame in ndt2d.hpp). `scale` maps the NDT score
+// scale to the caller's noise scale (1 keeps it as returned).
 inline gtsam::SharedNoiseModel toNoiseModel(const Result &r, double scale = 1.0)
 {
+    double info[9];
+    informationInLocalFrame(r, info);
     gtsam::Matrix3 H;
     for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) H(i, j) = 0.5 * scale * (r.hessian[3 * i + j] + r.hessian[3 * j + i]);
+        for (int j = 0; j < 3; ++j) H(i, j) = scale * info[3 * i + j];
     return gtsam::noiseModel::Gaussian::Information(H);
 }
 

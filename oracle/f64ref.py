@@ -1,4 +1,7 @@
-"""An independent double-precision 2D NDT ("f64 twin") used to bound how far the product's arithmetic is from a
+"""TEST INFRASTRUCTURE (like everything under oracle/): only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
+leg may import it; the product never does.
+
+An independent double-precision 2D NDT ("f64 twin") used to bound how far the product's arithmetic is from a
 plain f64 implementation of the same algorithm (north_star tolerances: pose 1e-5 m / 1e-6 rad, score and Hessian
 1e-6 relative, cell assignment exact).
 

@@ -62,3 +62,16 @@ def test_slam_frontend_writes_a_pose_graph(tmp_path):
         c22 = i[0] * i[3] - i[1] * i[1]
         det = i[0] * (i[3] * i[5] - i[4] * i[4]) - i[1] * (i[1] * i[5] - i[4] * i[2]) + i[2] * (i[1] * i[4] - i[3] * i[2])
         assert i[0] > 0 and c22 > 0 and det > 0
+
+
+def test_gtsam_glue_compiles_against_type_stub_and_rotates_the_hessian(tmp_path):
+    """include/ndt2d_gtsam.hpp is compile-gated on GTSAM's headers, which this container does not have. A type stub of the
+    four GTSAM names it uses (tests/gtsam_stub: NOT a solver) makes the header parse and lets the check read back the factor:
+    the information matrix must be J^T H J, J = blockdiag(R(theta), 1) (it used to be H in the wrong frame)."""
+    exe = str(tmp_path / "gtsam_glue_check")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "tests", "gtsam_stub"), os.path.join(ROOT, "tests", "gtsam_glue_check.cpp"), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "gtsam glue ok" in r.stdout, (r.returncode, r.stdout, r.stderr)

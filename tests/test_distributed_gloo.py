@@ -39,6 +39,27 @@ def _worker(rank, world, port, q):
         full, _, _ = o.sweep(xy, hyp, nthreads=1)
         exp = np.lexsort((np.arange(len(full)), -full))[:5]
         ok = np.array_equal(gi, exp) and np.array_equal(gs, full[exp])
+        # multi-GPU relocalisation (sharded sweep -> global top-k -> refinement dealt out over the ranks -> gathered records)
+        # with the oracle standing in for this rank's GPU matcher: every rank must hold what one matcher computes alone
+        class OracleMatcher:
+            def sweep(self, xy_, hyp_, k=1, level=0, want_scores=True):
+                return (None,) + score_shard_of(hyp_, k)
+
+            def align_batch(self, xy_, off_, init_):
+                return o.align_batch(xy_, off_, init_, nthreads=1)
+
+        def score_shard_of(h, k):
+            s, _, _ = o.sweep(xy, h, nthreads=1)
+            order = np.lexsort((np.arange(len(s)), -s))[:k]
+            idx = np.full(k, -1, np.int64); val = np.zeros(k)
+            idx[: len(order)] = order; val[: len(order)] = s[order]
+            return idx, val
+
+        for kk in (1, 3, 5):
+            ri, rr = D.relocalize_sharded(OracleMatcher(), xy, hyp, k=kk)
+            ei, _ = score_shard_of(hyp, kk)
+            er = o.align_batch(np.tile(xy, (kk, 1)), np.arange(kk + 1, dtype=np.int64) * len(xy), hyp[ei].astype(np.float64), nthreads=1)
+            ok = ok and np.array_equal(ri, ei) and rr.tobytes() == er.tobytes()
         lo, hi = D.align_sharded_counts(101)
         # the plumbing of the peer-memory exchange: one 64-byte blob per rank (a CUDA IPC handle on the GPU box), by rank
         blobs = D.all_gather_blobs(bytes([rank + 1]) * 64)

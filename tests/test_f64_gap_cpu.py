@@ -1,5 +1,5 @@
 """CPU counterpart of test_gpu_vs_f64.py: the SPEC ORACLE (bit-identical to the CUDA path, see test_gpu_parity.py)
-against the independent double-precision twin in tests/f64ref.py, at north_star's tolerances. This pins SPEC.md v4's
+against the independent double-precision twin in oracle/f64ref.py, at north_star's tolerances. This pins SPEC.md v4's
 claim that a f32 per-point algebra on cell-local coordinates stays within 1e-6 of f64 arithmetic (v3 did not: 1.3e-4
 on the score, 7e-3 on the Hessian with the same inputs).
 PARITY UNPINNED: the twin stands in for the reference's double-precision CPU NDT, which is not in the mount."""
@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle
-from tests import f64ref
+from oracle import f64ref
 
 
 @pytest.fixture(scope="module")

@@ -1,7 +1,7 @@
 """How far is the CUDA path from a plain double-precision NDT? (missing #2.)
 
 The bit-exact GPU-vs-oracle tests only show that two implementations of SPEC.md agree. This file measures the product
-against `tests/f64ref.py`, an independent f64 implementation of the same algorithm that follows none of SPEC.md's
+against `oracle/f64ref.py`, an independent f64 implementation of the same algorithm that follows none of SPEC.md's
 bit-level choices, at BASELINE.json's north_star tolerances:
 
   score and Hessian within 1e-6 relative - checked on evaluations at the f64 twin's converged poses (configs[1]:
@@ -20,7 +20,7 @@ import math
 import numpy as np
 import pytest
 
-from tests import f64ref
+from oracle import f64ref
 
 pytestmark = pytest.mark.gpu
 
