@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ndt2d.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert lib.ndt2d_version() == 100
+    assert lib.ndt2d_version() == 200
 
 
 def test_struct_layouts_match_header_and_oracle():
