@@ -134,6 +134,55 @@ __device__ __forceinline__ void finalize_record(unsigned n, long long s0, long l
     rb = make_float4(b01, (float)(cxx / det), (float)n, 1.0f);
 }
 
+// ---- SPEC 3: accumulation of one warp-wide window of target points ---------------------------------------------
+// One point per lane (valid == false: no point). For each of the K cells of the point, lanes holding the same cell in
+// consecutive positions (laser scans are spatially coherent) are combined with a segmented shuffle reduction and the
+// head of each run hands the run's count and five integer sums to `sink(key, count, sx, sy, sxx, sxy, syy)`, key being
+// the table index jy * njx + jx. Integer sums are associative, so any sink (global atomics into the dense table,
+// compare-and-swap into a hash table, ...) gives the cells SPEC 3 defines. Used by k_accumulate and k_pairs_build.
+template <int OV, class Sink>
+__device__ __forceinline__ void accumulate_window(const LevelDev &L, bool valid, float X, float Y, int lane, Sink sink)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int K = OV ? 2 : 1;
+    int hx = 0, hy = 0;
+    const bool inside = valid && lattice_of_point(L, X, Y, hx, hy);
+#pragma unroll
+    for (int b = 0; b < K; ++b) {
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+            const int jx = hx + a, jy = hy + b;
+            const int key = inside ? jy * L.njx + jx : -1;
+            const double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
+            const double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
+            const double dx = (double)X - cx, dy = (double)Y - cy;
+            const long long qx = inside ? __double2ll_rn(dx * L.qs) : 0;
+            const long long qy = inside ? __double2ll_rn(dy * L.qs) : 0;
+            int c = inside ? 1 : 0;
+            long long sx = qx, sy = qy, sxx = qx * qx, sxy = qx * qy, syy = qy * qy;
+            // run id: number of run heads at or below this lane
+            const int prev = __shfl_up_sync(FULL, key, 1);
+            const bool head = (lane == 0) || (prev != key);
+            const unsigned heads = __ballot_sync(FULL, head);
+            const int rid = __popc(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int rid2 = __shfl_down_sync(FULL, rid, d);
+                const int c2 = __shfl_down_sync(FULL, c, d);
+                const long long sx2 = __shfl_down_sync(FULL, sx, d);
+                const long long sy2 = __shfl_down_sync(FULL, sy, d);
+                const long long sxx2 = __shfl_down_sync(FULL, sxx, d);
+                const long long sxy2 = __shfl_down_sync(FULL, sxy, d);
+                const long long syy2 = __shfl_down_sync(FULL, syy, d);
+                if (lane + d < 32 && rid2 == rid) {
+                    c += c2; sx += sx2; sy += sy2; sxx += sxx2; sxy += sxy2; syy += syy2;
+                }
+            }
+            if (head && key >= 0) sink(key, (unsigned)c, sx, sy, sxx, sxy, syy);
+        }
+    }
+}
+
 // ---- SPEC 4.1: exp(-h), bit-exact sequence of f32 operations -----------------------------------------
 __device__ __forceinline__ float expneg(float h)
 {
@@ -280,7 +329,7 @@ __device__ __forceinline__ bool locate_point(const PosePk &P, float x, float y, 
     return in;
 }
 
-// The same for the gather path: the index of the point's first cell in the table, or G.sentinel outside the lattice.
+// The same for the gather path: the index of the point's first cell in the table, or G.outside outside the lattice.
 struct LatticePk;
 __device__ __forceinline__ unsigned locate_base(const PosePk &P, float x, float y, const LatticePk &G, u64 &df);
 
@@ -490,6 +539,8 @@ struct LatticePk {
                        // a point outside the lattice; sentinel + {0, 1, njx, njx + 1} are all zero records, so the four cells
                        // of an outside point need no test of their own). Hash tables: the one zero record after the slots.
     unsigned mask;     // hash tables only: slots - 1
+    unsigned outside;  // what lattice_base() returns for a point outside the lattice: `sentinel` for dense tables (the gather
+                       // goes straight to the zero records); 0xffffffff for hash tables, where every smaller value is a cell key
     float st;          // stride in metres: local coordinate = fma(df, st, off)
     u64 off[4];        // per cell of the point: minus the cell centre relative to node (hx, hy): (-st/2, -st/2) for one
                        // grid; (-a st, -b st) for cell (a, b) of the four half-shifted grids
@@ -502,6 +553,7 @@ __device__ __forceinline__ LatticePk lattice_pack(const LevelDev &L, bool hash)
     G.nhx = (unsigned)L.nhx; G.nhy = (unsigned)L.nhy; G.njx = (unsigned)L.njx;
     G.mask = L.hash_mask;
     G.sentinel = hash ? L.hash_mask + 1u : (unsigned)L.njx * (unsigned)L.njy;
+    G.outside = hash ? 0xffffffffu : G.sentinel;
     G.st = L.st;
     if (OV) {
 #pragma unroll
@@ -527,7 +579,7 @@ __device__ __forceinline__ unsigned locate_base(const PosePk &P, double xd, doub
     unsigned hx, hy;
     const unsigned wx = node_of(fx, hx, dfx), wy = node_of(fy, hy, dfy);
     df = pk(dfx, dfy);
-    return lattice_base(wx, wy, hx, hy, G.nhx, G.nhy, G.njx, G.sentinel);
+    return lattice_base(wx, wy, hx, hy, G.nhx, G.nhy, G.njx, G.outside);
 }
 
 // slot of a cell key in a per-target hash table: Fibonacci hashing, bits 15.. of the product (tables have <= 2^16 slots)
@@ -565,7 +617,7 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
             F.cB[k] = load_cell(cells, bB + o);
         }
     } else {
-        const bool inA = bA != G.sentinel, inB = bB != G.sentinel;
+        const bool inA = bA != G.outside, inB = bB != G.outside;
         // hash tables: the first probes of all cells go out together; only then are the (rare) collisions chased
         unsigned sA[Fetched<OV>::NC], sB[Fetched<OV>::NC];
 #pragma unroll

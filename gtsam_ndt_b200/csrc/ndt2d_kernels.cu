@@ -30,61 +30,20 @@ __global__ void __launch_bounds__(256) k_accumulate(const LevelDev L, const floa
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    constexpr int K = OV ? 2 : 1;
     for (int64_t base = warp_id * 32; base < n; base += warps_total * 32) {
-        int64_t i = base + lane;
-        float X = 0.0f, Y = 0.0f;
-        bool inside = false;
-        int hx = 0, hy = 0;
-        if (i < n) {
-            float2 p = __ldg(xy + i);
-            X = p.x;
-            Y = p.y;
-            inside = lattice_of_point(L, X, Y, hx, hy);
-        }
-#pragma unroll
-        for (int b = 0; b < K; ++b) {
-#pragma unroll
-            for (int a = 0; a < K; ++a) {
-                int jx = hx + a, jy = hy + b;
-                int key = inside ? jy * L.njx + jx : -1;
-                double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
-                double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
-                double dx = (double)X - cx, dy = (double)Y - cy;
-                long long qx = inside ? __double2ll_rn(dx * L.qs) : 0;
-                long long qy = inside ? __double2ll_rn(dy * L.qs) : 0;
-                int c = inside ? 1 : 0;
-                long long sx = qx, sy = qy, sxx = qx * qx, sxy = qx * qy, syy = qy * qy;
-                // run id: number of run heads at or below this lane
-                int prev = __shfl_up_sync(FULL_MASK, key, 1);
-                bool head = (lane == 0) || (prev != key);
-                unsigned heads = __ballot_sync(FULL_MASK, head);
-                int rid = __popc(heads & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int rid2 = __shfl_down_sync(FULL_MASK, rid, d);
-                    int c2 = __shfl_down_sync(FULL_MASK, c, d);
-                    long long sx2 = __shfl_down_sync(FULL_MASK, sx, d);
-                    long long sy2 = __shfl_down_sync(FULL_MASK, sy, d);
-                    long long sxx2 = __shfl_down_sync(FULL_MASK, sxx, d);
-                    long long sxy2 = __shfl_down_sync(FULL_MASK, sxy, d);
-                    long long syy2 = __shfl_down_sync(FULL_MASK, syy, d);
-                    if (lane + d < 32 && rid2 == rid) {
-                        c += c2; sx += sx2; sy += sy2; sxx += sxx2; sxy += sxy2; syy += syy2;
-                    }
-                }
-                if (head && key >= 0) {
-                    if (TOUCH && atomicExch(dirty + key, 1u) == 0u) list[atomicAdd(nlist, 1u)] = (unsigned)key;
-                    atomicAdd(L.cnt + key, (unsigned)c);
-                    unsigned long long *s = L.sums + 5 * (size_t)key;
-                    atomicAdd(s + 0, (unsigned long long)sx);
-                    atomicAdd(s + 1, (unsigned long long)sy);
-                    atomicAdd(s + 2, (unsigned long long)sxx);
-                    atomicAdd(s + 3, (unsigned long long)sxy);
-                    atomicAdd(s + 4, (unsigned long long)syy);
-                }
-            }
-        }
+        const int64_t i = base + lane;
+        float2 p = make_float2(0.0f, 0.0f);
+        if (i < n) p = __ldg(xy + i);
+        accumulate_window<OV>(L, i < n, p.x, p.y, lane, [&](int key, unsigned c, long long sx, long long sy, long long sxx, long long sxy, long long syy) {
+            if (TOUCH && atomicExch(dirty + key, 1u) == 0u) list[atomicAdd(nlist, 1u)] = (unsigned)key;
+            atomicAdd(L.cnt + key, c);
+            unsigned long long *s = L.sums + 5 * (size_t)key;
+            atomicAdd(s + 0, (unsigned long long)sx);
+            atomicAdd(s + 1, (unsigned long long)sy);
+            atomicAdd(s + 2, (unsigned long long)sxx);
+            atomicAdd(s + 3, (unsigned long long)sxy);
+            atomicAdd(s + 4, (unsigned long long)syy);
+        });
     }
 }
 
@@ -282,15 +241,26 @@ __device__ __noinline__ void eval_to_smem(const LevelDev *L, const float2 *pts, 
     __syncwarp();
 }
 
-// SPEC 5, one pyramid level, starting from and finishing in ws->p. The control flow is warp-uniform.
-template <int OV, bool STAGED, bool HASH>
-__device__ __forceinline__ int align_level(const LevelDev *L, const ndt2d_params &P, const ScanView &v, WarpState *ws,
-                                           int &evals_total)
+// The threads that share one WarpState: a warp (k_align) or a whole block (k_align_block)
+struct WarpScope {
+    static __device__ __forceinline__ void sync() { __syncwarp(); }
+    static __device__ __forceinline__ int id() { return threadIdx.x & 31; }
+};
+struct BlockScope {
+    static __device__ __forceinline__ void sync() { __syncthreads(); }
+    static __device__ __forceinline__ int id() { return threadIdx.x; }
+};
+
+// SPEC 5, one pyramid level, starting from and finishing in ws->p: THE Levenberg-Marquardt loop, shared by the
+// warp-per-scan and the block-per-scan kernels. Every thread of the scope computes the same f64 values from the shared
+// state, so the control flow is uniform; eval(trial) evaluates ws->p (trial == 0, result to ws->v / ws->count) or ws->pn
+// (trial != 0, result to ws->t / ws->tcount) and ends with a Scope::sync().
+template <class Scope, class EvalFn>
+__device__ __forceinline__ int lm_level(const ndt2d_params &P, int n, WarpState *ws, int &evals_total, EvalFn eval)
 {
-    const int n = v.n;
-    const int lane = threadIdx.x & 31;
-    if (lane == 0) ws->lambda = P.lambda_init;
-    eval_to_smem<OV, STAGED, HASH>(L, v.pts, n, ws, 0); // ends with __syncwarp()
+    const int id = Scope::id();
+    if (id == 0) ws->lambda = P.lambda_init;
+    eval(0);
     int evals = 1, status = NDT2D_MAX_ITERATIONS;
     if (n == 0 || ws->count == 0) {
         evals_total += evals;
@@ -320,37 +290,62 @@ __device__ __forceinline__ int align_level(const LevelDev *L, const ndt2d_params
             d[0] *= sc; d[1] *= sc; d[2] *= sc; n2 = n2 * (sc * sc);
         }
         const bool small = (n2 < P.eps_trans * P.eps_trans) && (fabs(d[2]) < P.eps_rot);
-        __syncwarp();
-        if (lane == 0) {
+        Scope::sync();
+        if (id == 0) {
             ws->pn[0] = ws->p[0] + d[0];
             ws->pn[1] = ws->p[1] + d[1];
             ws->pn[2] = ws->p[2] + d[2];
             ws->lambda = lambda;
         }
-        __syncwarp();
-        eval_to_smem<OV, STAGED, HASH>(L, v.pts, n, ws, 1);
+        Scope::sync();
+        eval(1);
         evals += 1;
         lambda = ws->lambda;
         const bool better = ws->t[0] > ws->v[0];
-        __syncwarp();
+        Scope::sync();
         if (better) {
-            if (lane < 10) ws->v[lane] = ws->t[lane];
-            if (lane == 10) ws->count = ws->tcount;
-            if (lane >= 11 && lane < 14) ws->p[lane - 11] = ws->pn[lane - 11];
+            if (id < 10) ws->v[id] = ws->t[id];
+            if (id == 10) ws->count = ws->tcount;
+            if (id >= 11 && id < 14) ws->p[id - 11] = ws->pn[id - 11];
             lambda = fmax(lambda / P.lambda_down, P.lambda_min);
-            if (lane == 14) ws->lambda = lambda;
-            __syncwarp();
+            if (id == 14) ws->lambda = lambda;
+            Scope::sync();
             if (small) { status = NDT2D_CONVERGED; break; }
         } else {
             if (small) { status = NDT2D_CONVERGED; break; }
             lambda = lambda * P.lambda_up;
-            if (lane == 14) ws->lambda = lambda;
-            __syncwarp();
+            if (id == 14) ws->lambda = lambda;
+            Scope::sync();
             if (lambda > P.lambda_max) { status = NDT2D_STALLED; break; }
         }
     }
     evals_total += evals;
     return status;
+}
+
+// what align returns (SPEC 5): the state after the finest level, theta wrapped
+__device__ __forceinline__ void write_result(const WarpState &E, int evals, int status, ndt2d_result *r)
+{
+    const double TWO_PI = 6.283185307179586476925286766559;
+    r->pose[0] = E.p[0];
+    r->pose[1] = E.p[1];
+    r->pose[2] = E.p[2] - TWO_PI * rint(E.p[2] / TWO_PI);
+    r->score = E.v[0];
+    r->grad[0] = E.v[1]; r->grad[1] = E.v[2]; r->grad[2] = E.v[3];
+    r->hessian[0] = E.v[4]; r->hessian[1] = E.v[5]; r->hessian[2] = E.v[6];
+    r->hessian[3] = E.v[5]; r->hessian[4] = E.v[7]; r->hessian[5] = E.v[8];
+    r->hessian[6] = E.v[6]; r->hessian[7] = E.v[8]; r->hessian[8] = E.v[9];
+    r->iterations = evals;
+    r->status = status;
+    r->count = E.count;
+    r->reserved = 0;
+}
+
+template <int OV, bool STAGED, bool HASH>
+__device__ __forceinline__ int align_level(const LevelDev *L, const ndt2d_params &P, const ScanView &v, WarpState *ws,
+                                           int &evals_total)
+{
+    return lm_level<WarpScope>(P, v.n, ws, evals_total, [&](int trial) { eval_to_smem<OV, STAGED, HASH>(L, v.pts, v.n, ws, trial); });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -428,69 +423,8 @@ template <int OV>
 __device__ __forceinline__ int align_level_block(const LevelDev *L, const ndt2d_params &P, const float2 *pts, int n, WarpState *ws,
                                                  u64 *fac, int &evals_total)
 {
-    const int tid = threadIdx.x;
-    if (tid == 0) ws->lambda = P.lambda_init;
-    eval_block<OV>(L, pts, n, ws, 0, fac); // begins its second half with __syncthreads(), ends with one
-    int evals = 1, status = NDT2D_MAX_ITERATIONS;
-    if (n == 0 || ws->count == 0) {
-        evals_total += evals;
-        return NDT2D_NO_OVERLAP;
-    }
-    for (;;) {
-        if (evals >= P.max_iterations) break;
-        double d[3];
-        double lambda = ws->lambda;
-        bool stalled = false;
-        {
-            double g[3] = {ws->v[1], ws->v[2], ws->v[3]};
-            double H6[6] = {ws->v[4], ws->v[5], ws->v[6], ws->v[7], ws->v[8], ws->v[9]};
-            while (!solve3(g, H6, lambda, d)) {
-                lambda = lambda * P.lambda_fail_up;
-                if (lambda > P.lambda_max) { stalled = true; break; }
-            }
-        }
-        if (stalled) { status = NDT2D_STALLED; break; }
-        double n2 = d[0] * d[0] + d[1] * d[1];
-        if (n2 > P.max_step_trans * P.max_step_trans) {
-            double sc = P.max_step_trans / sqrt(n2);
-            d[0] *= sc; d[1] *= sc; d[2] *= sc; n2 = P.max_step_trans * P.max_step_trans;
-        }
-        if (fabs(d[2]) > P.max_step_rot) {
-            double sc = P.max_step_rot / fabs(d[2]);
-            d[0] *= sc; d[1] *= sc; d[2] *= sc; n2 = n2 * (sc * sc);
-        }
-        const bool small = (n2 < P.eps_trans * P.eps_trans) && (fabs(d[2]) < P.eps_rot);
-        __syncthreads();
-        if (tid == 0) {
-            ws->pn[0] = ws->p[0] + d[0];
-            ws->pn[1] = ws->p[1] + d[1];
-            ws->pn[2] = ws->p[2] + d[2];
-            ws->lambda = lambda;
-        }
-        __syncthreads();
-        eval_block<OV>(L, pts, n, ws, 1, fac);
-        evals += 1;
-        lambda = ws->lambda;
-        const bool better = ws->t[0] > ws->v[0];
-        __syncthreads();
-        if (better) {
-            if (tid < 10) ws->v[tid] = ws->t[tid];
-            if (tid == 10) ws->count = ws->tcount;
-            if (tid >= 11 && tid < 14) ws->p[tid - 11] = ws->pn[tid - 11];
-            lambda = fmax(lambda / P.lambda_down, P.lambda_min);
-            if (tid == 14) ws->lambda = lambda;
-            __syncthreads();
-            if (small) { status = NDT2D_CONVERGED; break; }
-        } else {
-            if (small) { status = NDT2D_CONVERGED; break; }
-            lambda = lambda * P.lambda_up;
-            if (tid == 14) ws->lambda = lambda;
-            __syncthreads();
-            if (lambda > P.lambda_max) { status = NDT2D_STALLED; break; }
-        }
-    }
-    evals_total += evals;
-    return status;
+    // eval_block begins its second half with __syncthreads() and ends with one
+    return lm_level<BlockScope>(P, n, ws, evals_total, [&](int trial) { eval_block<OV>(L, pts, n, ws, trial, fac); });
 }
 
 template <int OV>
@@ -509,23 +443,7 @@ __global__ void __launch_bounds__(BLOCK_ALIGN_THREADS) k_align_block(const __gri
     __syncthreads();
     int evals = 0, status = NDT2D_NO_OVERLAP;
     for (int l = 0; l < a.nlevels; ++l) status = align_level_block<OV>(&a.lv[l], a.prm, pts, n, ws, fac, evals);
-    if (tid == 0) {
-        const WarpState &E = *ws;
-        ndt2d_result *r = a.res + job;
-        const double TWO_PI = 6.283185307179586476925286766559;
-        r->pose[0] = E.p[0];
-        r->pose[1] = E.p[1];
-        r->pose[2] = E.p[2] - TWO_PI * rint(E.p[2] / TWO_PI);
-        r->score = E.v[0];
-        r->grad[0] = E.v[1]; r->grad[1] = E.v[2]; r->grad[2] = E.v[3];
-        r->hessian[0] = E.v[4]; r->hessian[1] = E.v[5]; r->hessian[2] = E.v[6];
-        r->hessian[3] = E.v[5]; r->hessian[4] = E.v[7]; r->hessian[5] = E.v[8];
-        r->hessian[6] = E.v[6]; r->hessian[7] = E.v[8]; r->hessian[8] = E.v[9];
-        r->iterations = evals;
-        r->status = status;
-        r->count = E.count;
-        r->reserved = 0;
-    }
+    if (tid == 0) write_result(*ws, evals, status, a.res + job);
 }
 
 // Persistent kernel: warps pull scan indices from a global counter until the batch is drained.
@@ -614,23 +532,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
         int evals = 0, status = NDT2D_NO_OVERLAP;
         const LevelDev *levels = PAIRS ? a.geo + (size_t)__ldg(a.pairs + 2 * (size_t)job) * a.nlevels : a.lv;
         for (int l = 0; l < a.nlevels; ++l) status = align_level<OV, SM, PAIRS>(levels + l, a.prm, v, ws, evals);
-        if (lane == 0) {
-            const WarpState &E = *ws;
-            ndt2d_result *r = a.res + job;
-            const double TWO_PI = 6.283185307179586476925286766559;
-            r->pose[0] = E.p[0];
-            r->pose[1] = E.p[1];
-            r->pose[2] = E.p[2] - TWO_PI * rint(E.p[2] / TWO_PI);
-            r->score = E.v[0];
-            r->grad[0] = E.v[1]; r->grad[1] = E.v[2]; r->grad[2] = E.v[3];
-            r->hessian[0] = E.v[4]; r->hessian[1] = E.v[5]; r->hessian[2] = E.v[6];
-            r->hessian[3] = E.v[5]; r->hessian[4] = E.v[7]; r->hessian[5] = E.v[8];
-            r->hessian[6] = E.v[6]; r->hessian[7] = E.v[8]; r->hessian[8] = E.v[9];
-            r->iterations = evals;
-            r->status = status;
-            r->count = E.count;
-            r->reserved = 0;
-        }
+        if (lane == 0) write_result(*ws, evals, status, a.res + job);
         __syncwarp(); // the slot is rewritten by the next job
     }
 }

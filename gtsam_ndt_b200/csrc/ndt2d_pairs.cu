@@ -97,77 +97,36 @@ __global__ void __launch_bounds__(256) k_pairs_build(const PairBuildArgs a)
     // SPEC 3 accumulation, as k_accumulate: runs of equal cells are combined in the warp, run heads find or claim the
     // cell's slot (compare-and-swap on the key word) and add into its integer sums
     unsigned *keyword = reinterpret_cast<unsigned *>(rec);   // key of slot s = word 8 s + 6
-    constexpr int K = OV ? 2 : 1;
     float2 pnext = lane < n ? __ldg(src + lane) : make_float2(0.f, 0.f);   // the next window's point is requested one window ahead
     for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
         const float2 p = pnext;
         if (i + 32 < n) pnext = __ldg(src + i + 32);
-        float X = 0.0f, Y = 0.0f;
-        bool inside = false;
-        int hx = 0, hy = 0;
-        if (i < n) {
-            X = p.x;
-            Y = p.y;
-            inside = lattice_of_point(L, X, Y, hx, hy);
-        }
-#pragma unroll
-        for (int b = 0; b < K; ++b) {
-#pragma unroll
-            for (int aa = 0; aa < K; ++aa) {
-                int jx = hx + aa, jy = hy + b;
-                int key = inside ? jy * L.njx + jx : -1;
-                double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
-                double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
-                double dx = (double)X - cx, dy = (double)Y - cy;
-                long long qx = inside ? __double2ll_rn(dx * L.qs) : 0;
-                long long qy = inside ? __double2ll_rn(dy * L.qs) : 0;
-                int c = inside ? 1 : 0;
-                long long sx = qx, sy = qy, sxx = qx * qx, sxy = qx * qy, syy = qy * qy;
-                int prev = __shfl_up_sync(FULL_MASK, key, 1);
-                bool head = (lane == 0) || (prev != key);
-                unsigned heads = __ballot_sync(FULL_MASK, head);
-                int rid = __popc(heads & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int rid2 = __shfl_down_sync(FULL_MASK, rid, d);
-                    int c2 = __shfl_down_sync(FULL_MASK, c, d);
-                    long long sx2 = __shfl_down_sync(FULL_MASK, sx, d);
-                    long long sy2 = __shfl_down_sync(FULL_MASK, sy, d);
-                    long long sxx2 = __shfl_down_sync(FULL_MASK, sxx, d);
-                    long long sxy2 = __shfl_down_sync(FULL_MASK, sxy, d);
-                    long long syy2 = __shfl_down_sync(FULL_MASK, syy, d);
-                    if (lane + d < 32 && rid2 == rid) {
-                        c += c2; sx += sx2; sy += sy2; sxx += sxx2; sxy += sxy2; syy += syy2;
-                    }
+        accumulate_window<OV>(L, i < n, p.x, p.y, lane, [&](int key, unsigned c, long long sx, long long sy, long long sxx, long long sxy, long long syy) {
+            unsigned s = hash_slot((unsigned)key, L.hash_mask);
+            bool placed = false;
+            // the table is at most 2/3 full by construction; the probe count is bounded all the same, so that
+            // inconsistent arguments (offsets on the device that differ from the host copy) cannot hang the GPU
+            for (unsigned probes = 0; probes <= L.hash_mask; ++probes) {
+                unsigned was = atomicCAS(keyword + 8 * (size_t)s + 6, kEmptyKey, (unsigned)key);
+                if (was == kEmptyKey) {
+                    const int pos = atomicAdd(&s_nlist[w], 1);
+                    if (pos < PAIRS_LIST_CAP) s_list[w][pos] = (unsigned short)s;
+                    placed = true;
+                    break;
                 }
-                if (head && key >= 0) {
-                    unsigned s = hash_slot((unsigned)key, L.hash_mask);
-                    bool placed = false;
-                    // the table is at most 2/3 full by construction; the probe count is bounded all the same, so that
-                    // inconsistent arguments (offsets on the device that differ from the host copy) cannot hang the GPU
-                    for (unsigned probes = 0; probes <= L.hash_mask; ++probes) {
-                        unsigned was = atomicCAS(keyword + 8 * (size_t)s + 6, kEmptyKey, (unsigned)key);
-                        if (was == kEmptyKey) {
-                            const int pos = atomicAdd(&s_nlist[w], 1);
-                            if (pos < PAIRS_LIST_CAP) s_list[w][pos] = (unsigned short)s;
-                            placed = true;
-                            break;
-                        }
-                        if (was == (unsigned)key) { placed = true; break; }
-                        s = (s + 1u) & L.hash_mask;
-                    }
-                    if (!placed) { atomicMax(a.error, t + 1); continue; }
-                    atomicAdd(cnt + s, (unsigned)c);
-                    unsigned long long *q = sums + 5 * (size_t)s;
-                    atomicAdd(q + 0, (unsigned long long)sx);
-                    atomicAdd(q + 1, (unsigned long long)sy);
-                    atomicAdd(q + 2, (unsigned long long)sxx);
-                    atomicAdd(q + 3, (unsigned long long)sxy);
-                    atomicAdd(q + 4, (unsigned long long)syy);
-                }
+                if (was == (unsigned)key) { placed = true; break; }
+                s = (s + 1u) & L.hash_mask;
             }
-        }
+            if (!placed) { atomicMax(a.error, t + 1); return; }
+            atomicAdd(cnt + s, c);
+            unsigned long long *q = sums + 5 * (size_t)s;
+            atomicAdd(q + 0, (unsigned long long)sx);
+            atomicAdd(q + 1, (unsigned long long)sy);
+            atomicAdd(q + 2, (unsigned long long)sxx);
+            atomicAdd(q + 3, (unsigned long long)sxy);
+            atomicAdd(q + 4, (unsigned long long)syy);
+        });
     }
     __threadfence();
     __syncwarp();

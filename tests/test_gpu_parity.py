@@ -470,8 +470,8 @@ def test_set_cells_roundtrip(mods, small_world):
     # a table of another size is refused (it used to be copied into the larger table, rows sheared)
     with pytest.raises(g.NdtError, match="records"):
         m2.set_cells(cells[:-1])
-    with pytest.raises(ValueError):
-        m2.set_cells(cells.reshape(cells.shape[1], cells.shape[0], 8))
+    with pytest.raises(ValueError):     # right record count, wrong shape: rows would be sheared
+        m2.set_cells(cells.reshape(cells.shape[0] * 2, cells.shape[1] // 2, 8))
 
 
 @pytest.mark.parametrize("cfg", [dict(res=[2.0, 0.5], overlap=1, grid=(-100.0, -100.0, 200.0, 200.0)),
