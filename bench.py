@@ -369,14 +369,37 @@ def bind_to_gpu_numa(local):
         info["gpu_pci"] = bdf
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
         info["gpu_numa_node"] = node
-        if node < 0:
-            info["note"] = "the platform reports no NUMA node for the GPU"
-            return info
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
         allowed = set(os.sched_getaffinity(0))
+        nodes = numa_nodes()
+        info["host_numa_nodes"] = {str(k): len(v & allowed) for k, v in nodes.items()}
+        if node < 0:
+            # virtualised platforms report -1: find the node by measurement (pinned buffer first-touched on each node in turn)
+            usable = {k: v & allowed for k, v in nodes.items() if v & allowed}
+            if len(usable) < 2:
+                info["note"] = "the platform reports no NUMA node for the GPU and the process can run on one node only"
+                return info
+            probe = {}
+            for k, cpus_k in usable.items():
+                os.sched_setaffinity(0, cpus_k)
+                h = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+                h.zero_()
+                d = torch.empty_like(h, device=torch.device("cuda", local))
+                d.copy_(h, non_blocking=True)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(4):
+                    d.copy_(h, non_blocking=True)
+                e1.record()
+                torch.cuda.synchronize()
+                probe[k] = 4 * h.numel() / (e0.elapsed_time(e1) / 1e3) / 1e9
+                del h, d
+            os.sched_setaffinity(0, allowed)
+            node = max(probe, key=probe.get)
+            info["probe_h2d_gbs_by_node"] = {str(k): round(v, 1) for k, v in probe.items()}
+            info["gpu_numa_node"] = node
+            info["note"] = "node chosen by measured pinned-copy bandwidth (sysfs reports -1)"
+        cpus = nodes.get(node, set())
         info["allowed_cpus"] = len(allowed)
         info["allowed_on_gpu_node"] = len(allowed & cpus)
         if allowed & cpus and (allowed & cpus) != allowed:
@@ -389,6 +412,24 @@ def bind_to_gpu_numa(local):
     except Exception as e:      # /sys not mounted, nvidia-smi missing, ...
         info["note"] = f"not bound: {type(e).__name__}: {e}"
     return info
+
+
+def numa_nodes():
+    """{node: set of CPUs} from sysfs ({} where it is not mounted)."""
+    out = {}
+    base = "/sys/devices/system/node"
+    try:
+        for d in os.listdir(base):
+            if d.startswith("node") and d[4:].isdigit():
+                cpus = set()
+                for part in open(f"{base}/{d}/cpulist").read().strip().split(","):
+                    if part:
+                        lo, _, hi = part.partition("-")
+                        cpus.update(range(int(lo), int(hi or lo) + 1))
+                out[int(d[4:])] = cpus
+    except OSError:
+        pass
+    return out
 
 
 def make_matcher(ctx, res, map_xy, overlap=0):

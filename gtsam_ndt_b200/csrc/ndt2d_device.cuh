@@ -533,6 +533,14 @@ struct Fetched {
     Cell4 cA[NC], cB[NC];
 };
 
+// How a level's cell records are stored (template parameter TABLE of the evaluation):
+//   TABLE_DENSE  L.cells is the dense row-major table (scan-to-map, set_target)
+//   TABLE_GHASH  L.cells is an open-addressing hash table in global memory keyed by the dense index (ndt2d_align_pairs,
+//                general path): hash_mask + 1 records, key in the record's `n` word, sentinel record behind them
+//   TABLE_SHASH  the valid cells of one target scan in SHARED memory (ndt2d_align_pairs, fused path): L.cells is the compact
+//                record array (key in the `n` word), L.cnt points at a u16 index of hash_mask + 1 slots (0xffff = empty)
+enum { TABLE_DENSE = 0, TABLE_GHASH = 1, TABLE_SHASH = 2 };
+
 struct LatticePk {
     unsigned nhx, nhy, njx;
     unsigned sentinel; // dense tables: index of the first of the njx + 2 all-zero records that follow the cells (the gather target of
@@ -541,19 +549,25 @@ struct LatticePk {
     unsigned mask;     // hash tables only: slots - 1
     unsigned outside;  // what lattice_base() returns for a point outside the lattice: `sentinel` for dense tables (the gather
                        // goes straight to the zero records); 0xffffffff for hash tables, where every smaller value is a cell key
+    unsigned srec, sidx; // TABLE_SHASH: shared-window addresses of the record array and of the u16 slot index
     float st;          // stride in metres: local coordinate = fma(df, st, off)
     u64 off[4];        // per cell of the point: minus the cell centre relative to node (hx, hy): (-st/2, -st/2) for one
                        // grid; (-a st, -b st) for cell (a, b) of the four half-shifted grids
 };
 
 template <int OV>
-__device__ __forceinline__ LatticePk lattice_pack(const LevelDev &L, bool hash)
+__device__ __forceinline__ LatticePk lattice_pack(const LevelDev &L, int table)
 {
     LatticePk G;
     G.nhx = (unsigned)L.nhx; G.nhy = (unsigned)L.nhy; G.njx = (unsigned)L.njx;
     G.mask = L.hash_mask;
-    G.sentinel = hash ? L.hash_mask + 1u : (unsigned)L.njx * (unsigned)L.njy;
-    G.outside = hash ? 0xffffffffu : G.sentinel;
+    G.sentinel = table != TABLE_DENSE ? L.hash_mask + 1u : (unsigned)L.njx * (unsigned)L.njy;
+    G.outside = table != TABLE_DENSE ? 0xffffffffu : G.sentinel;
+    G.srec = G.sidx = 0u;
+    if (table == TABLE_SHASH) {
+        G.srec = (unsigned)__cvta_generic_to_shared(L.cells);
+        G.sidx = (unsigned)__cvta_generic_to_shared(L.cnt);
+    }
     G.st = L.st;
     if (OV) {
 #pragma unroll
@@ -588,8 +602,41 @@ __device__ __forceinline__ unsigned hash_slot(unsigned key, unsigned mask) { ret
 // the point relative to the centre of its cell k (SPEC 4, v4): one f32 fma per coordinate
 __device__ __forceinline__ u64 local_xy(const LatticePk &G, u64 df, int k) { return fma2(df, bc(G.st), G.off[k]); }
 
+// TABLE_SHASH: record `id` of the compact array in shared memory (two 128-bit shared loads)
+__device__ __forceinline__ Cell4 load_cell_shared(unsigned srec, unsigned id)
+{
+    Cell4 r;
+    const unsigned a = srec + id * 32u;
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(r.mu), "=l"(r.B0) : "r"(a));
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2+16];" : "=l"(r.B1), "=l"(r.nv) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ unsigned load_slot_shared(unsigned sidx, unsigned slot)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(sidx + slot * 2u));
+    return v;
+}
+// the record of cell `key` (0xffffffff: the point is outside the lattice), or the all-zero record when the target has no
+// valid cell there. The first probe is unconditional; collisions (the index is at most 1/3 full) are chased in a loop.
+__device__ __forceinline__ Cell4 lookup_shared(const LatticePk &G, unsigned key)
+{
+    unsigned slot = hash_slot(key, G.mask);
+    unsigned id = key == 0xffffffffu ? 0xffffu : load_slot_shared(G.sidx, slot);
+    Cell4 c;
+    c.mu = c.B0 = c.B1 = c.nv = 0ull;
+    for (unsigned probes = 0; id != 0xffffu && probes <= G.mask; ++probes) {
+        c = load_cell_shared(G.srec, id);
+        if ((unsigned)__float_as_int(lo32(c.nv)) == key) return c;
+        slot = (slot + 1u) & G.mask;
+        id = load_slot_shared(G.sidx, slot);
+    }
+    c.mu = c.B0 = c.B1 = c.nv = 0ull;
+    return c;
+}
+
 // P64 (score-only kernels with the scan staged in shared memory): pts holds double2 per point, r and j are not needed
-template <int OV, bool SMEM, bool HASH = false, bool P64 = false>
+template <int OV, bool SMEM, int TABLE = TABLE_DENSE, bool P64 = false>
 __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const LatticePk &G, const PosePk &P, const float2 *pts,
                                       int n, int i, Fetched<OV> &F)
 {
@@ -609,12 +656,19 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
     }
     // K = 1: one record per point. K = 4: two rows of two adjacent records (64 contiguous bytes per row).
     // Outside the lattice: the zero records behind the table (invalid), so the gather needs no predicate.
-    if (!HASH) {
+    if (TABLE == TABLE_DENSE) {
 #pragma unroll
         for (int k = 0; k < Fetched<OV>::NC; ++k) {
             const unsigned o = (k & 1) + (k >> 1) * G.njx;
             F.cA[k] = load_cell(cells, bA + o);
             F.cB[k] = load_cell(cells, bB + o);
+        }
+    } else if (TABLE == TABLE_SHASH) {
+#pragma unroll
+        for (int k = 0; k < Fetched<OV>::NC; ++k) {
+            const unsigned o = (k & 1) + (k >> 1) * G.njx;
+            F.cA[k] = lookup_shared(G, bA == G.outside ? bA : bA + o);
+            F.cB[k] = lookup_shared(G, bB == G.outside ? bB : bB + o);
         }
     } else {
         const bool inA = bA != G.outside, inB = bB != G.outside;
@@ -674,8 +728,8 @@ __device__ __forceinline__ void accumulate_step(const LatticePk &G, Fetched<OV> 
 template <bool FULL, bool TR>
 __device__ __forceinline__ void finish_partials(const Partials &S, int cnt, int lane, Eval &E);
 
-// HASH: L.cells is a per-target hash table (L.hash_mask), probed in fetch().
-template <int OV, bool FULL, bool SMEM, int PIPE, bool TR = false, bool HASH = false, bool P64 = false>
+// TABLE: how L's records are stored (TABLE_DENSE / TABLE_GHASH / TABLE_SHASH), resolved in fetch().
+template <int OV, bool FULL, bool SMEM, int PIPE, bool TR = false, int TABLE = TABLE_DENSE, bool P64 = false>
 __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E)
 {
     Partials S;
@@ -686,7 +740,7 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
     int cnt = 0;
     const float4 *__restrict__ cells = L.cells;
     const PosePk P = pose_pack(q);
-    const LatticePk G = lattice_pack<OV>(L, HASH);
+    const LatticePk G = lattice_pack<OV>(L, TABLE);
     const int npad = (n + 63) & ~63;
     if (PIPE == 1 && OV == 0) {
         // Software pipeline over registers, two steps per trip: the records of the next step are requested before
@@ -697,19 +751,19 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
         int i = lane;
         if ((npad >> 6) & 1) {
             Fetched<OV> cur;
-            fetch<OV, SMEM, HASH, P64>(cells, G, P, pts, n, i, cur);
+            fetch<OV, SMEM, TABLE, P64>(cells, G, P, pts, n, i, cur);
             accumulate_step<OV, FULL>(G, cur, S, cnt);
             i += 64;
         }
         if (i < npad) {
             const int last = npad - 64 + lane;
             Fetched<OV> F0, F1;
-            fetch<OV, SMEM, HASH, P64>(cells, G, P, pts, n, i, F0);
+            fetch<OV, SMEM, TABLE, P64>(cells, G, P, pts, n, i, F0);
 #pragma unroll 1
             for (; i < npad; i += 128) {
-                fetch<OV, SMEM, HASH, P64>(cells, G, P, pts, n, i + 64, F1);
+                fetch<OV, SMEM, TABLE, P64>(cells, G, P, pts, n, i + 64, F1);
                 accumulate_step<OV, FULL>(G, F0, S, cnt);
-                fetch<OV, SMEM, HASH, P64>(cells, G, P, pts, n, min(i + 128, last), F0);
+                fetch<OV, SMEM, TABLE, P64>(cells, G, P, pts, n, min(i + 128, last), F0);
                 accumulate_step<OV, FULL>(G, F1, S, cnt);
             }
         }
@@ -717,7 +771,7 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
 #pragma unroll kUnroll
         for (int i = lane; i < npad; i += 64) {
             Fetched<OV> cur;
-            fetch<OV, SMEM, HASH, P64>(cells, G, P, pts, n, i, cur);
+            fetch<OV, SMEM, TABLE, P64>(cells, G, P, pts, n, i, cur);
             accumulate_step<OV, FULL>(G, cur, S, cnt);
         }
     }

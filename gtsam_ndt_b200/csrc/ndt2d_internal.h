@@ -87,6 +87,32 @@ struct PairBuildArgs {
     int *error;              // out: set to 1 + slot when a target's lattice would exceed 2^31 cells
 };
 cudaError_t launch_pairs_build(const LaunchCfg &c, const PairBuildArgs &a, int64_t *launches);
+
+// Batched scan-to-scan, fused path (K = 1, scans small enough for shared memory): one warp per PAIR builds the target's
+// grid for one pyramid level in its own shared-memory slice (radix sort of the cell keys, one lane per cell for the sums
+// and the finalisation, compact record array behind a u16 hash index), aligns the source on it, and goes on to the next
+// level - no table ever touches global memory.
+struct PairFusedArgs {
+    const float2 *xy;
+    const int64_t *offsets;
+    const int32_t *pairs;    // (target scan, source scan) per pair
+    const double *init;
+    ndt2d_result *res;
+    int npairs, nlevels, explicit_grid;
+    float res_m[NDT2D_MAX_LEVELS];
+    float gox, goy, gex, gey;
+    ndt2d_params prm;
+    unsigned cap_t;          // sort capacity in points (longest target, padded to 32)
+    unsigned cap_s;          // source slot capacity in points (longest source, padded to 64)
+    unsigned rmax;           // record capacity: longest target / min_points
+    unsigned hslots;         // slots of the u16 hash index (power of two >= 2 * rmax)
+    unsigned off_a, off_r, off_h, warp_bytes;   // byte offsets of the three areas in a warp's slice, and its size
+    unsigned int *counter;   // work queue head, zero on entry
+    int *error;              // set to 1 + pair when a target's lattice would exceed 2^31 cells
+};
+// fills cap_*, rmax, hslots, off_*, warp_bytes; returns false when the fused path cannot be used (smem_optin too small)
+bool pairs_fused_layout(PairFusedArgs &a, int64_t max_target_points, int64_t max_source_points, int smem_optin);
+cudaError_t launch_pairs_fused(const LaunchCfg &c, const PairFusedArgs &a, int64_t *launches);
 size_t align_smem_bytes(int cap_points); // dynamic shared memory per k_align block
 // Publication of a shard's best hypothesis into every rank's exchange table (peer pointers, NVLink stores).
 struct PublishArgs {

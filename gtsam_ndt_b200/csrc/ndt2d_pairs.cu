@@ -2,7 +2,7 @@
 // table (k_pairs_build, below); the pairs are then aligned by k_align in pairs mode (ndt2d_kernels.cu). The host side
 // finds the distinct targets, sizes the tables and cuts the call into chunks that fit the table budget.
 // Reference interface: none citable (/root/reference/README.md:1 is the whole mount).
-#include "ndt2d_device.cuh"
+#include "ndt2d_align.cuh"
 #include "ndt2d_host.h"
 
 namespace ndt2d {
@@ -155,6 +155,298 @@ __global__ void __launch_bounds__(256) k_pairs_build(const PairBuildArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused path: one warp per pair, the target's grid in shared memory
+// ------------------------------------------------------------------------------------------------
+
+static constexpr int FUSED_WARPS = 4;            // warps per block; two such blocks share an SM at 1080-point scans
+static constexpr unsigned FUSED_STATE_BYTES = 352; // WarpState (216 B) + LevelDev (112 B), rounded up to 16
+
+// SPEC 2 geometry of one level of a target's grid from its bounding box: the f32 expressions of setup_level() in
+// ndt2d_capi.cu (every lane computes the same values). Returns false when the lattice is unusable (empty or >= 2^31
+// cells): nothing is inside then and every align against this target ends NO_OVERLAP.
+__device__ __forceinline__ bool pair_level_geometry(LevelDev &L, float res, int ov, bool explicit_grid, float gox, float goy, float gex,
+                                                    float gey, float xmin, float ymin, float xmax, float ymax)
+{
+    L.res = res;
+    L.ov = ov;
+    L.st = L.ov ? __fmul_rn(L.res, 0.5f) : L.res;
+    L.inv_st = __fdiv_rn(1.0f, L.st);
+    if (explicit_grid) {
+        L.ox = gox; L.oy = goy;
+        L.nhx = (int)ceilf(__fdiv_rn(gex, L.st));
+        L.nhy = (int)ceilf(__fdiv_rn(gey, L.st));
+    } else {
+        if (!(xmin <= xmax)) { xmin = xmax = ymin = ymax = 0.0f; }
+        L.ox = __fsub_rn(__fmul_rn(floorf(__fdiv_rn(xmin, L.res)), L.res), L.res);
+        L.oy = __fsub_rn(__fmul_rn(floorf(__fdiv_rn(ymin, L.res)), L.res), L.res);
+        L.nhx = (int)ceilf(__fdiv_rn(__fsub_rn(xmax, L.ox), L.st)) + 2;
+        L.nhy = (int)ceilf(__fdiv_rn(__fsub_rn(ymax, L.oy), L.st)) + 2;
+    }
+    const bool bad = L.nhx < 1 || L.nhy < 1 || (int64_t)(L.nhx + L.ov) * (int64_t)(L.nhy + L.ov) >= ((int64_t)1 << 31);
+    if (bad) { L.nhx = L.nhy = 0; }
+    L.njx = L.nhx + L.ov;
+    L.njy = L.nhy + L.ov;
+    L.inv_std = __ddiv_rn(1.0, (double)L.st);
+    L.qs = __ddiv_rn(4194304.0, (double)L.res);
+    L.qu = __dmul_rn((double)L.res, 1.0 / 4194304.0);
+    return !bad;
+}
+
+// SPEC 3 for one (target scan, level) by ONE warp, entirely in its shared-memory slice. The integer sums are order
+// independent, so grouping the points by cell with a sort and summing each group in one lane gives the sums - and
+// therefore the records - of the dense build bit for bit. Steps: (1) cell key of every point inside the lattice,
+// compacted; (2) LSD radix sort of (key, point index) by key, 8 bits per pass, only as many passes as the lattice has
+// key bits; (3) run heads = the cells; (4) one lane per cell with at least min_points points: integer sums over its
+// points, finalisation, record appended to the compact array; its key goes into the u16 hash index (first free slot
+// from hash_slot(key), resolved inside the warp without atomics). Returns the number of records.
+__device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 *__restrict__ src, int n, int min_points, double eig_ratio,
+                                               unsigned *key0, unsigned cap_t, float4 *rec, unsigned short *hidx, unsigned hslots)
+{
+    const LevelDev &L = *Lp;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned *key[2] = {key0, key0 + cap_t};
+    unsigned short *idx[2] = {reinterpret_cast<unsigned short *>(key0 + 2 * (size_t)cap_t),
+                              reinterpret_cast<unsigned short *>(key0 + 2 * (size_t)cap_t) + cap_t};
+    unsigned *hist = reinterpret_cast<unsigned *>(rec);     // 256 counters; the record area is not in use during the sort
+    // the index starts empty (0xffff in every slot)
+    for (unsigned s = lane; s < hslots / 2; s += 32) reinterpret_cast<unsigned *>(hidx)[s] = 0xffffffffu;
+    // (1) keys
+    int m = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        int hx = 0, hy = 0;
+        bool in = false;
+        if (i < n) {
+            const float2 p = __ldg(src + i);
+            in = lattice_of_point(L, p.x, p.y, hx, hy);
+        }
+        const unsigned mask = __ballot_sync(FULL_MASK, in);
+        if (in) {
+            const int pos = m + __popc(mask & lt);
+            key[0][pos] = (unsigned)(hy * L.njx + hx);
+            idx[0][pos] = (unsigned short)i;
+        }
+        m += __popc(mask);
+    }
+    __syncwarp();
+    if (m == 0) return 0;
+    // (2) radix sort by key
+    const unsigned ncells = (unsigned)L.njx * (unsigned)L.njy;
+    const int nbits = ncells > 1u ? 32 - __clz(ncells - 1u) : 1;
+    int cur = 0;
+    for (int shift = 0; shift < nbits; shift += 8) {
+        for (int b = lane; b < 256; b += 32) hist[b] = 0u;
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) atomicAdd(&hist[(key[cur][i] >> shift) & 255u], 1u);
+        __syncwarp();
+        unsigned c[8], sum = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = hist[8 * lane + j]; sum += c[j]; }
+        unsigned incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += v;
+        }
+        unsigned run = incl - sum;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { hist[8 * lane + j] = run; run += c[j]; }
+        __syncwarp();
+        for (int base = 0; base < m; base += 32) {      // windows in order: the scatter is stable
+            const int i = base + lane;
+            const bool valid = i < m;
+            const unsigned k = valid ? key[cur][i] : 0u;
+            const unsigned short ix = valid ? idx[cur][i] : (unsigned short)0;
+            const unsigned d = valid ? (k >> shift) & 255u : 256u + (unsigned)lane;
+            const unsigned peers = __match_any_sync(FULL_MASK, d);
+            const unsigned rank = __popc(peers & lt);
+            const unsigned off = valid ? hist[d] : 0u;
+            __syncwarp();
+            if (valid && rank == 0u) hist[d] = off + __popc(peers);
+            __syncwarp();
+            if (valid) {
+                key[cur ^ 1][off + rank] = k;
+                idx[cur ^ 1][off + rank] = ix;
+            }
+        }
+        __syncwarp();
+        cur ^= 1;
+    }
+    // (3) run heads
+    unsigned short *hpos = reinterpret_cast<unsigned short *>(key[cur ^ 1]);
+    int nruns = 0;
+    for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        const bool head = i < m && (i == 0 || key[cur][i] != key[cur][i - 1]);
+        const unsigned mask = __ballot_sync(FULL_MASK, head);
+        if (head) hpos[nruns + __popc(mask & lt)] = (unsigned short)i;
+        nruns += __popc(mask);
+    }
+    if (lane == 0) hpos[nruns] = (unsigned short)m;
+    __syncwarp();
+    // (4) one lane per cell
+    const unsigned hmask = hslots - 1u;
+    int nrec = 0;
+    for (int base = 0; base < nruns; base += 32) {
+        const int r = base + lane;
+        const int start = r < nruns ? (int)hpos[r] : 0;
+        const int len = r < nruns ? (int)hpos[r + 1] - start : 0;
+        const bool ok = len >= min_points;
+        unsigned kr = 0u;
+        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+        if (ok) {
+            kr = key[cur][start];
+            const int jx = (int)(kr % (unsigned)L.njx), jy = (int)(kr / (unsigned)L.njx);
+            const double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
+            const double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
+            long long s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+            for (int p = start; p < start + len; ++p) {
+                const float2 pt = __ldg(src + idx[cur][p]);
+                const double dx = (double)pt.x - cx, dy = (double)pt.y - cy;
+                const long long qx = __double2ll_rn(dx * L.qs), qy = __double2ll_rn(dy * L.qs);
+                s0 += qx; s1 += qy; s2 += qx * qx; s3 += qx * qy; s4 += qy * qy;
+            }
+            finalize_record((unsigned)len, s0, s1, s2, s3, s4, L.qu, min_points, eig_ratio, ra, rb);
+            rb.z = __int_as_float((int)kr);     // the key sits in the record's `n` word for the probing reader
+        }
+        const unsigned mask = __ballot_sync(FULL_MASK, ok);
+        const unsigned id = (unsigned)nrec + __popc(mask & lt);
+        if (ok) {
+            rec[2 * (size_t)id] = ra;
+            rec[2 * (size_t)id + 1] = rb;
+        }
+        // index insertion: every pending lane looks at its slot; of the lanes that found the same free slot the lowest
+        // takes it, everybody else moves on by one (the index is at most a third full)
+        unsigned slot = hash_slot(kr, hmask);
+        bool pending = ok;
+        while (__any_sync(FULL_MASK, pending)) {
+            const bool free_slot = pending && hidx[slot] == 0xffffu;
+            const unsigned peers = __match_any_sync(FULL_MASK, free_slot ? slot : 0x10000u + (unsigned)lane);
+            const bool win = free_slot && (__ffs(peers) - 1 == lane);
+            __syncwarp();
+            if (win) hidx[slot] = (unsigned short)id;
+            __syncwarp();
+            if (win) pending = false;
+            else if (pending) slot = (slot + 1u) & hmask;
+        }
+        nrec += __popc(mask);
+    }
+    __syncwarp();
+    return nrec;
+}
+
+__global__ void __launch_bounds__(FUSED_WARPS * 32) k_pairs_fused(const __grid_constant__ PairFusedArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *slice = smem_raw + (size_t)warp * a.warp_bytes;
+    WarpState *ws = reinterpret_cast<WarpState *>(slice);
+    LevelDev *Ls = reinterpret_cast<LevelDev *>(slice + 224);
+    unsigned *area_a = reinterpret_cast<unsigned *>(slice + a.off_a);
+    float2 *slot = reinterpret_cast<float2 *>(slice + a.off_a);
+    float4 *rec = reinterpret_cast<float4 *>(slice + a.off_r);
+    unsigned short *hidx = reinterpret_cast<unsigned short *>(slice + a.off_h);
+    const float2 far = make_float2(1e18f, 1e18f);
+    for (;;) {
+        unsigned job = 0;
+        if (lane == 0) job = atomicAdd(a.counter, 1u);
+        job = __shfl_sync(FULL_MASK, job, 0);
+        if (job >= (unsigned)a.npairs) break;
+        const int tscan = __ldg(a.pairs + 2 * (size_t)job), sscan = __ldg(a.pairs + 2 * (size_t)job + 1);
+        const int64_t t0 = __ldg(a.offsets + tscan), t1 = __ldg(a.offsets + tscan + 1);
+        const int64_t s0 = __ldg(a.offsets + sscan), s1 = __ldg(a.offsets + sscan + 1);
+        const int tn = (int)(t1 - t0), sn = (int)(s1 - s0);
+        const float2 *__restrict__ tsrc = a.xy + t0;
+        const float2 *__restrict__ ssrc = a.xy + s0;
+        // SPEC 2 auto-fit: bounding box of the target's finite points
+        float xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY;
+        if (!a.explicit_grid) {
+            for (int i = lane; i < tn; i += 32) {
+                const float2 p = __ldg(tsrc + i);
+                if (!isfinite(p.x) || !isfinite(p.y)) continue;
+                xmin = fminf(xmin, p.x); xmax = fmaxf(xmax, p.x);
+                ymin = fminf(ymin, p.y); ymax = fmaxf(ymax, p.y);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                xmin = fminf(xmin, __shfl_xor_sync(FULL_MASK, xmin, o));
+                ymin = fminf(ymin, __shfl_xor_sync(FULL_MASK, ymin, o));
+                xmax = fmaxf(xmax, __shfl_xor_sync(FULL_MASK, xmax, o));
+                ymax = fmaxf(ymax, __shfl_xor_sync(FULL_MASK, ymax, o));
+            }
+        }
+        if (lane < 3) ws->p[lane] = __ldg(a.init + 3 * (size_t)job + lane);
+        __syncwarp();
+        int evals = 0, status = NDT2D_NO_OVERLAP;
+        for (int l = 0; l < a.nlevels; ++l) {
+            LevelDev L;
+            const bool usable = pair_level_geometry(L, a.res_m[l], 0, a.explicit_grid != 0, a.gox, a.goy, a.gex, a.gey, xmin, ymin, xmax, ymax);
+            L.cells = rec;
+            L.cnt = reinterpret_cast<uint32_t *>(hidx);      // TABLE_SHASH: the u16 slot index
+            L.sums = nullptr;
+            L.hash_mask = a.hslots - 1u;
+            if (!usable && lane == 0) atomicMax(a.error, (int)job + 1);
+            __syncwarp();                                    // the previous level's evaluation has finished with *Ls
+            if (lane == 0) *Ls = L;
+            __syncwarp();
+            build_table_shared(Ls, tsrc, tn, a.prm.min_points, a.prm.eig_ratio, area_a, a.cap_t, rec, hidx, a.hslots);
+            // the sort buffers are dead: the same area takes the source scan (sanitised, padded with the far-away point)
+            const int npad = (sn + 63) & ~63;
+            for (int i = lane; i < npad; i += 32) slot[i] = i < sn ? sanitize(__ldg(ssrc + i)) : far;
+            __syncwarp();
+            status = lm_level<WarpScope>(a.prm, sn, ws, evals, [&](int trial) { eval_to_smem<0, true, TABLE_SHASH>(Ls, slot, sn, ws, trial); });
+        }
+        if (lane == 0) write_result(*ws, evals, status, a.res + job);
+        __syncwarp();
+    }
+}
+
+bool pairs_fused_layout(PairFusedArgs &a, int64_t max_target_points, int64_t max_source_points, int smem_optin)
+{
+    if (max_target_points > 65535 || max_source_points > (1 << 20)) return false;
+    a.cap_t = (unsigned)((std::max<int64_t>(max_target_points, 1) + 31) & ~(int64_t)31);
+    a.cap_s = (unsigned)((std::max<int64_t>(max_source_points, 1) + 63) & ~(int64_t)63);
+    a.rmax = (unsigned)(a.cap_t / (unsigned)std::max(a.prm.min_points, 2)) + 1u;
+    a.hslots = 64;
+    while (a.hslots < 2u * a.rmax + 2u) a.hslots <<= 1;
+    if (a.hslots > 65536u) return false;          // hash_slot() yields 17 bits at most
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t size_a = up16(std::max<size_t>((size_t)a.cap_s * 8, (size_t)a.cap_t * 12));
+    const size_t size_r = up16(std::max<size_t>((size_t)a.rmax * 32, 1024));
+    a.off_a = FUSED_STATE_BYTES;
+    a.off_r = (unsigned)(a.off_a + size_a);
+    a.off_h = (unsigned)(a.off_r + size_r);
+    a.warp_bytes = (unsigned)up16(a.off_h + (size_t)a.hslots * 2);
+    static_assert(sizeof(WarpState) <= 224 && sizeof(LevelDev) <= FUSED_STATE_BYTES - 224, "per-warp state area");
+    return (size_t)a.warp_bytes * FUSED_WARPS <= (size_t)smem_optin;
+}
+
+cudaError_t launch_pairs_fused(const LaunchCfg &c, const PairFusedArgs &a, int64_t *launches)
+{
+    if (a.npairs <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), c.stream);
+    if (e != cudaSuccess) return e;
+    const size_t smem = (size_t)a.warp_bytes * FUSED_WARPS;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(k_pairs_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    e = cudaFuncSetAttribute(k_pairs_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_fused, FUSED_WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t need = ((int64_t)a.npairs + FUSED_WARPS - 1) / FUSED_WARPS;
+    const int64_t cap = (int64_t)c.sm_count * per_sm;
+    k_pairs_fused<<<(int)std::min(need, cap), FUSED_WARPS * 32, smem, c.stream>>>(a);
+    ++*launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pairs_build(const LaunchCfg &c, const PairBuildArgs &a, int64_t *launches)
 {
     const int64_t warps = (int64_t)a.ntargets * a.nlevels;
@@ -195,7 +487,34 @@ static int align_pairs_impl(ndt2d_matcher *m, const float *d_xy, const int64_t *
         max_src = std::max(max_src, h_offsets[s + 1] - h_offsets[s]);
     }
     const int K = m->prm.overlap ? 4 : 1, L = m->nlevels;
-    // slots per table: 1.5 x the most cells a target can occupy (every point in cells of its own), rounded up to a power
+    CK(m, m->b_perr.ensure(4));
+    CK(m, cudaMemsetAsync(m->b_perr.p, 0, 4, m->cfg.stream));
+    // fused path: K = 1 and scans that fit a warp's shared-memory slice (1080-beam scans: 27 KB per warp, 8 warps per SM)
+    {
+        PairFusedArgs f;
+        memset(&f, 0, sizeof(f));
+        f.prm = m->prm;
+        const char *env = getenv("NDT2D_PAIRS_FUSED");
+        if (K == 1 && !(env && atoi(env) == 0) && pairs_fused_layout(f, max_tgt, max_src, m->cfg.max_smem_optin)) {
+            int rcu;
+            if ((rcu = upload(m, m->b_ppairs, pairs, (size_t)npairs * 8))) return rcu;
+            CK(m, cudaStreamSynchronize(m->cfg.stream));     // `pairs` is the caller's buffer
+            f.xy = reinterpret_cast<const float2 *>(d_xy);
+            if (!f.xy) f.xy = m->b_counter.as<float2>();
+            f.offsets = d_offsets;
+            f.pairs = m->b_ppairs.as<int32_t>();
+            f.init = d_init;
+            f.res = d_res;
+            f.npairs = npairs; f.nlevels = L; f.explicit_grid = m->explicit_grid ? 1 : 0;
+            for (int l = 0; l < L; ++l) f.res_m[l] = m->res[l];
+            f.gox = m->gox; f.goy = m->goy; f.gex = m->gex; f.gey = m->gey;
+            f.counter = m->b_counter.as<unsigned int>();
+            f.error = m->b_perr.as<int>();
+            CK(m, launch_pairs_fused(m->cfg, f, &m->launches));
+            return NDT2D_OK;
+        }
+    }
+    // general path (overlapping grids, long scans): slots per table: 1.5 x the most cells a target can occupy (every point in cells of its own), rounded up to a power
     // of two: at most 2/3 full in that worst case, typically a quarter (a 1080-beam scan occupies ~500 cells)
     const uint64_t want = 3ull * (uint64_t)std::max<int64_t>(max_tgt, 16) * K / 2;
     if (want > 65536) return fail(m, NDT2D_EINVAL, "align_pairs: target scans of %lld points need more than 65536 table slots",
@@ -205,9 +524,7 @@ static int align_pairs_impl(ndt2d_matcher *m, const float *d_xy, const int64_t *
     size_t budget = (size_t)8 << 30;
     if (const char *e = getenv("NDT2D_PAIRS_BYTES")) budget = (size_t)strtoull(e, nullptr, 10);
     const int tmax = (int)std::max<size_t>(1, std::min<size_t>(budget / per_target, (size_t)nscans));
-    CK(m, m->b_perr.ensure(4));
     int rc;
-    CK(m, cudaMemsetAsync(m->b_perr.p, 0, 4, m->cfg.stream));
     std::vector<int32_t> slot((size_t)nscans, -1), targets, resolved;
     int p0 = 0;
     while (p0 < npairs) {

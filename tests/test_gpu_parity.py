@@ -355,11 +355,15 @@ def _between(a, b):
 
 
 @pytest.mark.parametrize("cfg", [dict(res=[0.5]), dict(res=[2.0, 1.0, 0.5]), dict(res=[1.0, 0.5], overlap=1),
-                                 dict(res=[0.5], grid=(-120.0, -120.0, 240.0, 240.0)), dict(res=[1.0], chunk_bytes=3_000_000)])
+                                 dict(res=[0.5], grid=(-120.0, -120.0, 240.0, 240.0)), dict(res=[1.0], chunk_bytes=3_000_000, fused=0),
+                                 dict(res=[0.5], fused=0), dict(res=[2.0, 0.25], fused=0), dict(res=[0.3, 0.1]), dict(res=[0.5], min_points=2),
+                                 dict(res=[1.0, 0.5], min_points=5, eig_ratio=0.05)])
 def test_align_pairs_equals_set_target_plus_align(mods, cfg, monkeypatch):
     """Batched scan-to-scan: every pair of ndt2d_align_pairs must be byte-identical to ndt2d_set_target(target scan) +
-    ndt2d_align(source scan) on the GPU, and to the same two calls of the CPU spec oracle. Covers pyramids, overlapping
-    grids, an explicit lattice, repeated and self targets, empty / tiny / unusable scans, and chunking of the table budget."""
+    ndt2d_align(source scan) on the GPU, and to the same two calls of the CPU spec oracle. Covers both implementations
+    (fused: the target's grid built by the aligning warp in shared memory, K = 1; general: per-target hash tables in global
+    memory), pyramids, overlapping grids, an explicit lattice, fine cells (many radix passes), other min_points, repeated
+    and self targets, empty / tiny / unusable scans, and chunking of the table budget."""
     from gtsam_ndt_b200 import synth
     cfg = dict(cfg)
     grid = cfg.pop("grid", None)
@@ -367,6 +371,8 @@ def test_align_pairs_equals_set_target_plus_align(mods, cfg, monkeypatch):
     res = cfg.pop("res")
     if chunk:
         monkeypatch.setenv("NDT2D_PAIRS_BYTES", str(chunk))
+    if cfg.pop("fused", 1) == 0:        # K = 1 takes the fused shared-memory path by default; this forces the general (global hash table) path
+        monkeypatch.setenv("NDT2D_PAIRS_FUSED", "0")
     m, o = make_pair(mods, res, grid, **cfg)
     sc = synth.SCAN_1080
     ranges, poses = synth.scans(14, traj_len=4000, first=50, step=9, sigma=0.01, **sc)     # neighbours 0.85 m apart
