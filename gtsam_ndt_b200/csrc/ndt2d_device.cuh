@@ -538,18 +538,20 @@ struct Fetched {
 //   TABLE_GHASH  L.cells is an open-addressing hash table in global memory keyed by the dense index (ndt2d_align_pairs,
 //                general path): hash_mask + 1 records, key in the record's `n` word, sentinel record behind them
 //   TABLE_SHASH  the valid cells of one target scan in SHARED memory (ndt2d_align_pairs, fused path): L.cells is the compact
-//                record array (key in the `n` word), L.cnt points at a u16 index of hash_mask + 1 slots (0xffff = empty)
+//                array of 24-byte records, L.cnt the index of hash_mask + 1 four-entry buckets (see lookup_shared), and
+//                L.zero_rec the number of the all-zero record that a failed lookup returns
 enum { TABLE_DENSE = 0, TABLE_GHASH = 1, TABLE_SHASH = 2 };
 
 struct LatticePk {
     unsigned nhx, nhy, njx;
     unsigned sentinel; // dense tables: index of the first of the njx + 2 all-zero records that follow the cells (the gather target of
                        // a point outside the lattice; sentinel + {0, 1, njx, njx + 1} are all zero records, so the four cells
-                       // of an outside point need no test of their own). Hash tables: the one zero record after the slots.
+                       // of an outside point need no test of their own). Global hash tables: the one zero record after the
+                       // slots. Shared tables: the number of the zero record behind the compact array.
     unsigned mask;     // hash tables only: slots - 1
     unsigned outside;  // what lattice_base() returns for a point outside the lattice: `sentinel` for dense tables (the gather
                        // goes straight to the zero records); 0xffffffff for hash tables, where every smaller value is a cell key
-    unsigned srec, sidx; // TABLE_SHASH: shared-window addresses of the record array and of the u16 slot index
+    unsigned srec, sidx; // TABLE_SHASH: shared-window addresses of the record array and of the u32 slot index
     float st;          // stride in metres: local coordinate = fma(df, st, off)
     u64 off[4];        // per cell of the point: minus the cell centre relative to node (hx, hy): (-st/2, -st/2) for one
                        // grid; (-a st, -b st) for cell (a, b) of the four half-shifted grids
@@ -561,7 +563,7 @@ __device__ __forceinline__ LatticePk lattice_pack(const LevelDev &L, int table)
     LatticePk G;
     G.nhx = (unsigned)L.nhx; G.nhy = (unsigned)L.nhy; G.njx = (unsigned)L.njx;
     G.mask = L.hash_mask;
-    G.sentinel = table != TABLE_DENSE ? L.hash_mask + 1u : (unsigned)L.njx * (unsigned)L.njy;
+    G.sentinel = table == TABLE_DENSE ? (unsigned)L.njx * (unsigned)L.njy : table == TABLE_GHASH ? L.hash_mask + 1u : L.zero_rec;
     G.outside = table != TABLE_DENSE ? 0xffffffffu : G.sentinel;
     G.srec = G.sidx = 0u;
     if (table == TABLE_SHASH) {
@@ -602,37 +604,73 @@ __device__ __forceinline__ unsigned hash_slot(unsigned key, unsigned mask) { ret
 // the point relative to the centre of its cell k (SPEC 4, v4): one f32 fma per coordinate
 __device__ __forceinline__ u64 local_xy(const LatticePk &G, u64 df, int k) { return fma2(df, bc(G.st), G.off[k]); }
 
-// TABLE_SHASH: record `id` of the compact array in shared memory (two 128-bit shared loads)
-__device__ __forceinline__ Cell4 load_cell_shared(unsigned srec, unsigned id)
+// TABLE_SHASH: the valid cells of one target in shared memory. Records are 24 bytes {mux, muy, B00, B01, B11, key}
+// (B01 once, no count: the evaluation needs neither), appended in key order, followed by one all-zero record (key word
+// 0xffffffff) for lookups that find nothing. The index is made of hash_mask + 1 BUCKETS of four u32 entries (one 128-bit
+// shared load): a used entry is (key & 0x7fff) << 16 | record id, an empty one 0xffffffff, entries fill from the front;
+// a key whose bucket hash_slot(key) is full goes to the next bucket. The common lookup is therefore branch-free - one
+// bucket load, four tag compares, one record load, the record's own key word as the verdict - and only a full bucket or
+// a false tag match (both rare: about one bucket in 300 overflows) sends the lane to the probing slow path.
+static constexpr unsigned kSharedRecordBytes = 24;
+__device__ __forceinline__ void lds_record(unsigned a, u64 &mu, u64 &b0, u64 &b1k)
 {
-    Cell4 r;
-    const unsigned a = srec + id * 32u;
-    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(r.mu), "=l"(r.B0) : "r"(a));
-    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2+16];" : "=l"(r.B1), "=l"(r.nv) : "r"(a));
-    return r;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(mu) : "r"(a));
+    asm volatile("ld.shared.b64 %0, [%1+8];" : "=l"(b0) : "r"(a));
+    asm volatile("ld.shared.b64 %0, [%1+16];" : "=l"(b1k) : "r"(a));
 }
-__device__ __forceinline__ unsigned load_slot_shared(unsigned sidx, unsigned slot)
+__device__ __forceinline__ void lds_bucket(unsigned a, unsigned &e0, unsigned &e1, unsigned &e2, unsigned &e3)
 {
-    unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(sidx + slot * 2u));
-    return v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3) : "r"(a));
 }
-// the record of cell `key` (0xffffffff: the point is outside the lattice), or the all-zero record when the target has no
-// valid cell there. The first probe is unconditional; collisions (the index is at most 1/3 full) are chased in a loop.
-__device__ __forceinline__ Cell4 lookup_shared(const LatticePk &G, unsigned key)
+__device__ __forceinline__ Cell4 record_to_cell(u64 mu, u64 b0, u64 b1k, bool valid)
 {
-    unsigned slot = hash_slot(key, G.mask);
-    unsigned id = key == 0xffffffffu ? 0xffffu : load_slot_shared(G.sidx, slot);
     Cell4 c;
-    c.mu = c.B0 = c.B1 = c.nv = 0ull;
-    for (unsigned probes = 0; id != 0xffffu && probes <= G.mask; ++probes) {
-        c = load_cell_shared(G.srec, id);
-        if ((unsigned)__float_as_int(lo32(c.nv)) == key) return c;
-        slot = (slot + 1u) & G.mask;
-        id = load_slot_shared(G.sidx, slot);
-    }
-    c.mu = c.B0 = c.B1 = c.nv = 0ull;
+    c.mu = mu;
+    c.B0 = b0;
+    c.B1 = pk(hi32(b0), lo32(b1k));            // (B01, B11)
+    c.nv = pk(0.0f, valid ? 1.0f : 0.0f);
     return c;
+}
+// the probing lookup: buckets from hash_slot(key) on, every tag match verified against the record's key
+static __device__ __noinline__ Cell4 lookup_shared_slow(unsigned srec, unsigned sidx, unsigned mask, unsigned zid, unsigned key)
+{
+    const unsigned tag = key & 0x7fffu;
+    unsigned b = hash_slot(key, mask);
+    u64 mu, b0, b1k;
+    for (unsigned probes = 0; probes <= mask; ++probes) {
+        unsigned e[4];
+        lds_bucket(sidx + b * 16u, e[0], e[1], e[2], e[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if ((e[j] >> 16) == tag) {
+                lds_record(srec + (e[j] & 0xffffu) * kSharedRecordBytes, mu, b0, b1k);
+                if ((unsigned)__float_as_int(hi32(b1k)) == key) return record_to_cell(mu, b0, b1k, true);
+            }
+        }
+        if (e[3] == 0xffffffffu) break;        // the bucket never filled up: the key is not in the table
+        b = (b + 1u) & mask;
+    }
+    lds_record(srec + zid * kSharedRecordBytes, mu, b0, b1k);
+    return record_to_cell(mu, b0, b1k, false);
+}
+// common path; `slow` is set when this lane has to take the probing path (key 0xffffffff = outside the lattice: no record)
+__device__ __forceinline__ Cell4 lookup_shared(const LatticePk &G, unsigned key, bool &slow)
+{
+    const unsigned tag = key & 0x7fffu;
+    unsigned e0, e1, e2, e3;
+    lds_bucket(G.sidx + hash_slot(key, G.mask) * 16u, e0, e1, e2, e3);
+    unsigned e = 0xffffffffu;
+    e = (e3 >> 16) == tag ? e3 : e;
+    e = (e2 >> 16) == tag ? e2 : e;
+    e = (e1 >> 16) == tag ? e1 : e;
+    e = (e0 >> 16) == tag ? e0 : e;
+    const bool inside = key != 0xffffffffu;
+    const bool tagged = inside && e != 0xffffffffu;
+    u64 mu, b0, b1k;
+    lds_record(G.srec + (tagged ? (e & 0xffffu) : G.sentinel) * kSharedRecordBytes, mu, b0, b1k);
+    const bool ok = tagged && (unsigned)__float_as_int(hi32(b1k)) == key;
+    slow = inside && !ok && (tagged || e3 != 0xffffffffu);   // a false tag match, or a full bucket without a match
+    return record_to_cell(mu, b0, b1k, ok);
 }
 
 // P64 (score-only kernels with the scan staged in shared memory): pts holds double2 per point, r and j are not needed
@@ -667,8 +705,14 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
 #pragma unroll
         for (int k = 0; k < Fetched<OV>::NC; ++k) {
             const unsigned o = (k & 1) + (k >> 1) * G.njx;
-            F.cA[k] = lookup_shared(G, bA == G.outside ? bA : bA + o);
-            F.cB[k] = lookup_shared(G, bB == G.outside ? bB : bB + o);
+            const unsigned kA = bA == G.outside ? bA : bA + o, kB = bB == G.outside ? bB : bB + o;
+            bool slowA, slowB;
+            F.cA[k] = lookup_shared(G, kA, slowA);
+            F.cB[k] = lookup_shared(G, kB, slowB);
+            if (__any_sync(0xffffffffu, slowA || slowB)) {
+                if (slowA) F.cA[k] = lookup_shared_slow(G.srec, G.sidx, G.mask, G.sentinel, kA);
+                if (slowB) F.cB[k] = lookup_shared_slow(G.srec, G.sidx, G.mask, G.sentinel, kB);
+            }
         }
     } else {
         const bool inA = bA != G.outside, inB = bB != G.outside;

@@ -20,6 +20,7 @@ struct LevelDev {
     // hash_mask+1 records keyed by that index (the key sits in the record's `n` word, 0xffffffff = empty slot), with the
     // sentinel record at index hash_mask+1: the per-target tables of the batched scan-to-scan path (ndt2d_align_pairs).
     unsigned hash_mask;
+    unsigned zero_rec;        // shared-memory tables of the fused pairs path only (TABLE_SHASH in ndt2d_device.cuh)
 };
 
 static constexpr unsigned kEmptyKey = 0xffffffffu;
@@ -90,7 +91,7 @@ cudaError_t launch_pairs_build(const LaunchCfg &c, const PairBuildArgs &a, int64
 
 // Batched scan-to-scan, fused path (K = 1, scans small enough for shared memory): one warp per PAIR builds the target's
 // grid for one pyramid level in its own shared-memory slice (radix sort of the cell keys, one lane per cell for the sums
-// and the finalisation, compact record array behind a u16 hash index), aligns the source on it, and goes on to the next
+// and the finalisation, compact record array behind a tagged u32 hash index), aligns the source on it, and goes on to the next
 // level - no table ever touches global memory.
 struct PairFusedArgs {
     const float2 *xy;
@@ -105,8 +106,9 @@ struct PairFusedArgs {
     unsigned cap_t;          // sort capacity in points (longest target, padded to 32)
     unsigned cap_s;          // source slot capacity in points (longest source, padded to 64)
     unsigned rmax;           // record capacity: longest target / min_points
-    unsigned hslots;         // slots of the u16 hash index (power of two >= 2 * rmax)
+    unsigned hslots;         // u32 entries of the hash index: four per bucket, a power of two of buckets >= 0.7 * rmax
     unsigned off_a, off_r, off_h, warp_bytes;   // byte offsets of the three areas in a warp's slice, and its size
+    unsigned warps_per_block;
     unsigned int *counter;   // work queue head, zero on entry
     int *error;              // set to 1 + pair when a target's lattice would exceed 2^31 cells
 };

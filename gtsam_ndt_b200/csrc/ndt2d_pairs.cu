@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) k_pairs_build(const PairBuildArgs a)
 // fused path: one warp per pair, the target's grid in shared memory
 // ------------------------------------------------------------------------------------------------
 
-static constexpr int FUSED_WARPS = 4;            // warps per block; two such blocks share an SM at 1080-point scans
+static constexpr int FUSED_WARPS_MAX = 8;        // warps per block: as many as let two blocks share an SM, at most this (5 at 1080-point scans)
 static constexpr unsigned FUSED_STATE_BYTES = 352; // WarpState (216 B) + LevelDev (112 B), rounded up to 16
 
 // SPEC 2 geometry of one level of a target's grid from its bounding box: the f32 expressions of setup_level() in
@@ -195,51 +195,59 @@ __device__ __forceinline__ bool pair_level_geometry(LevelDev &L, float res, int 
 
 // SPEC 3 for one (target scan, level) by ONE warp, entirely in its shared-memory slice. The integer sums are order
 // independent, so grouping the points by cell with a sort and summing each group in one lane gives the sums - and
-// therefore the records - of the dense build bit for bit. Steps: (1) cell key of every point inside the lattice,
-// compacted; (2) LSD radix sort of (key, point index) by key, 8 bits per pass, only as many passes as the lattice has
-// key bits; (3) run heads = the cells; (4) one lane per cell with at least min_points points: integer sums over its
-// points, finalisation, record appended to the compact array; its key goes into the u16 hash index (first free slot
-// from hash_slot(key), resolved inside the warp without atomics). Returns the number of records.
+// therefore the records - of the dense build bit for bit. Steps: (1) cell key of every point (one past the last cell
+// for a point outside the lattice); (2) LSD radix sort of the point indices by key, 8 bits per pass, only as many passes
+// as the lattice has key bits; (3) run heads = the cells; (4) one lane per cell with at least min_points points: integer
+// sums over its points, finalisation, 24-byte record appended to the compact array (so the records are in key order),
+// and (key tag, record id) entered into the bucket index: first bucket from hash_slot(key) with a free entry, conflicts
+// between the lanes of a round resolved inside the warp, no atomics. Returns the number of records.
+// Shared memory: keyof[cap_t] u32, two index buffers of cap_t + 2 u16 (ping-pong; the idle one holds the run heads
+// afterwards), the record area (the radix histogram lives there during the sort) and the slot index.
 __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 *__restrict__ src, int n, int min_points, double eig_ratio,
-                                               unsigned *key0, unsigned cap_t, float4 *rec, unsigned short *hidx, unsigned hslots)
+                                               unsigned *keyof, unsigned cap_t, float *rec, unsigned *hidx, unsigned hslots)
 {
     const LevelDev &L = *Lp;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    unsigned *key[2] = {key0, key0 + cap_t};
-    unsigned short *idx[2] = {reinterpret_cast<unsigned short *>(key0 + 2 * (size_t)cap_t),
-                              reinterpret_cast<unsigned short *>(key0 + 2 * (size_t)cap_t) + cap_t};
+    unsigned short *perm[2] = {reinterpret_cast<unsigned short *>(keyof + cap_t), reinterpret_cast<unsigned short *>(keyof + cap_t) + cap_t + 2};
     unsigned *hist = reinterpret_cast<unsigned *>(rec);     // 256 counters; the record area is not in use during the sort
-    // the index starts empty (0xffff in every slot)
-    for (unsigned s = lane; s < hslots / 2; s += 32) reinterpret_cast<unsigned *>(hidx)[s] = 0xffffffffu;
-    // (1) keys
+    for (unsigned s = lane; s < hslots; s += 32) hidx[s] = 0xffffffffu;
+    const unsigned ncells = (unsigned)L.njx * (unsigned)L.njy;
+    // (1) keys; four windows of points are requested at a time (a warp has no other latency hiding here)
     int m = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        int hx = 0, hy = 0;
-        bool in = false;
-        if (i < n) {
-            const float2 p = __ldg(src + i);
-            in = lattice_of_point(L, p.x, p.y, hx, hy);
+    for (int base = 0; base < n; base += 128) {
+        float2 pw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + 32 * u + lane;
+            pw[u] = i < n ? __ldg(src + i) : make_float2(0.f, 0.f);
         }
-        const unsigned mask = __ballot_sync(FULL_MASK, in);
-        if (in) {
-            const int pos = m + __popc(mask & lt);
-            key[0][pos] = (unsigned)(hy * L.njx + hx);
-            idx[0][pos] = (unsigned short)i;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + 32 * u + lane;
+            int hx = 0, hy = 0;
+            const bool in = i < n && lattice_of_point(L, pw[u].x, pw[u].y, hx, hy);
+            if (i < n) {
+                keyof[i] = in ? (unsigned)(hy * L.njx + hx) : ncells;
+                perm[0][i] = (unsigned short)i;
+            }
+            m += __popc(__ballot_sync(FULL_MASK, in));
         }
-        m += __popc(mask);
     }
     __syncwarp();
-    if (m == 0) return 0;
-    // (2) radix sort by key
-    const unsigned ncells = (unsigned)L.njx * (unsigned)L.njy;
-    const int nbits = ncells > 1u ? 32 - __clz(ncells - 1u) : 1;
+    if (m == 0) {
+        __syncwarp();
+        if (lane < 6) rec[lane] = lane == 5 ? __int_as_float(-1) : 0.0f;      // no records: only the zero record
+        __syncwarp();
+        return 0;
+    }
+    // (2) radix sort of the indices by key (keys 0 .. ncells)
+    const int nbits = 32 - __clz(ncells);
     int cur = 0;
     for (int shift = 0; shift < nbits; shift += 8) {
         for (int b = lane; b < 256; b += 32) hist[b] = 0u;
         __syncwarp();
-        for (int i = lane; i < m; i += 32) atomicAdd(&hist[(key[cur][i] >> shift) & 255u], 1u);
+        for (int i = lane; i < n; i += 32) atomicAdd(&hist[(keyof[perm[cur][i]] >> shift) & 255u], 1u);
         __syncwarp();
         unsigned c[8], sum = 0u;
 #pragma unroll
@@ -255,32 +263,29 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
 #pragma unroll
         for (int j = 0; j < 8; ++j) { hist[8 * lane + j] = run; run += c[j]; }
         __syncwarp();
-        for (int base = 0; base < m; base += 32) {      // windows in order: the scatter is stable
+        for (int base = 0; base < n; base += 32) {      // windows in order: the scatter is stable
             const int i = base + lane;
-            const bool valid = i < m;
-            const unsigned k = valid ? key[cur][i] : 0u;
-            const unsigned short ix = valid ? idx[cur][i] : (unsigned short)0;
-            const unsigned d = valid ? (k >> shift) & 255u : 256u + (unsigned)lane;
+            const bool valid = i < n;
+            const unsigned short ix = valid ? perm[cur][i] : (unsigned short)0;
+            const unsigned d = valid ? (keyof[ix] >> shift) & 255u : 256u + (unsigned)lane;
             const unsigned peers = __match_any_sync(FULL_MASK, d);
             const unsigned rank = __popc(peers & lt);
             const unsigned off = valid ? hist[d] : 0u;
             __syncwarp();
             if (valid && rank == 0u) hist[d] = off + __popc(peers);
             __syncwarp();
-            if (valid) {
-                key[cur ^ 1][off + rank] = k;
-                idx[cur ^ 1][off + rank] = ix;
-            }
+            if (valid) perm[cur ^ 1][off + rank] = ix;
         }
         __syncwarp();
         cur ^= 1;
     }
-    // (3) run heads
-    unsigned short *hpos = reinterpret_cast<unsigned short *>(key[cur ^ 1]);
+    // (3) run heads among the m points inside the lattice (they come first: the outside key is the largest)
+    const unsigned short *order = perm[cur];
+    unsigned short *hpos = perm[cur ^ 1];
     int nruns = 0;
     for (int base = 0; base < m; base += 32) {
         const int i = base + lane;
-        const bool head = i < m && (i == 0 || key[cur][i] != key[cur][i - 1]);
+        const bool head = i < m && (i == 0 || keyof[order[i]] != keyof[order[i - 1]]);
         const unsigned mask = __ballot_sync(FULL_MASK, head);
         if (head) hpos[nruns + __popc(mask & lt)] = (unsigned short)i;
         nruns += __popc(mask);
@@ -288,7 +293,7 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
     if (lane == 0) hpos[nruns] = (unsigned short)m;
     __syncwarp();
     // (4) one lane per cell
-    const unsigned hmask = hslots - 1u;
+    const unsigned bmask = hslots / 4u - 1u;
     int nrec = 0;
     for (int base = 0; base < nruns; base += 32) {
         const int r = base + lane;
@@ -298,47 +303,61 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
         unsigned kr = 0u;
         float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
         if (ok) {
-            kr = key[cur][start];
+            kr = keyof[order[start]];
             const int jx = (int)(kr % (unsigned)L.njx), jy = (int)(kr / (unsigned)L.njx);
             const double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
             const double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
             long long s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
-            for (int p = start; p < start + len; ++p) {
-                const float2 pt = __ldg(src + idx[cur][p]);
-                const double dx = (double)pt.x - cx, dy = (double)pt.y - cy;
-                const long long qx = __double2ll_rn(dx * L.qs), qy = __double2ll_rn(dy * L.qs);
-                s0 += qx; s1 += qy; s2 += qx * qx; s3 += qx * qy; s4 += qy * qy;
+            for (int p = start; p < start + len; p += 4) {      // four independent loads per trip (L2 round trips overlap)
+                float2 pt[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pt[u] = __ldg(src + order[min(p + u, start + len - 1)]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (p + u < start + len) {
+                        const double dx = (double)pt[u].x - cx, dy = (double)pt[u].y - cy;
+                        const long long qx = __double2ll_rn(dx * L.qs), qy = __double2ll_rn(dy * L.qs);
+                        s0 += qx; s1 += qy; s2 += qx * qx; s3 += qx * qy; s4 += qy * qy;
+                    }
+                }
             }
             finalize_record((unsigned)len, s0, s1, s2, s3, s4, L.qu, min_points, eig_ratio, ra, rb);
-            rb.z = __int_as_float((int)kr);     // the key sits in the record's `n` word for the probing reader
         }
-        const unsigned mask = __ballot_sync(FULL_MASK, ok);
+        const bool keep = ok && rb.w != 0.0f;               // a degenerate cell (SPEC 3: l1 <= 1e-10) stays invalid: no record
+        const unsigned mask = __ballot_sync(FULL_MASK, keep);
         const unsigned id = (unsigned)nrec + __popc(mask & lt);
-        if (ok) {
-            rec[2 * (size_t)id] = ra;
-            rec[2 * (size_t)id + 1] = rb;
+        if (keep) {
+            float *o = rec + 6 * (size_t)id;                 // {mux, muy, B00, B01, B11, key}
+            o[0] = ra.x; o[1] = ra.y; o[2] = ra.z; o[3] = ra.w; o[4] = rb.y; o[5] = __int_as_float((int)kr);
         }
-        // index insertion: every pending lane looks at its slot; of the lanes that found the same free slot the lowest
-        // takes it, everybody else moves on by one (the index is at most a third full)
-        unsigned slot = hash_slot(kr, hmask);
-        bool pending = ok;
+        // index insertion (lookup_shared in ndt2d_device.cuh): every pending lane counts the used entries of its bucket; the
+        // lanes of this round that want the same bucket take its free entries in lane order, the rest move on by one bucket
+        unsigned b = hash_slot(kr, bmask);
+        bool pending = keep;
         while (__any_sync(FULL_MASK, pending)) {
-            const bool free_slot = pending && hidx[slot] == 0xffffu;
-            const unsigned peers = __match_any_sync(FULL_MASK, free_slot ? slot : 0x10000u + (unsigned)lane);
-            const bool win = free_slot && (__ffs(peers) - 1 == lane);
+            unsigned used = 0u;
+            if (pending) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) used += hidx[4u * b + j] != 0xffffffffu ? 1u : 0u;
+            }
+            const unsigned peers = __match_any_sync(FULL_MASK, pending ? b : 0x100000u + (unsigned)lane);
+            const unsigned pos = used + __popc(peers & lt);
+            const bool win = pending && pos < 4u;
             __syncwarp();
-            if (win) hidx[slot] = (unsigned short)id;
+            if (win) hidx[4u * b + pos] = ((kr & 0x7fffu) << 16) | id;
             __syncwarp();
             if (win) pending = false;
-            else if (pending) slot = (slot + 1u) & hmask;
+            else if (pending) b = (b + 1u) & bmask;
         }
         nrec += __popc(mask);
     }
+    // the all-zero record behind the compact array: what a failed lookup loads (finite factors, valid = 0)
+    if (lane < 6) rec[6 * (size_t)nrec + lane] = lane == 5 ? __int_as_float(-1) : 0.0f;
     __syncwarp();
     return nrec;
 }
 
-__global__ void __launch_bounds__(FUSED_WARPS * 32) k_pairs_fused(const __grid_constant__ PairFusedArgs a)
+__global__ void __launch_bounds__(FUSED_WARPS_MAX * 32) k_pairs_fused(const __grid_constant__ PairFusedArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -347,8 +366,8 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32) k_pairs_fused(const __grid_c
     LevelDev *Ls = reinterpret_cast<LevelDev *>(slice + 224);
     unsigned *area_a = reinterpret_cast<unsigned *>(slice + a.off_a);
     float2 *slot = reinterpret_cast<float2 *>(slice + a.off_a);
-    float4 *rec = reinterpret_cast<float4 *>(slice + a.off_r);
-    unsigned short *hidx = reinterpret_cast<unsigned short *>(slice + a.off_h);
+    float *rec = reinterpret_cast<float *>(slice + a.off_r);
+    unsigned *hidx = reinterpret_cast<unsigned *>(slice + a.off_h);
     const float2 far = make_float2(1e18f, 1e18f);
     for (;;) {
         unsigned job = 0;
@@ -364,11 +383,19 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32) k_pairs_fused(const __grid_c
         // SPEC 2 auto-fit: bounding box of the target's finite points
         float xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY;
         if (!a.explicit_grid) {
-            for (int i = lane; i < tn; i += 32) {
-                const float2 p = __ldg(tsrc + i);
-                if (!isfinite(p.x) || !isfinite(p.y)) continue;
-                xmin = fminf(xmin, p.x); xmax = fmaxf(xmax, p.x);
-                ymin = fminf(ymin, p.y); ymax = fmaxf(ymax, p.y);
+            for (int base = 0; base < tn; base += 128) {
+                float2 pw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + 32 * u + lane;
+                    pw[u] = i < tn ? __ldg(tsrc + i) : make_float2(NAN, NAN);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!isfinite(pw[u].x) || !isfinite(pw[u].y)) continue;
+                    xmin = fminf(xmin, pw[u].x); xmax = fmaxf(xmax, pw[u].x);
+                    ymin = fminf(ymin, pw[u].y); ymax = fmaxf(ymax, pw[u].y);
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -384,17 +411,20 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32) k_pairs_fused(const __grid_c
         for (int l = 0; l < a.nlevels; ++l) {
             LevelDev L;
             const bool usable = pair_level_geometry(L, a.res_m[l], 0, a.explicit_grid != 0, a.gox, a.goy, a.gex, a.gey, xmin, ymin, xmax, ymax);
-            L.cells = rec;
-            L.cnt = reinterpret_cast<uint32_t *>(hidx);      // TABLE_SHASH: the u16 slot index
+            L.cells = reinterpret_cast<const float4 *>(rec); // TABLE_SHASH: the compact array of 24-byte records
+            L.cnt = hidx;                                    //              and the bucket index
             L.sums = nullptr;
-            L.hash_mask = a.hslots - 1u;
+            L.hash_mask = a.hslots / 4u - 1u;
+            L.zero_rec = 0u;
             if (!usable && lane == 0) atomicMax(a.error, (int)job + 1);
             __syncwarp();                                    // the previous level's evaluation has finished with *Ls
             if (lane == 0) *Ls = L;
             __syncwarp();
-            build_table_shared(Ls, tsrc, tn, a.prm.min_points, a.prm.eig_ratio, area_a, a.cap_t, rec, hidx, a.hslots);
+            const int nrec = build_table_shared(Ls, tsrc, tn, a.prm.min_points, a.prm.eig_ratio, area_a, a.cap_t, rec, hidx, a.hslots);
+            if (lane == 0) Ls->zero_rec = (unsigned)nrec;
             // the sort buffers are dead: the same area takes the source scan (sanitised, padded with the far-away point)
             const int npad = (sn + 63) & ~63;
+#pragma unroll 4
             for (int i = lane; i < npad; i += 32) slot[i] = i < sn ? sanitize(__ldg(ssrc + i)) : far;
             __syncwarp();
             status = lm_level<WarpScope>(a.prm, sn, ws, evals, [&](int trial) { eval_to_smem<0, true, TABLE_SHASH>(Ls, slot, sn, ws, trial); });
@@ -406,22 +436,24 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32) k_pairs_fused(const __grid_c
 
 bool pairs_fused_layout(PairFusedArgs &a, int64_t max_target_points, int64_t max_source_points, int smem_optin)
 {
-    if (max_target_points > 65535 || max_source_points > (1 << 20)) return false;
+    if (max_target_points > 65533 || max_source_points > (1 << 20)) return false;
     a.cap_t = (unsigned)((std::max<int64_t>(max_target_points, 1) + 31) & ~(int64_t)31);
     a.cap_s = (unsigned)((std::max<int64_t>(max_source_points, 1) + 63) & ~(int64_t)63);
     a.rmax = (unsigned)(a.cap_t / (unsigned)std::max(a.prm.min_points, 2)) + 1u;
-    a.hslots = 64;
-    while (a.hslots < 2u * a.rmax + 2u) a.hslots <<= 1;
-    if (a.hslots > 65536u) return false;          // hash_slot() yields 17 bits at most
+    a.hslots = 64;                                                  // four entries per bucket; buckets >= 0.7 * rmax
+    while (a.hslots < 4u * ((7u * a.rmax + 9u) / 10u)) a.hslots <<= 1;
+    if (a.rmax > 65534u || a.hslots > 4u * 65536u) return false;  // record ids are 16 bits; hash_slot() yields 17 bits
     auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
-    const size_t size_a = up16(std::max<size_t>((size_t)a.cap_s * 8, (size_t)a.cap_t * 12));
-    const size_t size_r = up16(std::max<size_t>((size_t)a.rmax * 32, 1024));
+    const size_t size_a = up16(std::max<size_t>((size_t)a.cap_s * 8, (size_t)a.cap_t * 4 + 2 * ((size_t)a.cap_t + 2) * 2));
+    const size_t size_r = up16(std::max<size_t>(((size_t)a.rmax + 1) * 24, 1024));      // records + the zero record; the radix histogram
     a.off_a = FUSED_STATE_BYTES;
     a.off_r = (unsigned)(a.off_a + size_a);
     a.off_h = (unsigned)(a.off_r + size_r);
-    a.warp_bytes = (unsigned)up16(a.off_h + (size_t)a.hslots * 2);
+    a.warp_bytes = (unsigned)up16(a.off_h + (size_t)a.hslots * 4);
     static_assert(sizeof(WarpState) <= 224 && sizeof(LevelDev) <= FUSED_STATE_BYTES - 224, "per-warp state area");
-    return (size_t)a.warp_bytes * FUSED_WARPS <= (size_t)smem_optin;
+    // two blocks per SM (each gets half of the opt-in limit minus the 1 KB the driver reserves per block)
+    a.warps_per_block = (unsigned)std::min<size_t>(FUSED_WARPS_MAX, ((size_t)smem_optin / 2 - 1024) / a.warp_bytes);
+    return a.warps_per_block >= 2;
 }
 
 cudaError_t launch_pairs_fused(const LaunchCfg &c, const PairFusedArgs &a, int64_t *launches)
@@ -429,7 +461,8 @@ cudaError_t launch_pairs_fused(const LaunchCfg &c, const PairFusedArgs &a, int64
     if (a.npairs <= 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), c.stream);
     if (e != cudaSuccess) return e;
-    const size_t smem = (size_t)a.warp_bytes * FUSED_WARPS;
+    const int wpb = (int)a.warps_per_block;
+    const size_t smem = (size_t)a.warp_bytes * wpb;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(k_pairs_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -437,12 +470,12 @@ cudaError_t launch_pairs_fused(const LaunchCfg &c, const PairFusedArgs &a, int64
     e = cudaFuncSetAttribute(k_pairs_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_fused, FUSED_WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_fused, wpb * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    const int64_t need = ((int64_t)a.npairs + FUSED_WARPS - 1) / FUSED_WARPS;
+    const int64_t need = ((int64_t)a.npairs + wpb - 1) / wpb;
     const int64_t cap = (int64_t)c.sm_count * per_sm;
-    k_pairs_fused<<<(int)std::min(need, cap), FUSED_WARPS * 32, smem, c.stream>>>(a);
+    k_pairs_fused<<<(int)std::min(need, cap), wpb * 32, smem, c.stream>>>(a);
     ++*launches;
     return cudaGetLastError();
 }
