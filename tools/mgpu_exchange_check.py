@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Multi-GPU check of the peer-memory best-hypothesis exchange (run under torchrun, one rank per GPU):
 the sharded sweep published through ndt2d_sweep_publish / ndt2d_exchange_wait must return, on every rank and for
-every query, exactly what one GPU returns for the unsharded sweep (SPEC.md section 6: ties to the smaller index).
+every query, exactly what one GPU returns for the unsharded sweep (SPEC.md section 6: ties to the smaller index), and
+distributed.relocalize_sharded must equal the single-GPU ndt2d_relocalize bit for bit.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_exchange_check.py
 """
@@ -69,6 +70,14 @@ def main():
         ex.wait(1000 + it * 8 + 7, timeout_ms=20000)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / 80
+    # multi-GPU relocalisation end to end: sharded sweep -> global top-k -> refinement dealt out over the ranks; every rank
+    # must hold, bit for bit, what ndt2d_relocalize returns on one GPU
+    for k in (1, 3, 8):
+        gi, gr = D.relocalize_sharded(m, xy, hyp, k=k)
+        si, sr = m.relocalize(xy, hyp, k=k)
+        if not (np.array_equal(gi, si) and gr.tobytes() == sr.tobytes()):
+            ok = False
+            print(f"rank {rank}: relocalize_sharded(k={k}) differs from the single-GPU ndt2d_relocalize", flush=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     ex.close()
