@@ -62,6 +62,7 @@ SIGNATURES = {
     "ndt2d_sweep": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, C.c_int64, _V, C.c_int, _V, _V]),
     "ndt2d_sweep_device": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, C.c_int64, _V, C.c_int, _V, _V]),
     "ndt2d_relocalize": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, C.c_int64, C.c_int, _V, _V]),
+    "ndt2d_relocalize_device": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, C.c_int64, C.c_int, _V, _V]),
     "ndt2d_exchange_create": (C.c_int, [_V, C.c_int, C.c_int, C.c_int, _V]),
     "ndt2d_exchange_open": (C.c_int, [_V, _V]),
     "ndt2d_sweep_publish": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, C.c_int64, _V, C.c_int64, C.c_uint64]),

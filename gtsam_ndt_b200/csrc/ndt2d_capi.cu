@@ -305,7 +305,7 @@ void ndt2d_destroy(ndt2d_matcher *m)
     m->b_ring.release();
     DevBuf *bufs[] = {&m->b_xy, &m->b_off, &m->b_init, &m->b_res, &m->b_pose, &m->b_out, &m->b_cnt, &m->b_idx, &m->b_terms,
                       &m->b_hyp, &m->b_scores, &m->b_tki, &m->b_tkv, &m->b_scratch, &m->b_counter, &m->b_beams, &m->b_ranges,
-                      &m->b_box, &m->b_ptab, &m->b_pcnt, &m->b_psums, &m->b_pgeo, &m->b_ptargets, &m->b_ppairs, &m->b_perr};
+                      &m->b_box, &m->b_ptab, &m->b_pcnt, &m->b_psums, &m->b_pgeo, &m->b_ptargets, &m->b_ppairs, &m->b_perr, &m->b_reloc};
     for (DevBuf *b : bufs) b->release();
     if (m->copy_stream) {
         cudaStreamSynchronize(m->copy_stream);
@@ -955,31 +955,67 @@ int ndt2d_sweep(ndt2d_matcher *m, int level, const float *xy, int n, const float
     return ndt2d_synchronize(m);
 }
 
+// Everything on the device, nothing synchronised: sweep of the level, top-k, then the k candidates become k refinement
+// jobs of the SAME scan (AlignArgs::job_scan) - no copy of the scan, no trip to the host in between.
+int ndt2d_relocalize_device(ndt2d_matcher *m, int level, const float *d_xy, int n, const float *d_hyp, int64_t nhyp, int k,
+                            int64_t *d_best_idx, ndt2d_result *d_res)
+{
+    int rc = check_level(m, level);
+    if (rc) return rc;
+    if (k < 1 || k > 1024 || n < 0 || nhyp < 0 || !d_best_idx || !d_res || (nhyp > 0 && !d_hyp))
+        return fail(m, NDT2D_EINVAL, "bad arguments");
+    DeviceGuard g(m->device);
+    CK(m, m->b_tkv.ensure((size_t)k * 8));
+    CK(m, m->b_reloc.ensure((size_t)k * (24 + 4) + 16 + 64));
+    rc = ndt2d_sweep_device(m, level, d_xy, n, d_hyp, nhyp, nullptr, k, d_best_idx, m->b_tkv.as<double>());
+    if (rc) return rc;
+    // layout of b_reloc: offsets[2] (i64) | init[3k] (f64) | job_scan[k] (i32)
+    int64_t *d_off = m->b_reloc.as<int64_t>();
+    double *d_init = reinterpret_cast<double *>(d_off + 2);
+    int32_t *d_jobs = reinterpret_cast<int32_t *>(d_init + 3 * (size_t)k);
+    m->reloc_off[0] = 0;
+    m->reloc_off[1] = n;
+    CK(m, cudaMemcpyAsync(d_off, m->reloc_off, 16, cudaMemcpyHostToDevice, m->cfg.stream));
+    CK(m, launch_topk_to_jobs(m->cfg, d_hyp, d_best_idx, k, d_init, d_jobs, &m->launches));
+    AlignArgs a;
+    fill_align_args(m, a);
+    a.xy = reinterpret_cast<const float2 *>(d_xy);
+    if (!a.xy) a.xy = m->b_counter.as<float2>();
+    a.offsets = d_off;
+    a.job_scan = d_jobs;
+    a.init = d_init;
+    a.res = d_res;
+    a.nscans = k;
+    a.cap_points = align_cap_points(m, n);
+    CK(m, launch_align(m->cfg, a, &m->launches));
+    return NDT2D_OK;
+}
+
 int ndt2d_relocalize(ndt2d_matcher *m, int level, const float *xy, int n, const float *hyp, int64_t nhyp, int k,
                      int64_t *best_idx, ndt2d_result *res)
 {
     if (!m) return NDT2D_EINVAL;
-    if (k < 1 || k > 1024 || !best_idx || !res) return fail(m, NDT2D_EINVAL, "bad arguments");
-    std::vector<double> best_score((size_t)k);
-    int rc = ndt2d_sweep(m, level, xy, n, hyp, nhyp, nullptr, k, best_idx, best_score.data());
+    if (k < 1 || k > 1024 || !best_idx || !res || n < 0 || nhyp < 0 || (n > 0 && !xy) || (nhyp > 0 && !hyp))
+        return fail(m, NDT2D_EINVAL, "bad arguments");
+    int rc = check_level(m, level);
     if (rc) return rc;
-    // refine each of the k best with the full pyramid align; the scan is replicated k times
-    int kk = 0;
-    while (kk < k && best_idx[kk] >= 0) ++kk;
-    std::vector<float> rep((size_t)kk * n * 2);
-    std::vector<int64_t> off((size_t)kk + 1, 0);
-    std::vector<double> init((size_t)kk * 3);
-    for (int j = 0; j < kk; ++j) {
-        if (n) memcpy(rep.data() + (size_t)j * n * 2, xy, (size_t)n * 8);
-        off[j + 1] = (int64_t)(j + 1) * n;
-        for (int t = 0; t < 3; ++t) init[3 * j + t] = (double)hyp[3 * best_idx[j] + t];
-    }
-    rc = ndt2d_align_batch(m, rep.data(), off.data(), kk, init.data(), res);
+    DeviceGuard g(m->device);
+    if ((rc = upload(m, m->b_xy, xy, (size_t)n * 8))) return rc;
+    if ((rc = upload(m, m->b_hyp, hyp, (size_t)nhyp * 12))) return rc;
+    CK(m, m->b_tki.ensure((size_t)k * 8));
+    CK(m, m->b_res.ensure((size_t)k * sizeof(ndt2d_result)));
+    rc = ndt2d_relocalize_device(m, level, m->b_xy.as<float>(), n, m->b_hyp.as<float>(), nhyp, k, m->b_tki.as<int64_t>(),
+                                 m->b_res.as<ndt2d_result>());
     if (rc) return rc;
-    for (int j = kk; j < k; ++j) {
-        memset(res + j, 0, sizeof(ndt2d_result));
-        res[j].status = NDT2D_NO_OVERLAP;
-    }
+    CK(m, cudaMemcpyAsync(best_idx, m->b_tki.p, (size_t)k * 8, cudaMemcpyDeviceToHost, m->cfg.stream));
+    CK(m, cudaMemcpyAsync(res, m->b_res.p, (size_t)k * sizeof(ndt2d_result), cudaMemcpyDeviceToHost, m->cfg.stream));
+    rc = ndt2d_synchronize(m);          // the one synchronisation of the call
+    if (rc) return rc;
+    for (int j = 0; j < k; ++j)
+        if (best_idx[j] < 0) {          // fewer than k hypotheses: no candidate, no result
+            memset(res + j, 0, sizeof(ndt2d_result));
+            res[j].status = NDT2D_NO_OVERLAP;
+        }
     return NDT2D_OK;
 }
 

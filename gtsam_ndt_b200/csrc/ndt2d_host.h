@@ -89,7 +89,8 @@ struct ndt2d_matcher {
     ndt2d::LevelDev lv[NDT2D_MAX_LEVELS]{};
     ndt2d::LevelMem mem[NDT2D_MAX_LEVELS];
     ndt2d::DevBuf b_xy, b_off, b_init, b_res, b_pose, b_out, b_cnt, b_idx, b_terms, b_hyp, b_scores, b_tki, b_tkv, b_scratch,
-        b_counter, b_beams, b_ranges, b_box, b_ptab, b_pcnt, b_psums, b_pgeo, b_ptargets, b_ppairs, b_perr;
+        b_counter, b_beams, b_ranges, b_box, b_ptab, b_pcnt, b_psums, b_pgeo, b_ptargets, b_ppairs, b_perr, b_reloc;
+    int64_t reloc_off[2] = {0, 0}; // source of the asynchronous offsets upload of ndt2d_relocalize_device
     double beams_amin = 0, beams_ainc = 0;
     int beams_n = 0;
     // host-buffer batch calls are cut into chunks: chunk i+1 is copied on copy_stream while chunk i computes

@@ -38,6 +38,9 @@ struct AlignArgs {
     float range_scale, range_min, range_max;
     const double *init;
     ndt2d_result *res;
+    // optional (xy mode): job j aligns scan job_scan[j] of the packed batch instead of scan j; a negative entry is an empty
+    // scan (ndt2d_relocalize: k refinements of ONE scan from k initial poses)
+    const int32_t *job_scan;
     // pairs mode (ndt2d_align_pairs): job p aligns scan pairs[2p+1] of the packed batch to the target whose per-level
     // geometry and hash tables are geo[pairs[2p] * nlevels + l]; lv[] is unused
     const int32_t *pairs;
@@ -129,6 +132,9 @@ struct PublishArgs {
 cudaError_t launch_topk(const LaunchCfg &c, const double *d_scores, int64_t nhyp, int k, int64_t *d_idx, double *d_val,
                         unsigned long long *d_scratch, int64_t *launches, const PublishArgs *pub = nullptr);
 int topk_scratch_words(int sm_count);
+// refinement jobs of a relocalisation: init[j] = hypothesis best_idx[j] widened to f64, job_scan[j] = 0 (or -1 when best_idx[j] < 0)
+cudaError_t launch_topk_to_jobs(const LaunchCfg &c, const float *d_hyp, const int64_t *d_best_idx, int k, double *d_init, int32_t *d_job_scan,
+                                int64_t *launches);
 // finite bounding box of points: d_box[4] = ordered-int encoded {xmin, ymin, xmax, ymax} (see bbox_decode)
 cudaError_t launch_bbox(const LaunchCfg &c, const float2 *d_xy, int64_t n, int *d_box, int64_t *launches);
 float bbox_decode(int v);

@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(BLOCK_ALIGN_THREADS) k_align_block(const __gri
     float2 *pts = reinterpret_cast<float2 *>(smem_raw + sizeof(WarpState));
     u64 *fac = reinterpret_cast<u64 *>(smem_raw + sizeof(WarpState) + (size_t)a.cap_points * sizeof(float2));
     const int job = blockIdx.x, tid = threadIdx.x;
-    const int64_t o0 = __ldg(a.offsets + job), o1 = __ldg(a.offsets + job + 1);
+    const int scan = a.job_scan ? __ldg(a.job_scan + job) : job;
+    const int64_t o0 = scan >= 0 ? __ldg(a.offsets + scan) : 0, o1 = scan >= 0 ? __ldg(a.offsets + scan + 1) : 0;
     const int n = (int)(o1 - o0), npad = (n + 63) & ~63;
     const float2 *src = a.xy + o0;
     for (int i = tid; i < npad; i += BLOCK_ALIGN_THREADS) pts[i] = i < n ? sanitize(__ldg(src + i)) : make_float2(1e18f, 1e18f);
@@ -366,8 +367,8 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
             }
             v.n = kept;
         } else {
-            const int src_scan = PAIRS ? __ldg(a.pairs + 2 * (size_t)job + 1) : (int)job;
-            int64_t o0 = __ldg(a.offsets + src_scan), o1 = __ldg(a.offsets + src_scan + 1);
+            const int src_scan = PAIRS ? __ldg(a.pairs + 2 * (size_t)job + 1) : a.job_scan ? __ldg(a.job_scan + job) : (int)job;
+            int64_t o0 = src_scan >= 0 ? __ldg(a.offsets + src_scan) : 0, o1 = src_scan >= 0 ? __ldg(a.offsets + src_scan + 1) : 0;
             v.n = (int)(o1 - o0);
             const float2 *src = a.xy + o0;
             if (STAGED) {
@@ -669,6 +670,26 @@ cudaError_t launch_topk(const LaunchCfg &c, const double *d_scores, int64_t nhyp
 }
 
 int topk_scratch_words(int sm_count) { return 1 + 2 * sm_count * 4; }
+
+__global__ void k_topk_to_jobs(const float *__restrict__ hyp, const int64_t *__restrict__ best_idx, int k, double *__restrict__ init,
+                               int32_t *__restrict__ job_scan)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    const int64_t i = best_idx[j];
+    job_scan[j] = i >= 0 ? 0 : -1;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) init[3 * j + t] = i >= 0 ? (double)__ldg(hyp + 3 * i + t) : 0.0;
+}
+
+cudaError_t launch_topk_to_jobs(const LaunchCfg &c, const float *d_hyp, const int64_t *d_best_idx, int k, double *d_init, int32_t *d_job_scan,
+                                int64_t *launches)
+{
+    if (k <= 0) return cudaSuccess;
+    k_topk_to_jobs<<<(k + 127) / 128, 128, 0, c.stream>>>(d_hyp, d_best_idx, k, d_init, d_job_scan);
+    ++*launches;
+    return cudaGetLastError();
+}
 
 // order-preserving float <-> int map so that integer atomicMin/atomicMax order floats
 __host__ __device__ static inline int float_to_ordered(float f)

@@ -296,6 +296,10 @@ class NdtMatcher2D:
     def exchange_close(self):
         self._ck(self._L.ndt2d_exchange_close(self._h))
 
+    def relocalize_device(self, d_xy, n, d_hyp, nhyp, k, d_best_idx, d_res, level=0):
+        """Sweep + top-k + k refinements, everything on the device, asynchronous (ndt2d_relocalize_device)."""
+        self._ck(self._L.ndt2d_relocalize_device(self._h, level, _ptr(d_xy), n, _ptr(d_hyp), nhyp, k, _ptr(d_best_idx), _ptr(d_res)))
+
     def relocalize(self, xy, hyp, k=4, level=0):
         xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
         hyp = np.ascontiguousarray(hyp, np.float32).reshape(-1, 3)

@@ -190,6 +190,11 @@ int ndt2d_sweep_device(ndt2d_matcher *m, int level, const float *d_xy, int n, co
 /* sweep, then full align from each of the k best hypotheses; res[k] sorted like the top-k */
 int ndt2d_relocalize(ndt2d_matcher *m, int level, const float *xy, int n, const float *hyp, int64_t nhyp,
                      int k, int64_t *best_idx, ndt2d_result *res);
+/* the same with scan, hypotheses, indices and results on the device; asynchronous on the handle's stream (sweep, top-k and
+ * the k refinements are queued back to back: the scan is not replicated and nothing returns to the host in between).
+ * Entries with d_best_idx[j] < 0 (fewer than k hypotheses) hold an empty-scan result with status NDT2D_NO_OVERLAP. */
+int ndt2d_relocalize_device(ndt2d_matcher *m, int level, const float *d_xy, int n, const float *d_hyp, int64_t nhyp,
+                            int k, int64_t *d_best_idx, ndt2d_result *d_res);
 
 /* ---- multi-GPU sweep: best-hypothesis exchange over peer memory (north_star: "independent ... pose
  *      hypotheses are split per GPU", only the best-hypothesis scores are combined) --------------

@@ -457,9 +457,25 @@ def test_relocalize_refines_topk(mods, small_world):
     for j in range(4):
         ro = o.align(xy, hyp[bi[j]].astype(np.float64))
         assert_results_match(np.array([res[j]]), np.array([ro]))
+        assert res[j].tobytes() == ro.tobytes()          # the k refinements are ordinary aligns, bit for bit
     best = res[np.argmax(res["score"])]
     dth = (best["pose"][2] - truth[2] + np.pi) % (2 * np.pi) - np.pi
     assert np.allclose(best["pose"][:2], truth[:2], atol=0.03) and abs(dth) < 3e-3
+    # more candidates asked for than there are hypotheses: the surplus entries are empty
+    bi2, res2 = m.relocalize(xy, hyp[:3], k=5, level=0)
+    assert list(bi2[3:]) == [-1, -1] and np.all(res2["status"][3:] == 3) and np.all(res2["iterations"][3:] == 0)
+    assert all(res2[j].tobytes() == o.align(xy, hyp[bi2[j]].astype(np.float64)).tobytes() for j in range(3))
+    # the all-device form (ndt2d_relocalize_device): same indices and records, one stream, no host round trip in between
+    import torch
+    g, _ = mods
+    dev = torch.device("cuda", 0)
+    d_xy, d_hyp = torch.from_numpy(xy).to(dev), torch.from_numpy(hyp).to(dev)
+    d_idx = torch.zeros(4, dtype=torch.int64, device=dev)
+    d_res = torch.zeros(4 * 144, dtype=torch.uint8, device=dev)
+    m.relocalize_device(d_xy, len(xy), d_hyp, len(hyp), 4, d_idx, d_res, level=0)
+    m.synchronize()
+    assert np.array_equal(d_idx.cpu().numpy(), bi)
+    assert d_res.cpu().numpy().tobytes() == res.tobytes()
 
 
 def test_set_cells_roundtrip(mods, small_world):
