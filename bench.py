@@ -23,6 +23,7 @@ The default run (`--workload scan2map`, what the driver launches at N = 1, 2, 4,
             with cross-shard ties are checked against the unsharded sweep on every rank - a mismatch makes the bench exit 3
   pyramid   configs[2]: 2.0/1.0/0.5 m pyramid, 10 000 scans in total sharded over the ranks, prior error 0.2 m / 3 deg
   prior2    configs[1] again with the 0.2 m / 3 deg prior (matches/s depends on the prior through the iteration count)
+  odometry  batched scan-to-scan (ndt2d_align_pairs): 16 384 consecutive scans per GPU, pair k = (scan k-1 -> scan k), 0.5 m cells
   dense     configs[1] in a cluttered world whose map has > 300 k valid cells (the default room has 14 k)
   config0   configs[0]: one 360-beam scan-to-scan align at 0.5 m cells, CPU oracle on one thread vs ndt2d_align latency
   precision distance of the GPU results from an independent f64 NDT (oracle/f64ref.py) at north_star's tolerances
@@ -71,7 +72,7 @@ def parse_args():
     ap.add_argument("--ref-scans", type=int, default=0, help="scans per step of the reference arm (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--legs", default="all", help="scan2map only: extra legs in the same JSON line: all | none | comma list of "
-                                                  "sweep,pyramid,prior2,dense,config0,precision")
+                                                  "sweep,pyramid,prior2,odometry,dense,config0,precision")
     ap.add_argument("--world", default="room", choices=["room", "dense"],
                     help="synthetic world of the scan2map workload: the SURVEY 8(d) room (14 k valid map cells) or the cluttered dense world (> 300 k)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the NUMA node of its GPU")
@@ -84,7 +85,7 @@ def parse_args():
         a.steps = 50 if a.workload == "sweep" else 10
     a.res = a.res or dflt[1]
     a.perturb = a.perturb or dflt[2]
-    legs = ["sweep", "pyramid", "prior2", "dense", "config0", "precision"]
+    legs = ["sweep", "pyramid", "prior2", "odometry", "dense", "config0", "precision"]
     a.legs = legs if a.legs == "all" else [] if a.legs == "none" else [x for x in a.legs.split(",") if x]
     if a.workload != "scan2map" or a.overlap or a.world != "room" or a.res != [0.25]:
         a.legs = []          # the legs belong to the default configuration
@@ -599,6 +600,10 @@ def run_native(args):
         leg = leg_pyramid(ctx, args, map_xy)
         if rank == 0:
             line["pyramid"] = leg
+    if "odometry" in args.legs:
+        leg = leg_odometry(ctx, args)
+        if rank == 0:
+            line["odometry"] = leg
     if "sweep" in args.legs:
         leg = leg_sweep(ctx, args, m)
         failed = failed or not leg.get("ok", True)
@@ -695,6 +700,47 @@ def leg_pyramid(ctx, args, map_xy):
             "l2": "steps alternate between two copies of the scans (2 x %.0f MB)" % (xy.nbytes / 1e6),
             "e2e": {"value": total * args.steps / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(ranges.nbytes + init.nbytes),
                     "d2h_bytes_per_step": int(n * 144), "api": "ndt2d_align_batch_ranges", "equals_device_run": same}}
+
+
+def leg_odometry(ctx, args):
+    """Batched scan-to-scan (ndt2d_align_pairs, the fused shared-memory path): 16 384 consecutive 1080-beam scans per GPU, 0.1 m
+    apart, pair k = (scan k-1 as target, scan k as source), 0.5 m cells (configs[0]'s align, batched), prior error 2 cm / 0.2 deg."""
+    import gtsam_ndt_b200 as g
+    from gtsam_ndt_b200 import synth
+    torch = ctx.torch
+    sc = synth.SCAN_1080
+    n = 16384
+    ranges, poses = synth.scans(n, traj_len=3770, first=ctx.rank * 911, step=1, **sc)
+    xy, offsets = to_points(ranges)
+    pairs = np.stack([np.arange(n - 1), np.arange(1, n)], 1).astype(np.int32)
+    c, s_ = np.cos(poses[:-1, 2]), np.sin(poses[:-1, 2])
+    d = poses[1:] - poses[:-1]
+    rel = np.stack([c * d[:, 0] + s_ * d[:, 1], -s_ * d[:, 0] + c * d[:, 1], d[:, 2]], 1)
+    init = rel + synth.uniform3(n - 1, first=ctx.rank * n + 99) * np.array([0.02, 0.02, math.radians(0.2)])
+    m = g.NdtMatcher2D([0.5], device=ctx.local, stream=ctx.stream.cuda_stream)
+    d_xy, d_off = torch.from_numpy(xy).to(ctx.dev), torch.from_numpy(offsets).to(ctx.dev)
+    d_init = torch.from_numpy(np.ascontiguousarray(init)).to(ctx.dev)
+    d_res = torch.zeros((n - 1) * 144, dtype=torch.uint8, device=ctx.dev)
+    l0 = m.kernel_launches
+    ms = ctx.timed(lambda: m.align_pairs_device(d_xy, d_off, offsets, pairs, d_init, d_res), args.steps, 3)
+    launches = (m.kernel_launches - l0) * args.steps // (args.steps + 3)
+    res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=g.RESULT_DTYPE)
+    # the same pairs one at a time through set_target + align (what a front end without the batched call does): must be identical
+    scans_list = xy.reshape(n, -1, 2)
+    same = True
+    for p in range(0, 64):
+        m.set_target(scans_list[pairs[p, 0]])
+        same = same and m.align(scans_list[pairs[p, 1]], init[p]).tobytes() == res[p].tobytes()
+    (ms,) = ctx.max_over_ranks(ms)
+    npairs, evals, conv, agree = ctx.sum_over_ranks(n - 1, float(res["iterations"].sum()), float((res["status"] == 0).sum()), 1.0 if same else 0.0)
+    err = np.abs(res["pose"] - rel)
+    m.close()
+    return {"workload": "batched scan-to-scan odometry: %d consecutive 1080-beam scans per GPU, pair k = (scan k-1 -> scan k), 0.5 m cells (K=1), prior error 0.02 m / 0.2 deg" % n,
+            "value": npairs * args.steps / (ms / 1e3), "unit": UNIT, "scaling": "weak", "ms_per_step": ms / args.steps, "mean_iterations": evals / npairs,
+            "converged_frac": conv / npairs, "median_abs_err_vs_truth_m": float(np.median(err[:, :2])), "gpu_launches": int(launches),
+            "first_64_pairs_equal_set_target_plus_align": bool(agree == ctx.world),
+            "l2": "per-step scan input %.0f MB > 126 MB L2; every target's grid lives in the building warp's shared memory" % (xy.nbytes / 1e6),
+            "kernel": "k_pairs_fused (one warp per pair: radix-sorted cell build in shared memory + LM loop)"}
 
 
 def sweep_lattice(hyps, centre):

@@ -211,7 +211,6 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
     const unsigned lt = (1u << lane) - 1u;
     unsigned short *perm[2] = {reinterpret_cast<unsigned short *>(keyof + cap_t), reinterpret_cast<unsigned short *>(keyof + cap_t) + cap_t + 2};
     unsigned *hist = reinterpret_cast<unsigned *>(rec);     // 256 counters; the record area is not in use during the sort
-    for (unsigned s = lane; s < hslots; s += 32) hidx[s] = 0xffffffffu;
     const unsigned ncells = (unsigned)L.njx * (unsigned)L.njy;
     // (1) keys; four windows of points are requested at a time (a warp has no other latency hiding here)
     int m = 0;
@@ -236,8 +235,8 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
     }
     __syncwarp();
     if (m == 0) {
-        __syncwarp();
-        if (lane < 6) rec[lane] = lane == 5 ? __int_as_float(-1) : 0.0f;      // no records: only the zero record
+        for (unsigned s = lane; s < hslots; s += 32) hidx[s] = 0xffffffffu;
+        if (lane < 6) rec[lane] = lane == 5 ? __int_as_float(-1) : 0.0f;      // no records: an empty index and the zero record
         __syncwarp();
         return 0;
     }
@@ -292,14 +291,25 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
     }
     if (lane == 0) hpos[nruns] = (unsigned short)m;
     __syncwarp();
-    // (4) one lane per cell
-    const unsigned bmask = hslots / 4u - 1u;
-    int nrec = 0;
+    // the cells with at least min_points points, compacted (start | length << 16): the index area is free until (4b)
+    int nvalid = 0;
     for (int base = 0; base < nruns; base += 32) {
         const int r = base + lane;
         const int start = r < nruns ? (int)hpos[r] : 0;
         const int len = r < nruns ? (int)hpos[r + 1] - start : 0;
         const bool ok = len >= min_points;
+        const unsigned mask = __ballot_sync(FULL_MASK, ok);
+        if (ok) hidx[nvalid + __popc(mask & lt)] = (unsigned)start | ((unsigned)len << 16);
+        nvalid += __popc(mask);
+    }
+    __syncwarp();
+    // (4a) one lane per cell: integer sums over its points, finalisation, record
+    int nrec = 0;
+    for (int base = 0; base < nvalid; base += 32) {
+        const int v = base + lane;
+        const bool ok = v < nvalid;
+        const unsigned sl = ok ? hidx[v] : 0u;
+        const int start = (int)(sl & 0xffffu), len = (int)(sl >> 16);
         unsigned kr = 0u;
         float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
         if (ok) {
@@ -330,10 +340,19 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
             float *o = rec + 6 * (size_t)id;                 // {mux, muy, B00, B01, B11, key}
             o[0] = ra.x; o[1] = ra.y; o[2] = ra.z; o[3] = ra.w; o[4] = rb.y; o[5] = __int_as_float((int)kr);
         }
-        // index insertion (lookup_shared in ndt2d_device.cuh): every pending lane counts the used entries of its bucket; the
-        // lanes of this round that want the same bucket take its free entries in lane order, the rest move on by one bucket
+        nrec += __popc(mask);
+    }
+    __syncwarp();
+    // (4b) the bucket index (lookup_shared in ndt2d_device.cuh): every pending lane counts the used entries of its bucket; the
+    // lanes of a round that want the same bucket take its free entries in lane order, the rest move on by one bucket
+    for (unsigned s = lane; s < hslots; s += 32) hidx[s] = 0xffffffffu;
+    __syncwarp();
+    const unsigned bmask = hslots / 4u - 1u;
+    for (int base = 0; base < nrec; base += 32) {
+        const unsigned id = (unsigned)(base + lane);
+        bool pending = id < (unsigned)nrec;
+        const unsigned kr = pending ? (unsigned)__float_as_int(rec[6 * (size_t)id + 5]) : 0u;
         unsigned b = hash_slot(kr, bmask);
-        bool pending = keep;
         while (__any_sync(FULL_MASK, pending)) {
             unsigned used = 0u;
             if (pending) {
@@ -349,7 +368,6 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
             if (win) pending = false;
             else if (pending) b = (b + 1u) & bmask;
         }
-        nrec += __popc(mask);
     }
     // the all-zero record behind the compact array: what a failed lookup loads (finite factors, valid = 0)
     if (lane < 6) rec[6 * (size_t)nrec + lane] = lane == 5 ? __int_as_float(-1) : 0.0f;
