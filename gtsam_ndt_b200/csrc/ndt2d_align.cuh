@@ -5,12 +5,10 @@
 #include "ndt2d_device.cuh"
 
 #ifndef NDT2D_EVAL_INLINE
-#define NDT2D_EVAL_INLINE 1 // 1: the evaluation is inlined into the LM loop (r2g: 18.70 vs 18.17 M matches/s, no spills at 80 registers, both gathers of a step issue back to back); 0: a separate function (the round-1 default)
-#endif
-#if NDT2D_EVAL_INLINE
-#define NDT2D_EVAL_ATTR __forceinline__
-#else
-#define NDT2D_EVAL_ATTR __noinline__
+#define NDT2D_EVAL_INLINE 1 // 1: k_align inlines the evaluation into the LM loop (r2g: 18.70 vs 18.17 M matches/s - no spills at
+                            // 80 registers and both gathers of a step issue back to back); 0: a separate function, the round-1
+                            // form. The fused pairs kernel always calls it as a function: inlined, its code outgrows the
+                            // instruction cache (r2h: 9.7 vs 10.8 M pairs/s).
 #endif
 #ifndef NDT2D_PIPE
 #define NDT2D_PIPE 0      // align kernel: 1 = register software pipeline (K = 1)
@@ -39,9 +37,9 @@ struct WarpState {
 };
 
 // One SPEC 4 evaluation at ws->p (trial == 0, result to ws->v) or ws->pn (trial != 0, result to ws->t); lane t stores
-// sum t. Deliberately not inlined: the point loop gets its own register allocation, independent of the f64 solver.
+// sum t.
 template <int OV, bool STAGED, int TABLE>
-__device__ NDT2D_EVAL_ATTR void eval_to_smem(const LevelDev *L, const float2 *pts, int n, WarpState *ws, int trial)
+__device__ __forceinline__ void eval_to_smem_body(const LevelDev *L, const float2 *pts, int n, WarpState *ws, int trial)
 {
     const int lane = threadIdx.x & 31;
     const double *pose = trial ? ws->pn : ws->p;
@@ -52,6 +50,18 @@ __device__ NDT2D_EVAL_ATTR void eval_to_smem(const LevelDev *L, const float2 *pt
     out[E.slot] = E.v[0]; // lanes holding the same sum store the same bits
     if (lane == 0) *(trial ? &ws->tcount : &ws->count) = E.count;
     __syncwarp();
+}
+// ... as a function of its own (the point loop then gets a register allocation independent of the f64 solver)
+template <int OV, bool STAGED, int TABLE>
+__device__ __noinline__ void eval_to_smem_call(const LevelDev *L, const float2 *pts, int n, WarpState *ws, int trial)
+{
+    eval_to_smem_body<OV, STAGED, TABLE>(L, pts, n, ws, trial);
+}
+template <int OV, bool STAGED, int TABLE>
+__device__ __forceinline__ void eval_to_smem(const LevelDev *L, const float2 *pts, int n, WarpState *ws, int trial)
+{
+    if (NDT2D_EVAL_INLINE && TABLE != TABLE_SHASH) eval_to_smem_body<OV, STAGED, TABLE>(L, pts, n, ws, trial);
+    else eval_to_smem_call<OV, STAGED, TABLE>(L, pts, n, ws, trial);
 }
 
 // The threads that share one WarpState: a warp (k_align) or a whole block (k_align_block)
