@@ -284,6 +284,8 @@ class Ctx:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         self.affinity0 = sorted(os.sched_getaffinity(0))
+        from gtsam_ndt_b200 import synth
+        synth.set_threads(max(1, len(self.affinity0) // self.world))   # torchrun exports OMP_NUM_THREADS=1: take this rank's share
         self.numa = {"bound": False, "note": "--no-numa"} if args.no_numa else bind_to_gpu_numa(self.local)
         if self.world > 1:
             # stdout carries exactly one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO is set, so

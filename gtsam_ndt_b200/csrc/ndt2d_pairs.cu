@@ -214,6 +214,7 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
     const unsigned ncells = (unsigned)L.njx * (unsigned)L.njy;
     // (1) keys; four windows of points are requested at a time (a warp has no other latency hiding here)
     int m = 0;
+#pragma unroll 1
     for (int base = 0; base < n; base += 128) {
         float2 pw[4];
 #pragma unroll
@@ -243,9 +244,11 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
     // (2) radix sort of the indices by key (keys 0 .. ncells)
     const int nbits = 32 - __clz(ncells);
     int cur = 0;
+#pragma unroll 1
     for (int shift = 0; shift < nbits; shift += 8) {
         for (int b = lane; b < 256; b += 32) hist[b] = 0u;
         __syncwarp();
+#pragma unroll 2
         for (int i = lane; i < n; i += 32) atomicAdd(&hist[(keyof[perm[cur][i]] >> shift) & 255u], 1u);
         __syncwarp();
         unsigned c[8], sum = 0u;
@@ -262,6 +265,7 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
 #pragma unroll
         for (int j = 0; j < 8; ++j) { hist[8 * lane + j] = run; run += c[j]; }
         __syncwarp();
+#pragma unroll 1
         for (int base = 0; base < n; base += 32) {      // windows in order: the scatter is stable
             const int i = base + lane;
             const bool valid = i < n;
@@ -282,6 +286,7 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
     const unsigned short *order = perm[cur];
     unsigned short *hpos = perm[cur ^ 1];
     int nruns = 0;
+#pragma unroll 1
     for (int base = 0; base < m; base += 32) {
         const int i = base + lane;
         const bool head = i < m && (i == 0 || keyof[order[i]] != keyof[order[i - 1]]);
@@ -293,6 +298,7 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
     __syncwarp();
     // the cells with at least min_points points, compacted (start | length << 16): the index area is free until (4b)
     int nvalid = 0;
+#pragma unroll 1
     for (int base = 0; base < nruns; base += 32) {
         const int r = base + lane;
         const int start = r < nruns ? (int)hpos[r] : 0;
@@ -305,6 +311,7 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
     __syncwarp();
     // (4a) one lane per cell: integer sums over its points, finalisation, record
     int nrec = 0;
+#pragma unroll 1
     for (int base = 0; base < nvalid; base += 32) {
         const int v = base + lane;
         const bool ok = v < nvalid;
@@ -318,6 +325,7 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
             const double cx = (double)L.ox + ((double)(jx - L.ov)) * (double)L.st + 0.5 * (double)L.res;
             const double cy = (double)L.oy + ((double)(jy - L.ov)) * (double)L.st + 0.5 * (double)L.res;
             long long s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+#pragma unroll 1
             for (int p = start; p < start + len; p += 4) {      // four independent loads per trip (L2 round trips overlap)
                 float2 pt[4];
 #pragma unroll
@@ -348,6 +356,7 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
     for (unsigned s = lane; s < hslots; s += 32) hidx[s] = 0xffffffffu;
     __syncwarp();
     const unsigned bmask = hslots / 4u - 1u;
+#pragma unroll 1
     for (int base = 0; base < nrec; base += 32) {
         const unsigned id = (unsigned)(base + lane);
         bool pending = id < (unsigned)nrec;

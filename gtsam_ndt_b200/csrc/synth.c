@@ -15,6 +15,9 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define SYNTH_MAX_BOXES 32768
 #define WALL 95.0
@@ -37,6 +40,17 @@ typedef struct {
  * defaults are the SURVEY 8(d) room (about 230 boxes survive of 400 candidates: 14 k occupied 0.25 m cells); the "dense"
  * world of bench.py (--world dense) uses many small boxes so that a third of the 640 k map cells are occupied. */
 static double g_hmin = 1.0, g_hspan = 3.0, g_clear = 3.0;
+/* threads of the ray-casting loops (torchrun exports OMP_NUM_THREADS=1 to every rank: the benchmark sets its share of the
+ * host cores explicitly); n <= 0 leaves the OpenMP default */
+void synth_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 void synth_set_world(double h_min, double h_span, double clear)
 {
     g_hmin = h_min; g_hspan = h_span; g_clear = clear;

@@ -60,6 +60,11 @@ def boxes(seed=WORLD_SEED, nboxes=NBOXES):
 DENSE_NBOXES = 30000
 
 
+def set_threads(n):
+    """OpenMP threads of the generator (torchrun sets OMP_NUM_THREADS=1 for every rank; a bench rank takes its share of the cores)."""
+    lib().synth_set_threads(C.c_int(int(n)))
+
+
 def set_world(dense=False):
     """Box shape of the synthetic world for every later call: the SURVEY 8(d) room (default), or the cluttered "dense"
     world (pass nboxes=DENSE_NBOXES to scans / boxes): ~17 000 boxes of 0.6-2 m, 1.5 m clear of the trajectory."""
