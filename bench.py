@@ -782,7 +782,12 @@ def leg_sweep(ctx, args, m):
 
     # ---- (1) peer-memory combine
     LAG, NSLOTS = 8, 64
-    ex = D.PeerExchange(m, nslots=NSLOTS)
+    try:
+        ex = D.PeerExchange(m, nslots=NSLOTS)
+    except Exception as e:      # CUDA IPC not permitted on this box: say so, the leg fails (rc 3) but the headline line is printed
+        print(f"[bench] rank {rank}: peer-memory exchange unavailable: {e}", file=sys.stderr, flush=True)
+        out.update({"ok": False, "error": f"peer-memory exchange unavailable: {e}"})
+        return out
     st = {"i": 0, "waited": 0, "best": None}
 
     def step_p2p():
