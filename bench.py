@@ -892,12 +892,37 @@ def leg_sweep(ctx, args, m):
     (reloc_ms,) = ctx.max_over_ranks(reloc_ms)
     bi1, res1 = m.relocalize(xy, hyp, k=k)                   # the single-GPU call on this rank's GPU
     same = bool(np.array_equal(reloc[0], bi1) and reloc[1].tobytes() == res1.tobytes())
-    (agree,) = ctx.sum_over_ranks(1.0 if same else 0.0)
+    # the same through peer memory: every rank refines its own k best and stores the candidates into every rank's table;
+    # one exchange per query, no collective, hypotheses resident on the device (ndt2d_relocalize_publish / _wait)
+    pr = D.PeerRelocalizer(m, nslots=16, kmax=k)
+    qn = {"q": 0}
+
+    def reloc_peer():
+        pr.publish(d_xy, len(xy), d_hyps[0], hi - lo, lo, k, qn["q"])
+        r = pr.wait(qn["q"], k)
+        qn["q"] += 1
+        return r
+
+    peer = reloc_peer()
+    ctx.sync_all()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        peer = reloc_peer()
+    peer_ms = (time.perf_counter() - t0) * 1e3 / reps
+    ctx.sync_all()
+    pr.close()
+    (peer_ms,) = ctx.max_over_ranks(peer_ms)
+    same_peer = bool(np.array_equal(peer[0], bi1) and peer[1].tobytes() == res1.tobytes())
+    agree, agree_peer = ctx.sum_over_ranks(1.0 if same else 0.0, 1.0 if same_peer else 0.0)
     best = reloc[1][np.lexsort((np.arange(k), -reloc[1]["score"]))[0]]
-    out["relocalize"] = {"ms_per_query": reloc_ms, "k": k, "api": "distributed.relocalize_sharded: ndt2d_sweep (shard, top-k) + combine_topk + ndt2d_align_batch (shard of the k candidates)",
-                         "equals_single_gpu_relocalize": bool(agree == world),
+    out["relocalize"] = {"ms_per_query": peer_ms, "k": k,
+                         "api": "ndt2d_relocalize_publish + ndt2d_relocalize_wait: shard sweep, its top-k and their refinement queued on the device, candidates stored into every rank's table over NVLink, local merge",
+                         "equals_single_gpu_relocalize": bool(agree_peer == world),
+                         "host_combine": {"ms_per_query": reloc_ms, "api": "distributed.relocalize_sharded: ndt2d_sweep from host hypotheses + torch.distributed all-gather of the top-k + ndt2d_align_batch of a share of the candidates + all-gather of the records",
+                                          "equals_single_gpu_relocalize": bool(agree == world)},
                          "best_pose_abs_err_vs_truth": [float(v) for v in np.abs(best["pose"] - poses[0])]}
     out["ok"] = bool(out["combine_equals_host_api_result"] and bad_total == 0 and out["relocalize"]["equals_single_gpu_relocalize"]
+                     and out["relocalize"]["host_combine"]["equals_single_gpu_relocalize"]
                      and out.get("nccl", {}).get("equals_p2p_result", True))
     ex.close()
     return out

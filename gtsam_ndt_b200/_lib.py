@@ -68,6 +68,11 @@ SIGNATURES = {
     "ndt2d_sweep_publish": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, C.c_int64, _V, C.c_int64, C.c_uint64]),
     "ndt2d_exchange_wait": (C.c_int, [_V, C.c_uint64, C.c_int, c_i64p, c_f64p]),
     "ndt2d_exchange_close": (C.c_int, [_V]),
+    "ndt2d_reloc_create": (C.c_int, [_V, C.c_int, C.c_int, C.c_int, C.c_int, _V]),
+    "ndt2d_reloc_open": (C.c_int, [_V, _V]),
+    "ndt2d_relocalize_publish": (C.c_int, [_V, C.c_int, _V, C.c_int, _V, C.c_int64, C.c_int64, C.c_int, C.c_uint64]),
+    "ndt2d_relocalize_wait": (C.c_int, [_V, C.c_uint64, C.c_int, C.c_int, _V, _V]),
+    "ndt2d_reloc_close": (C.c_int, [_V]),
     "ndt2d_host_alloc": (C.c_int, [C.POINTER(_V), C.c_size_t]),
     "ndt2d_host_free": (C.c_int, [_V]),
 }

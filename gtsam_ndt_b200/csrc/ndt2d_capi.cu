@@ -299,6 +299,7 @@ void ndt2d_destroy(ndt2d_matcher *m)
     cudaStreamSynchronize(m->cfg.stream);
     drop_target(m);
     ndt2d_exchange_close(m);
+    ndt2d_reloc_close(m);
     if (m->fast_host) cudaFreeHost(m->fast_host);
     if (m->fast_res) cudaFreeHost(m->fast_res);
     m->b_fast.release();

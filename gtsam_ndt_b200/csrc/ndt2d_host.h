@@ -39,6 +39,20 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// A table every rank owns a copy of and every rank writes into, through CUDA IPC peer pointers, from inside a kernel:
+// nslots rows of `world` blocks of block_bytes, block r of row (query % nslots) written by rank r. The first 32 bytes of a
+// block are an ndt2d_best-shaped header whose epoch word (offset 16) = query + 1 is stored last, after a system-scope
+// fence. Reading is a host-side poll of the OWN table (see peer_wait_row in ndt2d_exchange.cu).
+struct PeerTable {
+    int world = 0, rank = 0, slots = 0;
+    size_t block_bytes = 0;
+    unsigned char *table[NDT2D_MAX_RANKS] = {};
+    bool opened[NDT2D_MAX_RANKS] = {};
+    unsigned char *host = nullptr;      // pinned: the polled row, then a verified snapshot of the whole table
+    std::vector<char> verified_ok;      // per row: the snapshot holds a verified, complete row
+    size_t row_bytes() const { return (size_t)world * block_bytes; }
+};
+
 struct LevelMem {
     float4 *cells = nullptr;
     uint32_t *cnt = nullptr;
@@ -99,12 +113,10 @@ struct ndt2d_matcher {
     cudaStream_t work_stream[2] = {nullptr, nullptr}; // chunk kernels alternate so one chunk's tail overlaps the next
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
     cudaEvent_t ev_begin = nullptr, ev_done[2] = {nullptr, nullptr};
-    // multi-GPU best-hypothesis exchange (ndt2d_exchange_*): own table, the peers' tables opened through CUDA IPC
-    int ex_world = 0, ex_rank = 0, ex_slots = 0;
-    ndt2d_best *ex_table[NDT2D_MAX_RANKS] = {};
-    bool ex_opened[NDT2D_MAX_RANKS] = {};
-    ndt2d_best *ex_host = nullptr; // pinned staging for the host-side poll: two snapshots of the whole table
-    std::vector<char> ex_verified_ok; // per row: the second snapshot holds a verified, complete row
+    // multi-GPU exchanges over peer memory: the best hypothesis of a sharded sweep (ndt2d_exchange_*) and the refined
+    // candidates of a sharded relocalisation (ndt2d_reloc_*)
+    ndt2d::PeerTable ex, rx;
+    int rx_k = 0;                   // candidates per rank and query in `rx`
     int chunk_scans = 0; // NDT2D_CHUNK_SCANS override; 0 = choose by bytes (plan_chunks)
     // low-latency path of small host-buffer calls (a single align is 3 CUDA calls): pinned staging for one packed upload,
     // results written by the kernel straight into mapped pinned memory, work-queue counters from a pre-zeroed ring

@@ -127,6 +127,16 @@ struct PublishArgs {
     unsigned long long epoch;           // query + 1
 };
 
+// Publication of a shard's k refined relocalisation candidates into every rank's table (ndt2d_relocalize_publish)
+struct CandidatePublishArgs {
+    ndt2d_candidate *table[NDT2D_MAX_RANKS]; // table[r] = this rank's block of the query's row in rank r's table
+    int world, k;
+    long long index_offset;
+    unsigned long long epoch;           // query + 1
+};
+cudaError_t launch_publish_candidates(const LaunchCfg &c, const int64_t *d_best_idx, const double *d_best_score, const ndt2d_result *d_res,
+                                      const CandidatePublishArgs &pub, int64_t *launches);
+
 // top-k of scores by (-score, index); k small. d_work: nhyp bytes of scratch (mask). pub (optional, k == 1): the
 // finishing block also stores the winner into the peers' exchange tables.
 cudaError_t launch_topk(const LaunchCfg &c, const double *d_scores, int64_t nhyp, int k, int64_t *d_idx, double *d_val,

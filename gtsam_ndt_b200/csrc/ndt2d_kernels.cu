@@ -671,6 +671,37 @@ cudaError_t launch_topk(const LaunchCfg &c, const double *d_scores, int64_t nhyp
 
 int topk_scratch_words(int sm_count) { return 1 + 2 * sm_count * 4; }
 
+// One block: thread (r, j) builds candidate j - global index, sweep score, refined record - and stores it into rank r's table
+// (NVLink peer stores, or local for the own rank); after every thread's system-scope fence and a block barrier, thread r
+// stores the epoch of its rank's block: a reader that sees the epoch sees the k candidates.
+__global__ void __launch_bounds__(256) k_publish_candidates(const int64_t *__restrict__ best_idx, const double *__restrict__ best_score,
+                                                            const ndt2d_result *__restrict__ res, const CandidatePublishArgs pub)
+{
+    for (int t = threadIdx.x; t < pub.world * pub.k; t += blockDim.x) {
+        const int r = t / pub.k, j = t % pub.k;
+        ndt2d_candidate *dst = pub.table[r] + j;
+        const long long i = best_idx[j];
+        dst->index = i >= 0 ? i + pub.index_offset : -1;
+        dst->sweep_score = i >= 0 ? best_score[j] : 0.0;
+        dst->reserved = 0ull;
+        dst->refined = res[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pub.world) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(&pub.table[threadIdx.x]->epoch) = pub.epoch;
+    }
+}
+
+cudaError_t launch_publish_candidates(const LaunchCfg &c, const int64_t *d_best_idx, const double *d_best_score, const ndt2d_result *d_res,
+                                      const CandidatePublishArgs &pub, int64_t *launches)
+{
+    k_publish_candidates<<<1, 256, 0, c.stream>>>(d_best_idx, d_best_score, d_res, pub);
+    ++*launches;
+    return cudaGetLastError();
+}
+
 __global__ void k_topk_to_jobs(const float *__restrict__ hyp, const int64_t *__restrict__ best_idx, int k, double *__restrict__ init,
                                int32_t *__restrict__ job_scan)
 {

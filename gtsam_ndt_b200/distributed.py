@@ -152,6 +152,33 @@ class PeerExchange:
         self.m.exchange_close()
 
 
+class PeerRelocalizer:
+    """Multi-GPU relocalisation end to end through peer memory (include/ndt2d.h, ndt2d_reloc_* / ndt2d_relocalize_*): every
+    rank sweeps its shard, refines its own k best and stores the k candidates into every rank's table; the global top-k
+    with its refined records is a local merge - one exchange per query, no collective. torch.distributed is used once,
+    to hand the CUDA IPC handles round."""
+
+    def __init__(self, matcher, nslots=16, kmax=8):
+        self.m = matcher
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        matcher.reloc_open(all_gather_blobs(matcher.reloc_create(self.world, self.rank, nslots, kmax)))
+        if self.world > 1:
+            dist.barrier()
+
+    def publish(self, d_xy, n, d_hyp_shard, nhyp_shard, index_offset, k, query, level=0):
+        self.m.relocalize_publish(d_xy, n, d_hyp_shard, nhyp_shard, index_offset, k, query, level)
+
+    def wait(self, query, k, timeout_ms=10000):
+        return self.m.relocalize_wait(query, k, timeout_ms)
+
+    def close(self):
+        self.m.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        self.m.reloc_close()
+
+
 def align_sharded_counts(nscans):
     """[lo, hi) of this rank's scans for a batched align; results stay on the rank that computed them."""
     rank = dist.get_rank() if dist.is_initialized() else 0

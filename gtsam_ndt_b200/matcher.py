@@ -296,6 +296,30 @@ class NdtMatcher2D:
     def exchange_close(self):
         self._ck(self._L.ndt2d_exchange_close(self._h))
 
+    # ---- multi-GPU relocalisation over peer memory (one process per GPU; distributed.PeerRelocalizer wraps these) ----
+    def reloc_create(self, world, rank, nslots=16, kmax=8):
+        h = (C.c_ubyte * 64)()
+        self._ck(self._L.ndt2d_reloc_create(self._h, world, rank, nslots, kmax, C.cast(h, C.c_void_p)))
+        return bytes(h)
+
+    def reloc_open(self, handles):
+        buf = np.frombuffer(b"".join(handles) if isinstance(handles, (list, tuple)) else bytes(handles), np.uint8).copy()
+        self._ck(self._L.ndt2d_reloc_open(self._h, _ptr(buf)))
+
+    def relocalize_publish(self, d_xy, n, d_hyp, nhyp, index_offset, k, query, level=0):
+        """Sweep this rank's shard, refine its k best and store the k candidates into every rank's table (asynchronous)."""
+        self._ck(self._L.ndt2d_relocalize_publish(self._h, level, _ptr(d_xy), n, _ptr(d_hyp), nhyp, index_offset, k, query))
+
+    def relocalize_wait(self, query, k, timeout_ms=10000):
+        """Global (idx[k], res[k]) of `query` once every rank has published: what relocalize() returns on one GPU."""
+        bi = np.full(k, -1, np.int64)
+        res = np.zeros(k, RESULT_DTYPE)
+        self._ck(self._L.ndt2d_relocalize_wait(self._h, query, timeout_ms, k, _ptr(bi), _ptr(res)))
+        return bi, res
+
+    def reloc_close(self):
+        self._ck(self._L.ndt2d_reloc_close(self._h))
+
     def relocalize_device(self, d_xy, n, d_hyp, nhyp, k, d_best_idx, d_res, level=0):
         """Sweep + top-k + k refinements, everything on the device, asynchronous (ndt2d_relocalize_device)."""
         self._ck(self._L.ndt2d_relocalize_device(self._h, level, _ptr(d_xy), n, _ptr(d_hyp), nhyp, k, _ptr(d_best_idx), _ptr(d_res)))

@@ -229,6 +229,29 @@ int ndt2d_exchange_wait(ndt2d_matcher *m, uint64_t query, int timeout_ms, int64_
 /* frees the own table and closes the peers'. Synchronise the ranks first: a peer must not publish afterwards. */
 int ndt2d_exchange_close(ndt2d_matcher *m);
 
+/* ---- multi-GPU relocalisation end to end over peer memory ---------------------------------------------------------
+ * Every rank sweeps its shard of the hypotheses, refines ITS OWN k best (sweep, top-k and the k aligns are queued on the
+ * stream: ndt2d_relocalize_device) and stores the k candidates {global index, sweep score, refined record} into every
+ * rank's table with one more small kernel. Every member of the global top-k is among its own shard's k best, so the
+ * global answer - what ndt2d_relocalize returns on one GPU for the whole hypothesis set, bit for bit - is a local merge of
+ * the world x k candidates: ONE exchange per query and no collective. Slots, handles and the wait follow the
+ * best-hypothesis exchange above (same slot discipline). */
+typedef struct ndt2d_candidate {
+    int64_t index;          /* global hypothesis index, -1: the shard had fewer than k hypotheses */
+    double sweep_score;
+    uint64_t epoch;         /* of candidate 0 of a rank's block: query + 1, written last */
+    uint64_t reserved;
+    ndt2d_result refined;   /* the full align from that hypothesis */
+} ndt2d_candidate;
+int ndt2d_reloc_create(ndt2d_matcher *m, int world, int rank, int nslots, int kmax, unsigned char *handle);
+int ndt2d_reloc_open(ndt2d_matcher *m, const unsigned char *handles);
+/* asynchronous; hypothesis j of the shard has global index index_offset + j; 1 <= k <= kmax */
+int ndt2d_relocalize_publish(ndt2d_matcher *m, int level, const float *d_xy, int n, const float *d_hyp, int64_t nhyp,
+                             int64_t index_offset, int k, uint64_t query);
+/* blocks until every rank has published `query`; best_idx[k], res[k] ordered like ndt2d_relocalize's */
+int ndt2d_relocalize_wait(ndt2d_matcher *m, uint64_t query, int timeout_ms, int k, int64_t *best_idx, ndt2d_result *res);
+int ndt2d_reloc_close(ndt2d_matcher *m);
+
 /* ---- pinned host memory for callers that want full-speed copies ------------------------------ */
 int ndt2d_host_alloc(void **p, size_t bytes);
 int ndt2d_host_free(void *p);

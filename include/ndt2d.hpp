@@ -212,6 +212,30 @@ class Matcher {
     }
     void exchangeClose() { ck(ndt2d_exchange_close(h_)); }
 
+    // multi-GPU relocalisation end to end over peer memory (ndt2d_reloc_* / ndt2d_relocalize_* in ndt2d.h): every rank
+    // sweeps its shard, refines its own k best and stores the candidates into every rank's table; relocalizeWait merges them
+    std::array<unsigned char, NDT2D_IPC_HANDLE_BYTES> relocCreate(int world, int rank, int nslots = 16, int kmax = 8)
+    {
+        std::array<unsigned char, NDT2D_IPC_HANDLE_BYTES> h{};
+        ck(ndt2d_reloc_create(h_, world, rank, nslots, kmax, h.data()));
+        return h;
+    }
+    void relocOpen(const std::vector<unsigned char> &handles_by_rank) { ck(ndt2d_reloc_open(h_, handles_by_rank.data())); }
+    void relocalizePublish(int level, const float *d_scan_xy, int n, const float *d_hyp_xyt, std::int64_t nhyp, std::int64_t index_offset, int k,
+                           std::uint64_t query)
+    {
+        ck(ndt2d_relocalize_publish(h_, level, d_scan_xy, n, d_hyp_xyt, nhyp, index_offset, k, query));
+    }
+    std::vector<Result> relocalizeWait(std::uint64_t query, int k, std::vector<std::int64_t> *indices = nullptr, int timeout_ms = 10000)
+    {
+        std::vector<std::int64_t> idx(static_cast<size_t>(k), -1);
+        std::vector<Result> res(static_cast<size_t>(k));
+        ck(ndt2d_relocalize_wait(h_, query, timeout_ms, k, idx.data(), res.data()));
+        if (indices) *indices = idx;
+        return res;
+    }
+    void relocClose() { ck(ndt2d_reloc_close(h_)); }
+
     ndt2d_matcher *handle() const { return h_; }
     void synchronize() { ck(ndt2d_synchronize(h_)); }
 

@@ -476,6 +476,21 @@ def test_relocalize_refines_topk(mods, small_world):
     m.synchronize()
     assert np.array_equal(d_idx.cpu().numpy(), bi)
     assert d_res.cpu().numpy().tobytes() == res.tobytes()
+    # the sharded form through the peer-memory candidate exchange, world = 1 here (2..8 ranks: tools/mgpu_exchange_check.py):
+    # publish (sweep + refinement of the shard's k best + stores into the table) and wait (merge) give the same answer;
+    # slots are reused by later queries
+    from gtsam_ndt_b200 import distributed as D
+    pr = D.PeerRelocalizer(m, nslots=2, kmax=4)
+    for q in range(5):
+        pr.publish(d_xy, len(xy), d_hyp, len(hyp), 0, 4, q)
+        gi, gr = pr.wait(q, 4)
+        assert np.array_equal(gi, bi) and gr.tobytes() == res.tobytes()
+    pr.publish(d_xy, len(xy), d_hyp, 2, 7, 3, 5)       # a 2-hypothesis shard at offset 7, k = 3
+    gi, gr = pr.wait(5, 3)
+    assert list(gi) == [int(b) + 7 for b in m.relocalize(xy, hyp[:2], k=3)[0][:2]] + [-1] and gr["status"][2] == 3
+    with pytest.raises(g.NdtError, match="kmax"):
+        pr.publish(d_xy, len(xy), d_hyp, len(hyp), 0, 5, 6)
+    pr.close()
 
 
 def test_set_cells_roundtrip(mods, small_world):

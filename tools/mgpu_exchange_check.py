@@ -78,6 +78,19 @@ def main():
         if not (np.array_equal(gi, si) and gr.tobytes() == sr.tobytes()):
             ok = False
             print(f"rank {rank}: relocalize_sharded(k={k}) differs from the single-GPU ndt2d_relocalize", flush=True)
+    # ... and the same through the peer-memory candidate exchange (one exchange per query, no collective), slots reused
+    pr = D.PeerRelocalizer(m, nslots=4, kmax=8)
+    lo, hi = D.shard_range(len(hyp), rank, world)
+    d_shard = torch.from_numpy(hyp[lo:hi].copy()).to(dev)
+    for q, k in enumerate((1, 3, 8, 8, 5, 8)):
+        pr.publish(d_xy, len(xy), d_shard, hi - lo, lo, k, q)
+        gi, gr = pr.wait(q, k, timeout_ms=20000)
+        si, sr = m.relocalize(xy, hyp, k=k)
+        if not (np.array_equal(gi, si) and gr.tobytes() == sr.tobytes()):
+            ok = False
+            print(f"rank {rank}: peer relocalisation (k={k}, query {q}) differs from the single-GPU ndt2d_relocalize", flush=True)
+        dist.barrier()      # nslots = 4: nobody runs more than a query ahead here
+    pr.close()
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     ex.close()
