@@ -75,6 +75,8 @@ def parse_args():
                                                   "sweep,pyramid,prior2,odometry,dense,config0,precision")
     ap.add_argument("--world", default="room", choices=["room", "dense"],
                     help="synthetic world of the scan2map workload: the SURVEY 8(d) room (14 k valid map cells) or the cluttered dense world (> 300 k)")
+    ap.add_argument("--pinned", default="default", choices=["default", "wc"],
+                    help="e2e input buffer: ordinary pinned memory, or write-combined pinned memory (ndt2d_host_alloc_flags)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the NUMA node of its GPU")
     a = ap.parse_args()
     dflt = {"scan2map": (65536, [0.25], [0.03, 0.3]), "pyramid": (10000, [2.0, 1.0, 0.5], [0.2, 3.0]), "sweep": (1, [0.25], [0.0, 0.0]),
@@ -505,19 +507,27 @@ def run_native(args):
     U16_SCALE = 0.004  # 4 mm quantisation, 262 m maximum range
     h2d_gbs = None
 
+    def pin(a):
+        """the step's input in pinned host memory: torch's allocator, or the library's write-combined one (--pinned wc)"""
+        if args.pinned == "wc":
+            w = g.pinned_array(a.shape, a.dtype, write_combined=True)
+            w[...] = a
+            return torch.from_numpy(w)
+        return torch.from_numpy(a).pin_memory()
+
     def e2e_run(mode):
         nonlocal h2d_gbs
         if mode == "xy":
-            h_in = torch.from_numpy(xy).pin_memory()
+            h_in = pin(xy)
             h_off = torch.from_numpy(offsets).pin_memory()
             nbytes = h_in.numel() * 4 + h_off.numel() * 8 + h_init.numel() * 8
             fn = lambda: m.align_batch(h_in.numpy(), h_off.numpy(), h_init.numpy(), out=res_view)
         elif mode == "ranges_u16":
-            h_in = torch.from_numpy(np.round(ranges / U16_SCALE).clip(1, 65535).astype(np.uint16)).pin_memory()
+            h_in = pin(np.round(ranges / U16_SCALE).clip(1, 65535).astype(np.uint16))
             nbytes = h_in.numel() * 2 + h_init.numel() * 8
             fn = lambda: m.align_batch_ranges(h_in.numpy(), sc["angle_min"], sc["angle_inc"], h_init.numpy(), range_scale=U16_SCALE, out=res_view)
         else:
-            h_in = torch.from_numpy(ranges).pin_memory()
+            h_in = pin(ranges)
             nbytes = h_in.numel() * 4 + h_init.numel() * 8
             fn = lambda: m.align_batch_ranges(h_in.numpy(), sc["angle_min"], sc["angle_inc"], h_init.numpy(), range_scale=1.0, out=res_view)
         if mode == args.input:
@@ -565,7 +575,7 @@ def run_native(args):
                     "per_rank": {"h2d_gbs_plain_copy": h2d_gbs, "e2e_ms_per_step": [t / args.steps for t in e2e_rank_ms],
                                  "effective_h2d_gbs": [in_bytes / (t / args.steps / 1e3) / 1e9 for t in e2e_rank_ms],
                                  "note": "plain copy: the step's pinned input copied by every rank at the same time, no kernel; effective: input bytes / e2e step time"},
-                    "numa": ctx.numa},
+                    "numa": ctx.numa, "pinned": args.pinned},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                          "dram_frac": (traffic / (kernel_ms / 1e3) / 1e9 / hbm) if traffic else None,

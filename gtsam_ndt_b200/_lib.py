@@ -74,6 +74,7 @@ SIGNATURES = {
     "ndt2d_relocalize_wait": (C.c_int, [_V, C.c_uint64, C.c_int, C.c_int, _V, _V]),
     "ndt2d_reloc_close": (C.c_int, [_V]),
     "ndt2d_host_alloc": (C.c_int, [C.POINTER(_V), C.c_size_t]),
+    "ndt2d_host_alloc_flags": (C.c_int, [C.POINTER(_V), C.c_size_t, C.c_int]),
     "ndt2d_host_free": (C.c_int, [_V]),
 }
 

@@ -1020,10 +1020,12 @@ int ndt2d_relocalize(ndt2d_matcher *m, int level, const float *xy, int n, const 
     return NDT2D_OK;
 }
 
-int ndt2d_host_alloc(void **p, size_t bytes)
+int ndt2d_host_alloc(void **p, size_t bytes) { return ndt2d_host_alloc_flags(p, bytes, 0); }
+
+int ndt2d_host_alloc_flags(void **p, size_t bytes, int flags)
 {
     if (!p) return NDT2D_EINVAL;
-    cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, (flags & NDT2D_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
     if (e != cudaSuccess) {
         fail(nullptr, NDT2D_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
         return NDT2D_ENOMEM;

@@ -32,6 +32,28 @@ def _ptr(a):
     return C.c_void_p(int(a))
 
 
+def pinned_array(shape, dtype, write_combined=False):
+    """A numpy array in page-locked host memory from the library's allocator (ndt2d_host_alloc_flags): full-speed copies for
+    the host-buffer calls. write_combined: for input buffers the CPU only writes. The memory is freed with the array."""
+    L = _lib.load()
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = C.c_void_p()
+    if L.ndt2d_host_alloc_flags(C.byref(p), n, 1 if write_combined else 0) != 0:
+        raise NdtError(f"ndt2d_host_alloc_flags({n}) failed: {L.ndt2d_last_error(None).decode()}")
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            L.ndt2d_host_free(self.ptr)
+
+    buf = (C.c_ubyte * max(n, 1)).from_address(p.value)
+    buf._owner = _Owner(p)          # keeps the allocation alive as long as any view of `buf` exists
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+
 class NdtMatcher2D:
     """One handle = one CUDA device + one stream (not thread-safe)."""
 

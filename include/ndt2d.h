@@ -254,6 +254,10 @@ int ndt2d_reloc_close(ndt2d_matcher *m);
 
 /* ---- pinned host memory for callers that want full-speed copies ------------------------------ */
 int ndt2d_host_alloc(void **p, size_t bytes);
+/* flags: NDT2D_HOST_WRITE_COMBINED for buffers the CPU only writes (scan input): the copy engine reads them without
+ * snooping the CPU caches; CPU reads from such memory are very slow */
+#define NDT2D_HOST_WRITE_COMBINED 1
+int ndt2d_host_alloc_flags(void **p, size_t bytes, int flags);
 int ndt2d_host_free(void *p);
 
 #ifdef __cplusplus
