@@ -36,32 +36,30 @@ struct WarpState {
     int count, tcount;
 };
 
-// One SPEC 4 evaluation at ws->p (trial == 0, result to ws->v) or ws->pn (trial != 0, result to ws->t); lane t stores
-// sum t.
+// One SPEC 4 evaluation at the trial pose ws->pn, result to ws->t / ws->tcount; lane t stores sum t.
 template <int OV, bool STAGED, int TABLE>
-__device__ __forceinline__ void eval_to_smem_body(const LevelDev *L, const float2 *pts, int n, WarpState *ws, int trial)
+__device__ __forceinline__ void eval_to_smem_body(const LevelDev *L, const float2 *pts, int n, WarpState *ws)
 {
     const int lane = threadIdx.x & 31;
-    const double *pose = trial ? ws->pn : ws->p;
+    const double *pose = ws->pn;
     Eval E;
     eval_warp<OV, true, STAGED, (STAGED && OV == 0 && TABLE == TABLE_DENSE) ? NDT2D_PIPE : 0, true, TABLE>(*L, pts, n, pose_for_level(pose[0], pose[1], pose[2], *L), lane, E);
     __syncwarp();
-    double *out = trial ? ws->t : ws->v;
-    out[E.slot] = E.v[0]; // lanes holding the same sum store the same bits
-    if (lane == 0) *(trial ? &ws->tcount : &ws->count) = E.count;
+    ws->t[E.slot] = E.v[0]; // lanes holding the same sum store the same bits
+    if (lane == 0) ws->tcount = E.count;
     __syncwarp();
 }
 // ... as a function of its own (the point loop then gets a register allocation independent of the f64 solver)
 template <int OV, bool STAGED, int TABLE>
-__device__ __noinline__ void eval_to_smem_call(const LevelDev *L, const float2 *pts, int n, WarpState *ws, int trial)
+__device__ __noinline__ void eval_to_smem_call(const LevelDev *L, const float2 *pts, int n, WarpState *ws)
 {
-    eval_to_smem_body<OV, STAGED, TABLE>(L, pts, n, ws, trial);
+    eval_to_smem_body<OV, STAGED, TABLE>(L, pts, n, ws);
 }
 template <int OV, bool STAGED, int TABLE>
-__device__ __forceinline__ void eval_to_smem(const LevelDev *L, const float2 *pts, int n, WarpState *ws, int trial)
+__device__ __forceinline__ void eval_to_smem(const LevelDev *L, const float2 *pts, int n, WarpState *ws)
 {
-    if (NDT2D_EVAL_INLINE && TABLE != TABLE_SHASH) eval_to_smem_body<OV, STAGED, TABLE>(L, pts, n, ws, trial);
-    else eval_to_smem_call<OV, STAGED, TABLE>(L, pts, n, ws, trial);
+    if (NDT2D_EVAL_INLINE && TABLE != TABLE_SHASH) eval_to_smem_body<OV, STAGED, TABLE>(L, pts, n, ws);
+    else eval_to_smem_call<OV, STAGED, TABLE>(L, pts, n, ws);
 }
 
 // The threads that share one WarpState: a warp (k_align) or a whole block (k_align_block)
@@ -76,23 +74,47 @@ struct BlockScope {
 
 // SPEC 5, one pyramid level, starting from and finishing in ws->p: THE Levenberg-Marquardt loop, shared by the
 // warp-per-scan and the block-per-scan kernels. Every thread of the scope computes the same f64 values from the shared
-// state, so the control flow is uniform; eval(trial) evaluates ws->p (trial == 0, result to ws->v / ws->count) or ws->pn
-// (trial != 0, result to ws->t / ws->tcount) and ends with a Scope::sync().
+// state, so the control flow is uniform. eval() evaluates the trial pose ws->pn into ws->t / ws->tcount and ends with a
+// Scope::sync(). There is ONE call site: the first evaluation (at ws->p) runs as a trial at pn = p that is accepted
+// unconditionally, so an inlined evaluation exists once in the kernel (round 2: the second copy had the worse register
+// allocation - ten accumulator moves per 64 points - and it was the one that ran 11 times out of 12).
 template <class Scope, class EvalFn>
 __device__ __forceinline__ int lm_level(const ndt2d_params &P, int n, WarpState *ws, int &evals_total, EvalFn eval)
 {
     const int id = Scope::id();
     if (id == 0) ws->lambda = P.lambda_init;
-    eval(0);
-    int evals = 1, status = NDT2D_MAX_ITERATIONS;
-    if (n == 0 || ws->count == 0) {
-        evals_total += evals;
-        return NDT2D_NO_OVERLAP;
-    }
+    if (id < 3) ws->pn[id] = ws->p[id];
+    Scope::sync();
+    int evals = 0, status = NDT2D_MAX_ITERATIONS;
+    bool small = false;
     for (;;) {
+        eval();
+        evals += 1;
+        double lambda = ws->lambda;
+        const bool first = evals == 1;
+        const bool better = first || ws->t[0] > ws->v[0];
+        Scope::sync();
+        if (better) {
+            if (id < 10) ws->v[id] = ws->t[id];
+            if (id == 10) ws->count = ws->tcount;
+            if (id >= 11 && id < 14) ws->p[id - 11] = ws->pn[id - 11];
+            if (!first) {
+                lambda = fmax(lambda / P.lambda_down, P.lambda_min);
+                if (id == 14) ws->lambda = lambda;
+            }
+            Scope::sync();
+            if (first) {
+                if (n == 0 || ws->count == 0) { status = NDT2D_NO_OVERLAP; break; }
+            } else if (small) { status = NDT2D_CONVERGED; break; }
+        } else {
+            if (small) { status = NDT2D_CONVERGED; break; }
+            lambda = lambda * P.lambda_up;
+            if (id == 14) ws->lambda = lambda;
+            Scope::sync();
+            if (lambda > P.lambda_max) { status = NDT2D_STALLED; break; }
+        }
         if (evals >= P.max_iterations) break;
         double d[3];
-        double lambda = ws->lambda;
         bool stalled = false;
         {
             double g[3] = {ws->v[1], ws->v[2], ws->v[3]};
@@ -112,7 +134,7 @@ __device__ __forceinline__ int lm_level(const ndt2d_params &P, int n, WarpState 
             double sc = P.max_step_rot / fabs(d[2]);
             d[0] *= sc; d[1] *= sc; d[2] *= sc; n2 = n2 * (sc * sc);
         }
-        const bool small = (n2 < P.eps_trans * P.eps_trans) && (fabs(d[2]) < P.eps_rot);
+        small = (n2 < P.eps_trans * P.eps_trans) && (fabs(d[2]) < P.eps_rot);
         Scope::sync();
         if (id == 0) {
             ws->pn[0] = ws->p[0] + d[0];
@@ -121,26 +143,6 @@ __device__ __forceinline__ int lm_level(const ndt2d_params &P, int n, WarpState 
             ws->lambda = lambda;
         }
         Scope::sync();
-        eval(1);
-        evals += 1;
-        lambda = ws->lambda;
-        const bool better = ws->t[0] > ws->v[0];
-        Scope::sync();
-        if (better) {
-            if (id < 10) ws->v[id] = ws->t[id];
-            if (id == 10) ws->count = ws->tcount;
-            if (id >= 11 && id < 14) ws->p[id - 11] = ws->pn[id - 11];
-            lambda = fmax(lambda / P.lambda_down, P.lambda_min);
-            if (id == 14) ws->lambda = lambda;
-            Scope::sync();
-            if (small) { status = NDT2D_CONVERGED; break; }
-        } else {
-            if (small) { status = NDT2D_CONVERGED; break; }
-            lambda = lambda * P.lambda_up;
-            if (id == 14) ws->lambda = lambda;
-            Scope::sync();
-            if (lambda > P.lambda_max) { status = NDT2D_STALLED; break; }
-        }
     }
     evals_total += evals;
     return status;
@@ -168,7 +170,7 @@ template <int OV, bool STAGED, int TABLE>
 __device__ __forceinline__ int align_level(const LevelDev *L, const ndt2d_params &P, const ScanView &v, WarpState *ws,
                                            int &evals_total)
 {
-    return lm_level<WarpScope>(P, v.n, ws, evals_total, [&](int trial) { eval_to_smem<OV, STAGED, TABLE>(L, v.pts, v.n, ws, trial); });
+    return lm_level<WarpScope>(P, v.n, ws, evals_total, [&]() { eval_to_smem<OV, STAGED, TABLE>(L, v.pts, v.n, ws); });
 }
 
 

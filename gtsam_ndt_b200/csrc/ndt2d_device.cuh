@@ -19,7 +19,10 @@
 #define NDT2D_UNROLL 1
 #endif
 #ifndef NDT2D_JR1
-#define NDT2D_JR1 0 // 1: K = 1 kernels also take j from r by operand modifiers (see rotate_point)
+#define NDT2D_JR1 1 // 1: K = 1 kernels also take j from r by operand modifiers (see rotate_point)
+#endif
+#ifndef NDT2D_ESEL
+#define NDT2D_ESEL 1 // SPEC 4's pair tests, select and count written in PTX (see select_count)
 #endif
 #ifndef NDT2D_LDMODE
 #define NDT2D_LDMODE 4 // cell gather instruction variant; 4 = ld.global.nc.L1::no_allocate, one 256-bit load (measured best:
@@ -47,6 +50,9 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0,
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// acc = fma(a, b, acc) / acc = acc + a, accumulator tied to the destination
+__device__ __forceinline__ void fma2_acc(u64 &acc, u64 a, u64 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ void add2_acc(u64 &acc, u64 a) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(a)); }
 // lo + hi of a packed product pair: the "a*b + c*d" of SPEC 4 (two rounded products, one add)
 __device__ __forceinline__ float hsum(u64 v) { float a, b; upk(v, a, b); return __fadd_rn(a, b); }
 
@@ -305,8 +311,9 @@ struct PointPk {
 };
 // JR: take j from r instead of computing it. SPEC 4: jx = fma(ns,x,nc*y) = -ry and jy = fma(c,x,ns*y) = rx bit for bit
 // (round-to-nearest is symmetric under negation), so j is r with its halves swapped and one sign flipped; ptxas folds
-// that into operand modifiers (.HI_LO.NP) and four packed instructions per step disappear. Measured (v3): +2.3 % at K = 4,
-// where j is used by four cells, but -2 % at K = 1, so only the K = 4 kernels use it.
+// that into operand modifiers (.HI_LO.NP) and four packed instructions per step disappear. Measured: +2.3 % at K = 4 (v3), where j
+// is used by four cells; at K = 1 it was -2 % under SPEC v3 and is +5 % under v4 (x8: 20.31 vs 19.33 M matches/s - the f64
+// geometry made the loop longer and the four instructions count), so every kernel uses it now.
 template <bool JR = false>
 __device__ __forceinline__ void rotate_point(const PosePk &P, float x, float y, PointPk &p)
 {
@@ -340,6 +347,9 @@ struct Cell4 {
 __device__ __forceinline__ Cell4 load_cell(const float4 *__restrict__ cells, unsigned idx)
 {
     Cell4 r;
+#ifdef NDT2D_PROBE_IDXMASK
+    idx &= NDT2D_PROBE_IDXMASK; // speed-of-light probe, never shipped: every gather lands in the same few lines (results are garbage)
+#endif
     const float4 *p = cells + 2 * (size_t)idx;
 #if NDT2D_LDMODE == 0
     asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.mu), "=l"(r.B0), "=l"(r.B1), "=l"(r.nv) : "l"(p));
@@ -444,6 +454,30 @@ struct Factors {
     float c7[2];           // per point
 };
 
+// SPEC 4's two tests of a pair (the cell is valid, h < 30): returns e if the pair counts, else 0; COUNT: cnt += 1 if it counts
+template <bool COUNT>
+__device__ __forceinline__ float select_count(float valid, float nh, float e, int &cnt)
+{
+    float r;
+    if (COUNT) {
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.neu.f32 p, %2, 0f00000000;\n\t"
+            "setp.gt.and.f32 p, %3, 0fC1F00000, p;\n\t"
+            "selp.f32 %0, %4, 0f00000000, p;\n\t"
+            "@p add.s32 %1, %1, 1;\n\t}"
+            : "=f"(r), "+r"(cnt)
+            : "f"(valid), "f"(nh), "f"(e));
+    } else {
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.neu.f32 p, %1, 0f00000000;\n\t"
+            "setp.gt.and.f32 p, %2, 0fC1F00000, p;\n\t"
+            "selp.f32 %0, %3, 0f00000000, p;\n\t}"
+            : "=f"(r)
+            : "f"(valid), "f"(nh), "f"(e));
+    }
+    return r;
+}
+
 // A point outside the lattice was given the all-zero sentinel record (fetch()), so `valid` covers both tests of SPEC 4.
 template <bool FULL>
 __device__ __forceinline__ void cell_factors(const Cell4 &cA, const Cell4 &cB, const PointPk &A, const PointPk &B, Factors &F,
@@ -454,12 +488,18 @@ __device__ __forceinline__ void cell_factors(const Cell4 &cA, const Cell4 &cB, c
     u64 uA = fma2(cA.B0, bc(lo32(qA)), mul2(cA.B1, bc(hi32(qA))));
     u64 uB = fma2(cB.B0, bc(lo32(qB)), mul2(cB.B1, bc(hi32(qB))));
     u64 nh = mul2(bc(-0.5f), pk(hsum(mul2(qA, uA)), hsum(mul2(qB, uB))));
-    bool okA = (hi32(cA.nv) != 0.0f) && (lo32(nh) > -30.0f);
-    bool okB = (hi32(cB.nv) != 0.0f) && (hi32(nh) > -30.0f);
     u64 e = expneg2(nh);
     // skipped pairs get e = 0: fma(0, c, acc) == acc bit for bit (every c is finite, see sanitize())
+#if NDT2D_ESEL
+    // the two tests, the select and the count in PTX: one SEL and one predicated add per point (the compiler's own
+    // expansion is a zero move plus a predicated move for the select and an add plus a predicated move for the count)
+    F.e = pk(select_count<FULL>(hi32(cA.nv), lo32(nh), lo32(e), cnt), select_count<FULL>(hi32(cB.nv), hi32(nh), hi32(e), cnt));
+#else
+    bool okA = (hi32(cA.nv) != 0.0f) && (lo32(nh) > -30.0f);
+    bool okB = (hi32(cB.nv) != 0.0f) && (hi32(nh) > -30.0f);
     F.e = pk(okA ? lo32(e) : 0.0f, okB ? hi32(e) : 0.0f);
     if (FULL) cnt += (okA ? 1 : 0) + (okB ? 1 : 0);   // the score-only sweep reports no count
+#endif
     if (FULL) {
         float a2A = hsum(mul2(uA, A.j)), a2B = hsum(mul2(uB, B.j));
         u64 vA = fma2(cA.B0, bc(lo32(A.j)), mul2(cA.B1, bc(hi32(A.j))));
@@ -483,19 +523,19 @@ __device__ __forceinline__ void cell_factors(const Cell4 &cA, const Cell4 &cB, c
 template <bool FULL>
 __device__ __forceinline__ void apply_factors(const Factors &F, Partials &S)
 {
-    S.s0 = add2(S.s0, F.e);
+    add2_acc(S.s0, F.e);
     if (FULL) {
         const float eA = lo32(F.e), eB = hi32(F.e);
-        S.s12[0] = fma2(bc(eA), F.c12[0], S.s12[0]);
-        S.s12[1] = fma2(bc(eB), F.c12[1], S.s12[1]);
-        S.s45[0] = fma2(bc(eA), F.c45[0], S.s45[0]);
-        S.s45[1] = fma2(bc(eB), F.c45[1], S.s45[1]);
-        S.s68[0] = fma2(bc(eA), F.c68[0], S.s68[0]);
-        S.s68[1] = fma2(bc(eB), F.c68[1], S.s68[1]);
-        S.s3 = fma2(F.e, F.c3, S.s3);
+        fma2_acc(S.s12[0], F.c12[0], bc(eA));
+        fma2_acc(S.s12[1], F.c12[1], bc(eB));
+        fma2_acc(S.s45[0], F.c45[0], bc(eA));
+        fma2_acc(S.s45[1], F.c45[1], bc(eB));
+        fma2_acc(S.s68[0], F.c68[0], bc(eA));
+        fma2_acc(S.s68[1], F.c68[1], bc(eB));
+        fma2_acc(S.s3, F.e, F.c3);
         S.s7[0] = __fmaf_rn(eA, F.c7[0], S.s7[0]);
         S.s7[1] = __fmaf_rn(eB, F.c7[1], S.s7[1]);
-        S.s9 = fma2(F.e, F.c9, S.s9);
+        fma2_acc(S.s9, F.e, F.c9);
     }
 }
 
@@ -511,12 +551,14 @@ __device__ __forceinline__ void accumulate_cell(const Cell4 &cA, const Cell4 &cB
 
 // Where the warp's points come from: AoS float2 in shared memory, sanitised and padded with the far-away
 // point to a multiple of 64 (SMEM), or global memory with bounds checks (scans too long for the slot).
-template <bool SMEM>
+// ADDR (SMEM only): i is not a point index but the shared-window byte address of point A (see eval_warp)
+template <bool SMEM, bool ADDR = false>
 __device__ __forceinline__ void load_two(const float2 *pts, int n, int i, float2 &a, float2 &b)
 {
     if (SMEM) {
-        a = pts[i];
-        b = pts[i + 32];
+        const unsigned sa = ADDR ? (unsigned)i : (unsigned)__cvta_generic_to_shared(pts) + 8u * (unsigned)i;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a.x), "=f"(a.y) : "r"(sa));
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+256];" : "=f"(b.x), "=f"(b.y) : "r"(sa));
     } else {
         const float2 far = make_float2(1e18f, 1e18f);
         a = i < n ? sanitize(__ldg(pts + i)) : far;
@@ -672,7 +714,7 @@ __device__ __forceinline__ Cell4 lookup_shared(const LatticePk &G, unsigned key,
 }
 
 // P64 (score-only kernels with the scan staged in shared memory): pts holds double2 per point, r and j are not needed
-template <int OV, bool SMEM, int TABLE = TABLE_DENSE, bool P64 = false>
+template <int OV, bool SMEM, int TABLE = TABLE_DENSE, bool P64 = false, bool ADDR = false>
 __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const LatticePk &G, const PosePk &P, const float2 *pts,
                                       int n, int i, Fetched<OV> &F)
 {
@@ -684,7 +726,7 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
         bB = locate_base(P, b.x, b.y, G, F.B.df);
     } else {
         float2 a, b;
-        load_two<SMEM>(pts, n, i, a, b);
+        load_two<SMEM, ADDR>(pts, n, i, a, b);
         rotate_point<OV != 0 || NDT2D_JR1>(P, a.x, a.y, F.A);
         rotate_point<OV != 0 || NDT2D_JR1>(P, b.x, b.y, F.B);
         bA = locate_base(P, a.x, a.y, G, F.A.df);
@@ -808,6 +850,16 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
                 fetch<OV, SMEM, TABLE, P64>(cells, G, P, pts, n, min(i + 128, last), F0);
                 accumulate_step<OV, FULL>(G, F1, S, cnt);
             }
+        }
+    } else if (SMEM && !P64) {
+        // the staged scan is walked by its shared-window address: one register is loop counter and load address at once (as
+        // pts[i] the compiler recomputed slot base + warp * capacity + i with two multiply-adds and a constant load per step)
+        const unsigned s0 = (unsigned)__cvta_generic_to_shared(pts) + 8u * (unsigned)lane, s1 = s0 + 8u * (unsigned)npad;
+#pragma unroll kUnroll
+        for (unsigned sa = s0; sa < s1; sa += 512u) {
+            Fetched<OV> cur;
+            fetch<OV, SMEM, TABLE, P64, true>(cells, G, P, pts, n, (int)sa, cur);
+            accumulate_step<OV, FULL>(G, cur, S, cnt);
         }
     } else {
 #pragma unroll kUnroll

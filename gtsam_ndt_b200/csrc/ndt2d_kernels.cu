@@ -215,11 +215,11 @@ static constexpr int BLOCK_ALIGN_THREADS = 256; // 8 warps (18 warps, one round 
 static constexpr int FACTOR_WORDS = 10; // u64 per lane and (step, cell): e, c12[2], c45[2], c68[2], c3, c9, c7 pair
 
 template <int OV>
-__device__ __forceinline__ void eval_block(const LevelDev *L, const float2 *pts, int n, WarpState *ws, int trial, u64 *fac)
+__device__ __forceinline__ void eval_block(const LevelDev *L, const float2 *pts, int n, WarpState *ws, u64 *fac)
 {
     constexpr int NC = OV ? 4 : 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double *pose = trial ? ws->pn : ws->p;
+    const double *pose = ws->pn;
     const PosePk P = pose_pack(pose_for_level(pose[0], pose[1], pose[2], *L));
     const LatticePk G = lattice_pack<OV>(*L, TABLE_DENSE);
     const float4 *__restrict__ cells = L->cells;
@@ -266,9 +266,8 @@ __device__ __forceinline__ void eval_block(const LevelDev *L, const float2 *pts,
         }
         Eval E;
         finish_partials<true, true>(S, cnt, lane, E);
-        double *out = trial ? ws->t : ws->v;
-        out[E.slot] = E.v[0];
-        if (lane == 0) *(trial ? &ws->tcount : &ws->count) = E.count;
+        ws->t[E.slot] = E.v[0];
+        if (lane == 0) ws->tcount = E.count;
     }
     __syncthreads();
 }
@@ -278,7 +277,7 @@ __device__ __forceinline__ int align_level_block(const LevelDev *L, const ndt2d_
                                                  u64 *fac, int &evals_total)
 {
     // eval_block begins its second half with __syncthreads() and ends with one
-    return lm_level<BlockScope>(P, n, ws, evals_total, [&](int trial) { eval_block<OV>(L, pts, n, ws, trial, fac); });
+    return lm_level<BlockScope>(P, n, ws, evals_total, [&]() { eval_block<OV>(L, pts, n, ws, fac); });
 }
 
 template <int OV>

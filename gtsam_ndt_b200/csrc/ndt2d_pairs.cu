@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(256) k_pairs_build(const PairBuildArgs a)
 // ------------------------------------------------------------------------------------------------
 
 static constexpr int FUSED_WARPS_MAX = 8;        // warps per block: as many as let two blocks share an SM, at most this (5 at 1080-point scans)
-static constexpr unsigned FUSED_STATE_BYTES = 352; // WarpState (216 B) + LevelDev (112 B), rounded up to 16
+static constexpr unsigned FUSED_WS_BYTES = 224;    // room for the WarpState (216 B)
+static constexpr unsigned FUSED_STATE_BYTES = 352; // WarpState + LevelDev (112 B), rounded up to 16
 
 // SPEC 2 geometry of one level of a target's grid from its bounding box: the f32 expressions of setup_level() in
 // ndt2d_capi.cu (every lane computes the same values). Returns false when the lattice is unusable (empty or >= 2^31
@@ -209,7 +210,11 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
     const LevelDev &L = *Lp;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    unsigned short *perm[2] = {reinterpret_cast<unsigned short *>(keyof + cap_t), reinterpret_cast<unsigned short *>(keyof + cap_t) + cap_t + 2};
+    // the two index buffers, selected by pointer arithmetic: as an array of two pointers indexed by `cur` the compiler kept them in
+    // local memory and went through generic loads and stores in the sort loops (r2z profile: 14 % of the kernel's samples there)
+    unsigned short *const perm0 = reinterpret_cast<unsigned short *>(keyof + cap_t);
+    const unsigned perm_stride = cap_t + 2;
+    auto perm_of = [&](int which) { return perm0 + (which ? perm_stride : 0u); };
     unsigned *hist = reinterpret_cast<unsigned *>(rec);     // 256 counters; the record area is not in use during the sort
     const unsigned ncells = (unsigned)L.njx * (unsigned)L.njy;
     // (1) keys; four windows of points are requested at a time (a warp has no other latency hiding here)
@@ -229,7 +234,7 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
             const bool in = i < n && lattice_of_point(L, pw[u].x, pw[u].y, hx, hy);
             if (i < n) {
                 keyof[i] = in ? (unsigned)(hy * L.njx + hx) : ncells;
-                perm[0][i] = (unsigned short)i;
+                perm0[i] = (unsigned short)i;
             }
             m += __popc(__ballot_sync(FULL_MASK, in));
         }
@@ -246,10 +251,12 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
     int cur = 0;
 #pragma unroll 1
     for (int shift = 0; shift < nbits; shift += 8) {
+        const unsigned short *const pin = perm_of(cur);
+        unsigned short *const pout = perm_of(cur ^ 1);
         for (int b = lane; b < 256; b += 32) hist[b] = 0u;
         __syncwarp();
 #pragma unroll 2
-        for (int i = lane; i < n; i += 32) atomicAdd(&hist[(keyof[perm[cur][i]] >> shift) & 255u], 1u);
+        for (int i = lane; i < n; i += 32) atomicAdd(&hist[(keyof[pin[i]] >> shift) & 255u], 1u);
         __syncwarp();
         unsigned c[8], sum = 0u;
 #pragma unroll
@@ -269,7 +276,7 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
         for (int base = 0; base < n; base += 32) {      // windows in order: the scatter is stable
             const int i = base + lane;
             const bool valid = i < n;
-            const unsigned short ix = valid ? perm[cur][i] : (unsigned short)0;
+            const unsigned short ix = valid ? pin[i] : (unsigned short)0;
             const unsigned d = valid ? (keyof[ix] >> shift) & 255u : 256u + (unsigned)lane;
             const unsigned peers = __match_any_sync(FULL_MASK, d);
             const unsigned rank = __popc(peers & lt);
@@ -277,14 +284,14 @@ __device__ __noinline__ int build_table_shared(const LevelDev *Lp, const float2 
             __syncwarp();
             if (valid && rank == 0u) hist[d] = off + __popc(peers);
             __syncwarp();
-            if (valid) perm[cur ^ 1][off + rank] = ix;
+            if (valid) pout[off + rank] = ix;
         }
         __syncwarp();
         cur ^= 1;
     }
     // (3) run heads among the m points inside the lattice (they come first: the outside key is the largest)
-    const unsigned short *order = perm[cur];
-    unsigned short *hpos = perm[cur ^ 1];
+    const unsigned short *order = perm_of(cur);
+    unsigned short *hpos = perm_of(cur ^ 1);
     int nruns = 0;
 #pragma unroll 1
     for (int base = 0; base < m; base += 32) {
@@ -390,7 +397,7 @@ __global__ void __launch_bounds__(FUSED_WARPS_MAX * 32) k_pairs_fused(const __gr
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *slice = smem_raw + (size_t)warp * a.warp_bytes;
     WarpState *ws = reinterpret_cast<WarpState *>(slice);
-    LevelDev *Ls = reinterpret_cast<LevelDev *>(slice + 224);
+    LevelDev *Ls = reinterpret_cast<LevelDev *>(slice + FUSED_WS_BYTES);
     unsigned *area_a = reinterpret_cast<unsigned *>(slice + a.off_a);
     float2 *slot = reinterpret_cast<float2 *>(slice + a.off_a);
     float *rec = reinterpret_cast<float *>(slice + a.off_r);
@@ -454,7 +461,7 @@ __global__ void __launch_bounds__(FUSED_WARPS_MAX * 32) k_pairs_fused(const __gr
 #pragma unroll 4
             for (int i = lane; i < npad; i += 32) slot[i] = i < sn ? sanitize(__ldg(ssrc + i)) : far;
             __syncwarp();
-            status = lm_level<WarpScope>(a.prm, sn, ws, evals, [&](int trial) { eval_to_smem<0, true, TABLE_SHASH>(Ls, slot, sn, ws, trial); });
+            status = lm_level<WarpScope>(a.prm, sn, ws, evals, [&]() { eval_to_smem<0, true, TABLE_SHASH>(Ls, slot, sn, ws); });
         }
         if (lane == 0) write_result(*ws, evals, status, a.res + job);
         __syncwarp();
@@ -477,7 +484,7 @@ bool pairs_fused_layout(PairFusedArgs &a, int64_t max_target_points, int64_t max
     a.off_r = (unsigned)(a.off_a + size_a);
     a.off_h = (unsigned)(a.off_r + size_r);
     a.warp_bytes = (unsigned)up16(a.off_h + (size_t)a.hslots * 4);
-    static_assert(sizeof(WarpState) <= 224 && sizeof(LevelDev) <= FUSED_STATE_BYTES - 224, "per-warp state area");
+    static_assert(sizeof(WarpState) <= FUSED_WS_BYTES && sizeof(LevelDev) <= FUSED_STATE_BYTES - FUSED_WS_BYTES, "per-warp state area");
     // two blocks per SM (each gets half of the opt-in limit minus the 1 KB the driver reserves per block)
     a.warps_per_block = (unsigned)std::min<size_t>(FUSED_WARPS_MAX, ((size_t)smem_optin / 2 - 1024) / a.warp_bytes);
     return a.warps_per_block >= 2;
