@@ -243,36 +243,55 @@ struct Pose32 {
 // SPEC 4.2: sin and cos of the pose angle as a fixed sequence of f64 operations (two-constant Cody-Waite reduction,
 // fdlibm kernel polynomials, quadrant from the low bits of the magic sum): the oracle's bits, and about a third of
 // the instructions of the library sincos with its Payne-Hanek branch.
+// CM: the polynomial coefficients come from constant memory - a DFMA takes a constant-bank operand directly, whereas a 64-bit
+// literal costs two uniform moves in front of it (36 per evaluation). The sweep kernel uses it (233 -> 218 instructions per
+// hypothesis outside the point loop); in k_align the literals stay, because with the constant-bank form ptxas's register
+// allocation of the point loop came out twelve moves longer (tools/looplen.py: 129 -> 141 instructions).
+static __constant__ double kSinCos[15] = {
+    0.63661977236758138, 1.5707963267948966, 6.123233995736766e-17,
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+    8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+template <bool CM = false>
 __device__ __forceinline__ void sincos_spec(double th, double &sn_out, double &cs_out)
 {
     const double MAGIC = 6755399441055744.0; // 1.5 * 2^52
-    const double t = __fma_rn(th, 0.63661977236758138, MAGIC);
+    const double K[15] = {CM ? kSinCos[0] : 0.63661977236758138, CM ? kSinCos[1] : 1.5707963267948966, CM ? kSinCos[2] : 6.123233995736766e-17,
+                          CM ? kSinCos[3] : 1.58969099521155010221e-10, CM ? kSinCos[4] : -2.50507602534068634195e-08,
+                          CM ? kSinCos[5] : 2.75573137070700676789e-06, CM ? kSinCos[6] : -1.98412698298579493134e-04,
+                          CM ? kSinCos[7] : 8.33333333332248946124e-03, CM ? kSinCos[8] : -1.66666666666666324348e-01,
+                          CM ? kSinCos[9] : -1.13596475577881948265e-11, CM ? kSinCos[10] : 2.08757232129817482790e-09,
+                          CM ? kSinCos[11] : -2.75573143513906633035e-07, CM ? kSinCos[12] : 2.48015872894767294178e-05,
+                          CM ? kSinCos[13] : -1.38888888888741095749e-03, CM ? kSinCos[14] : 4.16666666666666019037e-02};
+    const double t = __fma_rn(th, K[0], MAGIC);
     const double k = __dadd_rn(t, -MAGIC);
     const int q = __double2loint(t) & 3;
-    double r = __fma_rn(-k, 1.5707963267948966, th);
-    r = __fma_rn(-k, 6.123233995736766e-17, r);
+    double r = __fma_rn(-k, K[1], th);
+    r = __fma_rn(-k, K[2], r);
     const double z = __dmul_rn(r, r);
-    double ps = __fma_rn(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = __fma_rn(z, ps, 2.75573137070700676789e-06);
-    ps = __fma_rn(z, ps, -1.98412698298579493134e-04);
-    ps = __fma_rn(z, ps, 8.33333333332248946124e-03);
-    ps = __fma_rn(z, ps, -1.66666666666666324348e-01);
+    double ps = __fma_rn(z, K[3], K[4]);
+    ps = __fma_rn(z, ps, K[5]);
+    ps = __fma_rn(z, ps, K[6]);
+    ps = __fma_rn(z, ps, K[7]);
+    ps = __fma_rn(z, ps, K[8]);
     const double sn = __fma_rn(__dmul_rn(r, z), ps, r);
-    double pc = __fma_rn(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = __fma_rn(z, pc, -2.75573143513906633035e-07);
-    pc = __fma_rn(z, pc, 2.48015872894767294178e-05);
-    pc = __fma_rn(z, pc, -1.38888888888741095749e-03);
-    pc = __fma_rn(z, pc, 4.16666666666666019037e-02);
+    double pc = __fma_rn(z, K[9], K[10]);
+    pc = __fma_rn(z, pc, K[11]);
+    pc = __fma_rn(z, pc, K[12]);
+    pc = __fma_rn(z, pc, K[13]);
+    pc = __fma_rn(z, pc, K[14]);
     const double cs = __fma_rn(__dmul_rn(z, z), pc, __fma_rn(z, -0.5, 1.0));
     const double s4 = (q & 1) ? cs : sn, c4 = (q & 1) ? sn : cs;
     sn_out = (q & 2) ? -s4 : s4;
     cs_out = ((q + 1) & 2) ? -c4 : c4;
 }
 
+template <bool CM = false>
 __device__ __forceinline__ Pose32 pose_for_level(double tx, double ty, double th, const LevelDev &L)
 {
     double sn, cs;
-    sincos_spec(th, sn, cs);
+    sincos_spec<CM>(th, sn, cs);
     Pose32 q;
     q.c = (float)cs;
     q.s = (float)sn;
@@ -720,7 +739,14 @@ __device__ __forceinline__ void fetch(const float4 *__restrict__ cells, const La
 {
     unsigned bA, bB;
     if (P64) {
-        const double2 a = reinterpret_cast<const double2 *>(pts)[i], b = reinterpret_cast<const double2 *>(pts)[i + 32];
+        double2 a, b;
+        if (ADDR) {     // i is the shared-window byte address of point A, 16 bytes per point
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a.x), "=d"(a.y) : "r"((unsigned)i));
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+512];" : "=d"(b.x), "=d"(b.y) : "r"((unsigned)i));
+        } else {
+            a = reinterpret_cast<const double2 *>(pts)[i];
+            b = reinterpret_cast<const double2 *>(pts)[i + 32];
+        }
         F.A.r = F.A.j = F.B.r = F.B.j = 0ull;
         bA = locate_base(P, a.x, a.y, G, F.A.df);
         bB = locate_base(P, b.x, b.y, G, F.B.df);
@@ -851,12 +877,13 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
                 accumulate_step<OV, FULL>(G, F1, S, cnt);
             }
         }
-    } else if (SMEM && !P64) {
+    } else if (SMEM) {
         // the staged scan is walked by its shared-window address: one register is loop counter and load address at once (as
         // pts[i] the compiler recomputed slot base + warp * capacity + i with two multiply-adds and a constant load per step)
-        const unsigned s0 = (unsigned)__cvta_generic_to_shared(pts) + 8u * (unsigned)lane, s1 = s0 + 8u * (unsigned)npad;
+        constexpr unsigned PB = P64 ? 16u : 8u;     // bytes per staged point
+        const unsigned s0 = (unsigned)__cvta_generic_to_shared(pts) + PB * (unsigned)lane, s1 = s0 + PB * (unsigned)npad;
 #pragma unroll kUnroll
-        for (unsigned sa = s0; sa < s1; sa += 512u) {
+        for (unsigned sa = s0; sa < s1; sa += 64u * PB) {
             Fetched<OV> cur;
             fetch<OV, SMEM, TABLE, P64, true>(cells, G, P, pts, n, (int)sa, cur);
             accumulate_step<OV, FULL>(G, cur, S, cnt);

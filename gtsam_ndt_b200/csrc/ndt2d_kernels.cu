@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, FULL ? EVAL_BLOCKS_FULL : NDT2D_
             const double *h = reinterpret_cast<const double *>(poses) + 3 * j;
             tx = __ldg(h); ty = __ldg(h + 1); th = __ldg(h + 2);
         }
-        Pose32 q = pose_for_level(tx, ty, th, L);
+        Pose32 q = pose_for_level<!FULL>(tx, ty, th, L);   // the score-only sweep takes the sin/cos coefficients from constant memory
         Eval E;
         // FULL: the transposed reduction leaves sum number E.slot in every lane (lanes with the same slot hold the same bits)
         if (STAGED) eval_warp<OV, FULL, true, OV == 0 ? EVAL_PIPE : 0, FULL, TABLE_DENSE, P64>(L, sp, n, q, lane, E);
@@ -193,14 +193,18 @@ __global__ void __launch_bounds__(EVAL_THREADS, FULL ? EVAL_BLOCKS_FULL : NDT2D_
 // (2c) batched align: one warp per scan, the whole LM loop on the device
 // ------------------------------------------------------------------------------------------------
 
+// 24 warps per SM at 80 registers, as six blocks of four warps. Measured operating points (gpurun_out/x10_variants.jsonl, M matches/s
+// on configs[1], all bit-identical): 128 x 6: 20.46, 256 x 3: 20.32, 384 x 2: 20.22 (the same 24 warps in larger blocks: a block
+// holds its shared memory until its last warp has drained the queue), 160 x 4 (20 warps, 96 registers): 19.53, 320 x 2 (20
+// warps): 19.43, 256 x 2 (16 warps, 104 registers, the only point whose loop has no register copies): 19.17.
 #ifndef NDT2D_ALIGN_THREADS
-#define NDT2D_ALIGN_THREADS 256
+#define NDT2D_ALIGN_THREADS 128
 #endif
 static constexpr int ALIGN_THREADS = NDT2D_ALIGN_THREADS;
 #ifndef NDT2D_ALIGN_MIN_BLOCKS
-#define NDT2D_ALIGN_MIN_BLOCKS 3
+#define NDT2D_ALIGN_MIN_BLOCKS 6
 #endif
-static constexpr int ALIGN_MIN_BLOCKS = NDT2D_ALIGN_MIN_BLOCKS; // 3: 24 warps/SM at 80 registers (2: 16 warps at 128; measured equal)
+static constexpr int ALIGN_MIN_BLOCKS = NDT2D_ALIGN_MIN_BLOCKS;
 
 // ------------------------------------------------------------------------------------------------
 // (2d) low-latency align: one BLOCK per scan, for calls with few scans (a single align above all)

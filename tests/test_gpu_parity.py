@@ -396,6 +396,26 @@ def test_align_pairs_equals_set_target_plus_align(mods, cfg, monkeypatch):
         assert rg[p].tobytes() == ref.tobytes(), (p, t, s_, rg[p], ref)
 
 
+@pytest.mark.parametrize("decimate", [3, 8, 24])
+def test_align_pairs_small_targets(mods, decimate):
+    """Calls whose longest target is short: the fused build's radix sort then runs with narrower digits (its counter matrix must
+    fit the smaller record + index areas: 6 bits at 360 points, 5 bits below ~170) and more passes. Still set_target + align."""
+    from gtsam_ndt_b200 import synth
+    m, o = make_pair(mods, [1.0, 0.5], None)
+    sc = synth.SCAN_1080
+    ranges, poses = synth.scans(8, traj_len=4000, first=80, step=7, sigma=0.01, **sc)
+    scans = [s[::decimate] for s in synth.polar_to_points(ranges, sc["angle_min"], sc["angle_inc"])]
+    pairs = [(i, i + 1) for i in range(7)] + [(4, 4), (6, 1)]
+    rng = np.random.default_rng(11)
+    init = np.array([_between(poses[t], poses[s]) + rng.normal(size=3) * [0.03, 0.03, 0.003] for t, s in pairs])
+    xy, off = synth.pack(scans)
+    rg = m.align_pairs(xy, off, pairs, init)
+    for p, (t, s_) in enumerate(pairs):
+        m.set_target(scans[t]); o.set_target(scans[t])
+        one = m.align(scans[s_], init[p]); ref = o.align(scans[s_], init[p])
+        assert rg[p].tobytes() == one.tobytes() == ref.tobytes(), (p, t, s_, rg[p], one, ref)
+
+
 @pytest.mark.parametrize("overlap", [0, 1])
 def test_align_pairs_large_scans(mods, overlap):
     """Targets with more occupied cells than the build warp's claimed-slot list holds (full-table finalisation) and
