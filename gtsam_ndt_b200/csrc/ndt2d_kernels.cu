@@ -5,6 +5,9 @@
 // These are gather-bound kernels over an L2-resident cell table: no tensor cores (north_star).
 // Reference file:line: none (the mount is /root/reference/README.md:1 only); arithmetic follows SPEC.md.
 #include "ndt2d_align.cuh"
+#ifdef NDT2D_PROBE_HALF
+#include "ndt2d_half_probe.cuh"
+#endif
 
 #include <math.h>
 #include <string.h>
@@ -144,7 +147,11 @@ static constexpr int EVAL_THREADS = 256;
 #define NDT2D_QUEUE 0 // 0: one global atomic work queue; 1: static per-block ranges (tuning experiment, slower)
 #endif
 static constexpr int EVAL_PIPE = NDT2D_EVAL_PIPE;
+#ifdef NDT2D_PROBE_HALF
+static constexpr int EVAL_BLOCKS_FULL = NDT2D_PROBE_HALF; // probe: resident blocks of the one-point-per-lane evaluation
+#else
 static constexpr int EVAL_BLOCKS_FULL = 3; // the full evaluation needs the align kernel's 80 registers: 24 warps per SM
+#endif
 
 // Block stages the scan in shared memory once (coalesced float2 loads), then each warp takes poses
 // from a grid-stride loop. FULL: ten f64 sums per pose; otherwise the score only (sweep).
@@ -181,6 +188,10 @@ __global__ void __launch_bounds__(EVAL_THREADS, FULL ? EVAL_BLOCKS_FULL : NDT2D_
         Pose32 q = pose_for_level<!FULL>(tx, ty, th, L);   // the score-only sweep takes the sin/cos coefficients from constant memory
         Eval E;
         // FULL: the transposed reduction leaves sum number E.slot in every lane (lanes with the same slot hold the same bits)
+#ifdef NDT2D_PROBE_HALF
+        if (STAGED && FULL && OV == 0) eval_warp_half_probe<true>(L, sp, n, q, lane, E);
+        else
+#endif
         if (STAGED) eval_warp<OV, FULL, true, OV == 0 ? EVAL_PIPE : 0, FULL, TABLE_DENSE, P64>(L, sp, n, q, lane, E);
         else eval_warp<OV, FULL, false, 0, FULL>(L, xy, n, q, lane, E);
         if (FULL) out[(size_t)j * out_stride + E.slot] = E.v[0];
