@@ -201,6 +201,19 @@ def gather_pipe(kernel_key, kernel_ms, clocks, sm_count):
         return None
 
 
+def ncu_pipes(kernel_key):
+    """Utilisation of the units that share the limit of this kernel, from the committed ncu capture of the configuration
+    (static, like `traffic`; `commit` names the build): issue slots, FMA pipe, L1TEX data pipe, L2 hit rate."""
+    try:
+        e = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel_key]
+        out = {k: e[k] for k in ("issue_active_pct", "fma_pipe_cycles_active_pct", "l1tex_data_pipe_pct", "l2_hit_pct", "inst_executed") if k in e}
+        out["commit"] = e.get("commit")
+        out["source"] = e.get("source")
+        return out
+    except Exception:
+        return None
+
+
 def ncu_traffic_sweep(args, hyps):
     try:
         tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -584,10 +597,11 @@ def run_native(args):
                          "convention": "frac = gather traffic: every point read and 32 B cell gather counts, bytes/eval = N*(8+32K)+92 (SURVEY 8(d)); "
                                        "cells are served by L2, so frac is NOT a utilisation. dram_frac = ncu DRAM bytes per launch / kernel time / peak "
                                        "(the real HBM utilisation); gather_pipe_frac = ncu L1TEX sectors per launch / kernel time / (SMs x clock), the "
-                                       "unit that actually bounds the path. The ncu counters are per-configuration constants from profiles/traffic.json "
+                                       "busiest unit on the memory side; `pipes` lists it beside the issue slots and the FMA pipe (no unit is saturated: "
+                                       "see DESIGN.md section 5). The ncu counters are per-configuration constants from profiles/traffic.json "
                                        "(its `commit` field names the build they were captured on); the times are measured live",
                          "evals_per_launch": float(iters.sum()), "bytes_per_eval": eval_bytes(npts, K),
-                         "evals_per_s": total_evals_per_step * args.steps / (ms / 1e3), "gather_pipe": gp},
+                         "evals_per_s": total_evals_per_step * args.steps / (ms / 1e3), "gather_pipe": gp, "pipes": ncu_pipes(key)},
             "mean_iterations": float(iters.mean()), "status_counts": np.bincount(res["status"], minlength=4).tolist(),
             "map_build_ms": build_ms, "clocks": clocks,
         }
