@@ -140,8 +140,12 @@ static constexpr int EVAL_THREADS = 256;
 #ifndef NDT2D_EVAL_PIPE
 #define NDT2D_EVAL_PIPE 0 // the same for k_eval_poses (evaluate / sweep)
 #endif
+#ifndef NDT2D_SWEEP_P64
+#define NDT2D_SWEEP_P64 1 // the score-only sweep stages the scan as f64 (no input conversions in the loop)
+#endif
 #ifndef NDT2D_EVAL_BLOCKS
-#define NDT2D_EVAL_BLOCKS 6 // resident k_eval_poses blocks per SM (38 registers; measured 4: 456, 6: 472, 8: 439 M hypotheses/s)
+#define NDT2D_EVAL_BLOCKS 4 // resident k_eval_poses blocks per SM for the score-only sweep: 4 (32 warps, 56 registers) and 5 (40 warps, 48
+                            // registers) both reach 446.8 M hypotheses/s, 6 (48 warps, 40 registers: constants re-materialised in the loop) 434 M
 #endif
 #ifndef NDT2D_QUEUE
 #define NDT2D_QUEUE 0 // 0: one global atomic work queue; 1: static per-block ranges (tuning experiment, slower)
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, FULL ? EVAL_BLOCKS_FULL : NDT2D_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int npad = (n + 63) & ~63;
     float2 *sp = reinterpret_cast<float2 *>(smem_raw);
-    constexpr bool P64 = STAGED && !FULL;   // the score-only sweep needs the points in f64 only: widen them once, here
+    constexpr bool P64 = NDT2D_SWEEP_P64 && STAGED && !FULL;   // the score-only sweep needs the points in f64 only: widen them once, here
     if (STAGED) {
         // sanitised points, padded with the far-away point to a multiple of 64 (SPEC 4)
         for (int i = threadIdx.x; i < npad; i += blockDim.x) {
@@ -556,7 +560,7 @@ template <int OV, bool FULL, bool F32POSE>
 static cudaError_t launch_eval_t(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const void *d_poses,
                                  int64_t npose, double *d_out, int out_stride, int32_t *d_count)
 {
-    size_t smem = (size_t)((n + 63) & ~63) * (FULL ? sizeof(float2) : sizeof(double2));   // score only: points staged as f64
+    size_t smem = (size_t)((n + 63) & ~63) * ((FULL || !NDT2D_SWEEP_P64) ? sizeof(float2) : sizeof(double2));   // score only: points staged as f64
     int grid = grid_for(npose, EVAL_THREADS / 32, c.sm_count, FULL ? EVAL_BLOCKS_FULL : NDT2D_EVAL_BLOCKS);
     if (smem <= (size_t)c.max_smem_optin - 1024) {
         auto kern = k_eval_poses<OV, FULL, F32POSE, true>;
