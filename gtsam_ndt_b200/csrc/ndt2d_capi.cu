@@ -276,6 +276,8 @@ int ndt2d_create_on_stream(int device, void *cuda_stream, ndt2d_matcher **out)
         }
         m->cfg.block_align_max = -1;
         if (const char *e = getenv("NDT2D_BLOCK_ALIGN_MAX")) m->cfg.block_align_max = atoi(e); // 0: always one warp per scan
+        m->cfg.align_help = -1;
+        if (const char *e = getenv("NDT2D_ALIGN_HELP")) m->cfg.align_help = atoi(e);             // 0: never, 1: always
         if (const char *e = getenv("NDT2D_CHUNK_SCANS")) {
             int v = atoi(e);
             if (v > 0) m->chunk_scans = v;
@@ -719,7 +721,7 @@ int ndt2d_point_terms(ndt2d_matcher *m, int level, const float *xy, int n, const
 }
 
 static int align_batch_device_impl(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, int nscans, int max_points,
-                                   const double *d_init, ndt2d_result *d_res, unsigned int *counter);
+                                   const double *d_init, ndt2d_result *d_res, unsigned int *counter, int batch_scans = 0);
 
 int ndt2d_align_batch_device(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, int nscans, int max_points,
                              const double *d_init, ndt2d_result *d_res)
@@ -727,8 +729,9 @@ int ndt2d_align_batch_device(ndt2d_matcher *m, const float *d_xy, const int64_t 
     return align_batch_device_impl(m, d_xy, d_offsets, nscans, max_points, d_init, d_res, nullptr);
 }
 
+// counter / batch_scans: set when this launch is one chunk of a pipelined host-buffer call of batch_scans scans
 static int align_batch_device_impl(ndt2d_matcher *m, const float *d_xy, const int64_t *d_offsets, int nscans, int max_points,
-                                   const double *d_init, ndt2d_result *d_res, unsigned int *counter)
+                                   const double *d_init, ndt2d_result *d_res, unsigned int *counter, int batch_scans)
 {
     if (!m) return NDT2D_EINVAL;
     if (!m->has_target) return fail(m, NDT2D_ENOTARGET, "no target set");
@@ -746,6 +749,7 @@ static int align_batch_device_impl(ndt2d_matcher *m, const float *d_xy, const in
     a.nscans = nscans;
     a.cap_points = align_cap_points(m, max_points);
     if (counter) a.counter = counter;
+    a.batch_scans = batch_scans;
     CK(m, launch_align(m->cfg, a, &m->launches));
     return NDT2D_OK;
 }
@@ -828,7 +832,7 @@ int ndt2d_align_batch(ndt2d_matcher *m, const float *xy, const int64_t *offsets,
         },
         [&](int s0, int s1, unsigned int *counter) -> int {
             return align_batch_device_impl(m, m->b_xy.as<float>(), m->b_off.as<int64_t>() + s0, s1 - s0, (int)maxn,
-                                           m->b_init.as<double>() + 3 * (size_t)s0, m->b_res.as<ndt2d_result>() + s0, counter);
+                                           m->b_init.as<double>() + 3 * (size_t)s0, m->b_res.as<ndt2d_result>() + s0, counter, nscans);
         });
 }
 
@@ -841,7 +845,7 @@ int ndt2d_align(ndt2d_matcher *m, const float *xy, int n, const double init[3], 
 
 static int align_ranges_device_impl(ndt2d_matcher *m, const void *d_ranges, int ranges_are_u16, int nscans, int nbeams,
                                     double angle_min, double angle_inc, float range_scale, float range_min, float range_max,
-                                    const double *d_init, ndt2d_result *d_res, unsigned int *counter);
+                                    const double *d_init, ndt2d_result *d_res, unsigned int *counter, int batch_scans = 0);
 
 int ndt2d_align_batch_ranges_device(ndt2d_matcher *m, const void *d_ranges, int ranges_are_u16, int nscans, int nbeams,
                                     double angle_min, double angle_inc, float range_scale, float range_min, float range_max,
@@ -853,7 +857,7 @@ int ndt2d_align_batch_ranges_device(ndt2d_matcher *m, const void *d_ranges, int 
 
 static int align_ranges_device_impl(ndt2d_matcher *m, const void *d_ranges, int ranges_are_u16, int nscans, int nbeams,
                                     double angle_min, double angle_inc, float range_scale, float range_min, float range_max,
-                                    const double *d_init, ndt2d_result *d_res, unsigned int *counter)
+                                    const double *d_init, ndt2d_result *d_res, unsigned int *counter, int batch_scans)
 {
     if (!m) return NDT2D_EINVAL;
     if (!m->has_target) return fail(m, NDT2D_ENOTARGET, "no target set");
@@ -880,6 +884,7 @@ static int align_ranges_device_impl(ndt2d_matcher *m, const void *d_ranges, int 
     a.nscans = nscans;
     a.cap_points = cap;
     if (counter) a.counter = counter;
+    a.batch_scans = batch_scans;
     CK(m, launch_align(m->cfg, a, &m->launches));
     return NDT2D_OK;
 }
@@ -910,7 +915,7 @@ int ndt2d_align_batch_ranges(ndt2d_matcher *m, const void *ranges, int ranges_ar
         [&](int s0, int s1, unsigned int *counter) -> int {
             return align_ranges_device_impl(m, m->b_ranges.as<unsigned char>() + (size_t)s0 * nbeams * esz, ranges_are_u16,
                                             s1 - s0, nbeams, angle_min, angle_inc, range_scale, range_min, range_max,
-                                            m->b_init.as<double>() + 3 * (size_t)s0, m->b_res.as<ndt2d_result>() + s0, counter);
+                                            m->b_init.as<double>() + 3 * (size_t)s0, m->b_res.as<ndt2d_result>() + s0, counter, nscans);
         });
 }
 

@@ -558,6 +558,34 @@ __device__ __forceinline__ void apply_factors(const Factors &F, Partials &S)
     }
 }
 
+// Parked factors: the SPEC 4 factors of one (64-point step, cell) for all 32 lanes, written to shared memory by one warp and
+// applied by another in SPEC order (k_align_block's eight warps; the helper warps of k_align). FACTOR_WORDS u64 per lane,
+// word-major: a warp's store or load of one word is one conflict-free 256-byte row. o = base of the entry + lane.
+static constexpr int FACTOR_WORDS = 10; // e, c12[2], c45[2], c68[2], c3, c9, c7 pair
+static constexpr unsigned kFactorBytes = FACTOR_WORDS * 32 * sizeof(u64);
+__device__ __forceinline__ void park_factors(const Factors &X, u64 *o)
+{
+    o[0 * 32] = X.e;
+    o[1 * 32] = X.c12[0]; o[2 * 32] = X.c12[1];
+    o[3 * 32] = X.c45[0]; o[4 * 32] = X.c45[1];
+    o[5 * 32] = X.c68[0]; o[6 * 32] = X.c68[1];
+    o[7 * 32] = X.c3; o[8 * 32] = X.c9;
+    o[9 * 32] = pk(X.c7[0], X.c7[1]);
+}
+__device__ __forceinline__ void apply_parked(const u64 *o, Partials &S, int &cnt)
+{
+    Factors X;
+    X.e = o[0 * 32];
+    X.c12[0] = o[1 * 32]; X.c12[1] = o[2 * 32];
+    X.c45[0] = o[3 * 32]; X.c45[1] = o[4 * 32];
+    X.c68[0] = o[5 * 32]; X.c68[1] = o[6 * 32];
+    X.c3 = o[7 * 32]; X.c9 = o[8 * 32];
+    upk(o[9 * 32], X.c7[0], X.c7[1]);
+    // a contributing pair has e = exp(-h) with h < 30, never zero; a skipped pair has e = 0 exactly
+    cnt += (lo32(X.e) != 0.0f ? 1 : 0) + (hi32(X.e) != 0.0f ? 1 : 0);
+    apply_factors<true>(X, S);
+}
+
 // one cell for the lane's two points, accumulated into the lane's partials: acc_t = fma(e, c_t, acc_t)
 template <bool FULL>
 __device__ __forceinline__ void accumulate_cell(const Cell4 &cA, const Cell4 &cB, const PointPk &A, const PointPk &B, Partials &S,
@@ -838,9 +866,20 @@ __device__ __forceinline__ void accumulate_step(const LatticePk &G, Fetched<OV> 
 template <bool FULL, bool TR>
 __device__ __forceinline__ void finish_partials(const Partials &S, int cnt, int lane, Eval &E);
 
+// No helper warps (every caller but k_align<..., HELP>): the warp evaluates all its steps itself.
+struct NoHelp {
+    static constexpr bool on = false;
+    __device__ __forceinline__ unsigned own_steps(unsigned nsteps) const { return nsteps; }
+    __device__ __forceinline__ void finish(Partials &, int &, int) const {}
+};
+
 // TABLE: how L's records are stored (TABLE_DENSE / TABLE_GHASH / TABLE_SHASH), resolved in fetch().
-template <int OV, bool FULL, bool SMEM, int PIPE, bool TR = false, int TABLE = TABLE_DENSE, bool P64 = false>
-__device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E)
+// Help (SMEM, un-pipelined form only): the warp evaluates the first help.own_steps(steps) 64-point steps; help.finish()
+// then applies the factors of the remaining steps, computed and parked by other warps, in step order (HelpPlan in
+// ndt2d_align.cuh) - SPEC 4's summation order is kept, so the sums are the same bits.
+template <int OV, bool FULL, bool SMEM, int PIPE, bool TR = false, int TABLE = TABLE_DENSE, bool P64 = false, class Help = NoHelp>
+__device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, int n, const Pose32 &q, int lane, Eval &E,
+                                          const Help help = Help())
 {
     Partials S;
     S.s0 = S.s3 = S.s9 = 0ull;
@@ -881,13 +920,15 @@ __device__ __forceinline__ void eval_warp(const LevelDev &L, const float2 *pts, 
         // the staged scan is walked by its shared-window address: one register is loop counter and load address at once (as
         // pts[i] the compiler recomputed slot base + warp * capacity + i with two multiply-adds and a constant load per step)
         constexpr unsigned PB = P64 ? 16u : 8u;     // bytes per staged point
-        const unsigned s0 = (unsigned)__cvta_generic_to_shared(pts) + PB * (unsigned)lane, s1 = s0 + PB * (unsigned)npad;
+        const unsigned s0 = (unsigned)__cvta_generic_to_shared(pts) + PB * (unsigned)lane;
+        const unsigned s1 = s0 + PB * (Help::on ? 64u * help.own_steps((unsigned)npad >> 6) : (unsigned)npad);
 #pragma unroll kUnroll
         for (unsigned sa = s0; sa < s1; sa += 64u * PB) {
             Fetched<OV> cur;
             fetch<OV, SMEM, TABLE, P64, true>(cells, G, P, pts, n, (int)sa, cur);
             accumulate_step<OV, FULL>(G, cur, S, cnt);
         }
+        if (Help::on) help.finish(S, cnt, lane);
     } else {
 #pragma unroll kUnroll
         for (int i = lane; i < npad; i += 64) {

@@ -46,6 +46,7 @@ struct AlignArgs {
     const int32_t *pairs;
     const LevelDev *geo;
     int nscans;              // jobs: scans, or pairs in pairs mode
+    int batch_scans;         // scans of the whole API call when this launch is one chunk of it (0: nscans); kernel selection only
     int cap_points;          // shared-memory slot capacity in points (0: read scans from global memory)
     unsigned int *counter;   // work queue head, zeroed before launch
     int counter_is_zero;     // host side only: the caller guarantees *counter == 0 (no memset in launch_align)
@@ -55,7 +56,8 @@ struct LaunchCfg {
     int sm_count;
     int max_smem_optin;
     cudaStream_t stream;
-    int block_align_max;     // calls with at most this many scans use the block-per-scan align kernel (-1: 2 x SMs)
+    int block_align_max;     // calls with at most this many scans use the block-per-scan align kernel (-1: one resident wave of blocks)
+    int align_help;          // helper warps in k_align (K = 1, staged scans): 0 never, 1 always, -1 up to NDT2D_HELP_MAX_SCANS scans
 };
 
 // all launchers return the cudaError_t of the launch; *launches is incremented per kernel launched
@@ -118,7 +120,7 @@ struct PairFusedArgs {
 // fills cap_*, rmax, hslots, off_*, warp_bytes; returns false when the fused path cannot be used (smem_optin too small)
 bool pairs_fused_layout(PairFusedArgs &a, int64_t max_target_points, int64_t max_source_points, int smem_optin);
 cudaError_t launch_pairs_fused(const LaunchCfg &c, const PairFusedArgs &a, int64_t *launches);
-size_t align_smem_bytes(int cap_points); // dynamic shared memory per k_align block
+size_t align_smem_bytes(int cap_points, bool help = true); // dynamic shared memory per k_align block (help: with the helper-warp desks)
 // Publication of a shard's best hypothesis into every rank's exchange table (peer pointers, NVLink stores).
 struct PublishArgs {
     ndt2d_best *table[NDT2D_MAX_RANKS]; // table[r] = rank r's table as seen from this device (world entries used)

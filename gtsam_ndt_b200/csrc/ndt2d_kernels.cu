@@ -212,10 +212,12 @@ __global__ void __launch_bounds__(EVAL_THREADS, FULL ? EVAL_BLOCKS_FULL : NDT2D_
 // on configs[1], all bit-identical): 128 x 6: 20.46, 256 x 3: 20.32, 384 x 2: 20.22 (the same 24 warps in larger blocks: a block
 // holds its shared memory until its last warp has drained the queue), 160 x 4 (20 warps, 96 registers): 19.53, 320 x 2 (20
 // warps): 19.43, 256 x 2 (16 warps, 104 registers, the only point whose loop has no register copies): 19.17.
-#ifndef NDT2D_ALIGN_THREADS
-#define NDT2D_ALIGN_THREADS 128
+// ALIGN_THREADS (k_align's block size, NDT2D_ALIGN_THREADS) lives in ndt2d_align.cuh with the helper-warp machinery
+#ifndef NDT2D_HELP_MAX_SCANS
+#define NDT2D_HELP_MAX_SCANS 8192 // batches of at most this many scans run k_align with helper warps, when the handle leaves the choice open
+                                  // (tools/midsize_probe.py: -12 % at 1250-2500 scans, -5 % at 5000, +-0 at 10 000, +2 % at 20 000,
+                                  // +8 % at 65 536 - the helper form's point loop is 134 instructions against 129)
 #endif
-static constexpr int ALIGN_THREADS = NDT2D_ALIGN_THREADS;
 #ifndef NDT2D_ALIGN_MIN_BLOCKS
 #define NDT2D_ALIGN_MIN_BLOCKS 6
 #endif
@@ -231,7 +233,6 @@ static constexpr int ALIGN_MIN_BLOCKS = NDT2D_ALIGN_MIN_BLOCKS;
 // of the one-warp kernel. The LM logic is executed by every thread on the same shared-memory state (uniform).
 
 static constexpr int BLOCK_ALIGN_THREADS = 256; // 8 warps (18 warps, one round for 1080 points, measured no faster: the serial part dominates)
-static constexpr int FACTOR_WORDS = 10; // u64 per lane and (step, cell): e, c12[2], c45[2], c68[2], c3, c9, c7 pair
 
 template <int OV>
 __device__ __forceinline__ void eval_block(const LevelDev *L, const float2 *pts, int n, WarpState *ws, u64 *fac)
@@ -253,13 +254,7 @@ __device__ __forceinline__ void eval_block(const LevelDev *L, const float2 *pts,
             F.A.XY = local_xy(G, F.A.df, k);
             F.B.XY = local_xy(G, F.B.df, k);
             cell_factors<true>(F.cA[k], F.cB[k], F.A, F.B, X, c);
-            u64 *o = fac + ((size_t)(step * NC + k) * FACTOR_WORDS) * 32 + lane;
-            o[0 * 32] = X.e;
-            o[1 * 32] = X.c12[0]; o[2 * 32] = X.c12[1];
-            o[3 * 32] = X.c45[0]; o[4 * 32] = X.c45[1];
-            o[5 * 32] = X.c68[0]; o[6 * 32] = X.c68[1];
-            o[7 * 32] = X.c3; o[8 * 32] = X.c9;
-            o[9 * 32] = pk(X.c7[0], X.c7[1]);
+            park_factors(X, fac + ((size_t)(step * NC + k) * FACTOR_WORDS) * 32 + lane);
         }
     }
     __syncthreads();
@@ -270,19 +265,7 @@ __device__ __forceinline__ void eval_block(const LevelDev *L, const float2 *pts,
 #pragma unroll
         for (int k = 0; k < 2; ++k) S.s12[k] = S.s45[k] = S.s68[k] = 0ull;
         int cnt = 0;
-        for (int e = 0; e < nsteps * NC; ++e) {
-            const u64 *o = fac + ((size_t)e * FACTOR_WORDS) * 32 + lane;
-            Factors X;
-            X.e = o[0 * 32];
-            X.c12[0] = o[1 * 32]; X.c12[1] = o[2 * 32];
-            X.c45[0] = o[3 * 32]; X.c45[1] = o[4 * 32];
-            X.c68[0] = o[5 * 32]; X.c68[1] = o[6 * 32];
-            X.c3 = o[7 * 32]; X.c9 = o[8 * 32];
-            upk(o[9 * 32], X.c7[0], X.c7[1]);
-            // a contributing pair has e = exp(-h) with h < 30, never zero; a skipped pair has e = 0 exactly
-            cnt += (lo32(X.e) != 0.0f ? 1 : 0) + (hi32(X.e) != 0.0f ? 1 : 0);
-            apply_factors<true>(X, S);
-        }
+        for (int e = 0; e < nsteps * NC; ++e) apply_parked(fac + ((size_t)e * FACTOR_WORDS) * 32 + lane, S, cnt);
         Eval E;
         finish_partials<true, true>(S, cnt, lane, E);
         ws->t[E.slot] = E.v[0];
@@ -325,16 +308,30 @@ __global__ void __launch_bounds__(BLOCK_ALIGN_THREADS) k_align_block(const __gri
 // RANGES: the scan arrives as LaserScan ranges and is converted in the staging step (SPEC 8).
 // PAIRS (ndt2d_align_pairs): job p aligns scan a.pairs[2p+1] to target slot a.pairs[2p]; the target's levels are
 // a.geo[slot * nlevels + l], whose cell tables are hash tables built by k_pairs_build.
-template <int OV, bool STAGED, bool RANGES, bool PAIRS = false>
+// HELP (K = 1, scans staged in shared memory, dense table): warps that find the queue empty help the warps of their block that
+// still hold a scan (ndt2d_align.cuh); the launch's tail and batches that do not fill the GPU finish sooner, same bits.
+template <int OV, bool STAGED, bool RANGES, bool PAIRS = false, bool HELP = false>
 __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_BLOCKS : 1) k_align(const __grid_constant__ AlignArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    static_assert(!HELP || (OV == 0 && (STAGED || RANGES) && !PAIRS), "helpers park one cell's factors per step and read the owner's staged scan");
+    unsigned char *smem_raw = align_smem();
     constexpr bool SM = STAGED || RANGES;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per-warp slot of cap points (a multiple of 64), after the warp states
+    // per-warp slot of cap points (a multiple of 64), after the warp states (and the help desks)
     WarpState *ws = reinterpret_cast<WarpState *>(smem_raw) + warp;
-    float2 *slot = reinterpret_cast<float2 *>(smem_raw + (ALIGN_THREADS / 32) * sizeof(WarpState)) + (size_t)warp * a.cap_points;
+    float2 *slot = reinterpret_cast<float2 *>(HELP ? help_slots() : smem_raw + kAlignWarps * sizeof(WarpState)) + (size_t)warp * a.cap_points;
     const float2 far = make_float2(1e18f, 1e18f);
+    if (HELP) {
+        HelpDesk *d = help_desk(warp);
+        if (lane == 0) {
+            d->post = d->cur = 0u;
+            d->active = 1u;          // every warp may own scans until it has seen the queue empty itself
+            d->slot_bytes = (unsigned)a.cap_points * (unsigned)sizeof(float2);
+            d->level = d->n = 0;
+        }
+        if (lane < 7) { d->helper[lane] = kNoHelper; d->done[lane] = 0u; }
+        __syncthreads();
+    }
 
 #if NDT2D_QUEUE == 1
     // static ranges (tuning experiment): each block owns a contiguous range of scans
@@ -344,17 +341,33 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
     if (threadIdx.x == 0) s_next = q_lo;
     __syncthreads();
 #endif
+    bool first_job = true;
     for (;;) {
         unsigned job = 0;
 #if NDT2D_QUEUE == 1
         if (lane == 0) job = atomicAdd(&s_next, 1u);
         job = __shfl_sync(FULL_MASK, job, 0);
-        if (job >= q_hi) break;
+        const bool drained = job >= q_hi;
 #else
-        if (lane == 0) job = atomicAdd(a.counter, 1u);
-        job = __shfl_sync(FULL_MASK, job, 0);
-        if (job >= (unsigned)a.nscans) break;
+        if (HELP && first_job) {
+            // a warp's first scan is assigned statically, warp w of every block before warp w + 1 of any: a batch that does
+            // not fill the GPU is spread over the blocks, and the warps left without a scan are helpers next to an owner
+            job = (unsigned)warp * gridDim.x + blockIdx.x;
+            first_job = false;
+        } else {
+            if (lane == 0) job = atomicAdd(a.counter, 1u);
+            job = __shfl_sync(FULL_MASK, job, 0);
+            if (HELP) job += gridDim.x * (unsigned)kAlignWarps;
+        }
+        const bool drained = job >= (unsigned)a.nscans;
 #endif
+        if (drained) {
+            if (HELP) {
+                if (lane == 0) sts_volatile(&help_desk(warp)->active, 0u);   // releases this warp's helpers
+                help_others<OV>(a.lv);
+            }
+            break;
+        }
         ScanView v;
         v.pts = slot; v.n = 0;
         if (RANGES) {
@@ -404,7 +417,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
         __syncwarp();
         int evals = 0, status = NDT2D_NO_OVERLAP;
         const LevelDev *levels = PAIRS ? a.geo + (size_t)__ldg(a.pairs + 2 * (size_t)job) * a.nlevels : a.lv;
-        for (int l = 0; l < a.nlevels; ++l) status = align_level<OV, SM, PAIRS ? TABLE_GHASH : TABLE_DENSE>(levels + l, a.prm, v, ws, evals);
+        for (int l = 0; l < a.nlevels; ++l) status = align_level<OV, SM, PAIRS ? TABLE_GHASH : TABLE_DENSE, HELP>(levels + l, a.prm, v, ws, evals, l);
         if (lane == 0) write_result(*ws, evals, status, a.res + job);
         __syncwarp(); // the slot is rewritten by the next job
     }
@@ -595,17 +608,17 @@ cudaError_t launch_eval_poses(const LaunchCfg &c, const LevelDev &L, const float
 }
 
 // dynamic shared memory of one k_align block whose warps stage scans of up to cap_points points (0: no staging)
-size_t align_smem_bytes(int cap_points)
+size_t align_smem_bytes(int cap_points, bool help)
 {
     return (cap_points > 0 ? (size_t)cap_points * sizeof(float2) : 0) * (ALIGN_THREADS / 32) +
-           (ALIGN_THREADS / 32) * sizeof(WarpState);
+           (ALIGN_THREADS / 32) * (sizeof(WarpState) + (help ? sizeof(HelpDesk) : 0));
 }
 
-template <int OV, bool STAGED, bool RANGES, bool PAIRS = false>
+template <int OV, bool STAGED, bool RANGES, bool PAIRS = false, bool HELP = false>
 static cudaError_t launch_align_t(const LaunchCfg &c, const AlignArgs &a)
 {
-    auto kern = k_align<OV, STAGED, RANGES, PAIRS>;
-    size_t smem = align_smem_bytes((STAGED || RANGES) ? a.cap_points : 0);
+    auto kern = k_align<OV, STAGED, RANGES, PAIRS, HELP>;
+    size_t smem = align_smem_bytes((STAGED || RANGES) ? a.cap_points : 0, HELP);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -624,7 +637,9 @@ static cudaError_t launch_align_t(const LaunchCfg &c, const AlignArgs &a)
 #ifdef NDT2D_PAIRS_BLOCKS_PER_SM
     if (PAIRS && per_sm > NDT2D_PAIRS_BLOCKS_PER_SM) per_sm = NDT2D_PAIRS_BLOCKS_PER_SM; // fewer tables in flight: L2 residency experiment
 #endif
-    int grid = grid_for(a.nscans, ALIGN_THREADS / 32, c.sm_count, per_sm);
+    // HELP: one block per scan while blocks are free (its other warps start as helpers); the first scans are dealt out
+    // warp 0 of every block first
+    int grid = grid_for(a.nscans, HELP ? 1 : ALIGN_THREADS / 32, c.sm_count, per_sm);
     kern<<<grid, ALIGN_THREADS, smem, c.stream>>>(a);
     return cudaGetLastError();
 }
@@ -640,7 +655,8 @@ cudaError_t launch_align(const LaunchCfg &c, const AlignArgs &a, int64_t *launch
     const bool ranges = (a.xy == nullptr);
     const bool staged = a.cap_points > 0;
     // few scans: latency matters, not throughput - one block per scan (k_align_block) if its factor buffer fits
-    if (!ranges && staged && !a.pairs && a.nscans <= (c.block_align_max >= 0 ? c.block_align_max : 2 * c.sm_count)) {
+    // (midsize_probe: the block form wins up to ~1000 scans on a 148-SM part, four resident blocks per SM)
+    if (!ranges && staged && !a.pairs && a.nscans <= (c.block_align_max >= 0 ? c.block_align_max : 6 * c.sm_count)) {
         const int NC = a.prm.overlap ? 4 : 1;
         const size_t smem = sizeof(WarpState) + (size_t)a.cap_points * sizeof(float2) +
                             (size_t)(a.cap_points / 64) * NC * FACTOR_WORDS * 32 * sizeof(u64);
@@ -666,8 +682,11 @@ cudaError_t launch_align(const LaunchCfg &c, const AlignArgs &a, int64_t *launch
         if (ranges) return launch_align_t<1, true, true>(c, a);
         return staged ? launch_align_t<1, true, false>(c, a) : launch_align_t<1, false, false>(c, a);
     }
-    if (ranges) return launch_align_t<0, true, true>(c, a);
-    return staged ? launch_align_t<0, true, false>(c, a) : launch_align_t<0, false, false>(c, a);
+    // K = 1, scans in shared memory: the helper-warp form (c.align_help: 0 never, 1 always, -1 = batches whose tail matters)
+    const bool help = c.align_help > 0 || (c.align_help < 0 && (a.batch_scans > 0 ? a.batch_scans : a.nscans) <= NDT2D_HELP_MAX_SCANS);
+    if (ranges) return help ? launch_align_t<0, true, true, false, true>(c, a) : launch_align_t<0, true, true>(c, a);
+    if (staged) return help ? launch_align_t<0, true, false, false, true>(c, a) : launch_align_t<0, true, false>(c, a);
+    return launch_align_t<0, false, false>(c, a);
 }
 
 cudaError_t launch_topk(const LaunchCfg &c, const double *d_scores, int64_t nhyp, int k, int64_t *d_idx, double *d_val,

@@ -348,6 +348,54 @@ def test_block_and_warp_align_kernels_agree(mods, small_world, cfg, monkeypatch)
     assert out["warp"].tobytes() == out["block"].tobytes() == ro.tobytes()
 
 
+@pytest.mark.parametrize("cfg", [dict(res=[0.5]), dict(res=[2.0, 1.0, 0.5]), dict(res=[0.25], reps=40), dict(res=[1.0, 0.5], reps=150)])
+def test_helper_warps_leave_every_bit_unchanged(mods, small_world, cfg, monkeypatch):
+    """k_align with helper warps (NDT2D_ALIGN_HELP=1: warps that find the queue empty compute the factors of the last steps
+    of a block-mate's evaluation) against the same kernel without them and against the oracle: ragged scans incl. an empty
+    and a five-point one, one level and pyramids, batches smaller than the grid (every owner has three helpers from the
+    start), larger than one wave of blocks (helpers appear as block-mates finish) and LaserScan input."""
+    from gtsam_ndt_b200 import synth
+    g, oracle = mods
+    base = [s[:: 1 + i % 3][: len(s) - 7 * i] for i, s in enumerate(small_world["scans"])] + [np.zeros((0, 2), np.float32), small_world["scans"][0][:5]]
+    binit = np.vstack([small_world["init"], small_world["init"][:2]])
+    reps = cfg.get("reps", 1)
+    scans = base * reps
+    init = np.tile(binit, (reps, 1)) + (np.arange(len(scans)) % 7)[:, None] * np.array([0.004, -0.003, 0.0005])
+    xy, off = synth.pack(scans)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NDT2D_BLOCK_ALIGN_MAX", "0")
+        monkeypatch.setenv("NDT2D_ALIGN_HELP", mode)
+        m = g.NdtMatcher2D(cfg["res"])
+        m.set_target(small_world["map_xy"])
+        out[mode] = m.align_batch(xy, off, init)
+        m.close()
+    assert out["0"].tobytes() == out["1"].tobytes()
+    if reps == 1:
+        o = oracle.Oracle(cfg["res"])
+        o.set_target(small_world["map_xy"])
+        assert o.align_batch(xy, off, init).tobytes() == out["1"].tobytes()
+    assert out["1"]["iterations"].max() > out["1"]["iterations"].min()        # unequal scans: some warps do turn helper
+
+
+def test_helper_warps_ranges_input(mods, small_world, monkeypatch):
+    """The LaserScan form of the same check (the helpers read the owner's converted points)."""
+    from gtsam_ndt_b200 import synth
+    g, _ = mods
+    sc = synth.SCAN_1080
+    ranges, poses = synth.scans(37, traj_len=600, first=3, step=13, **sc)
+    init = poses + synth.uniform3(37) * np.array([0.05, 0.05, np.radians(0.5)])
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NDT2D_ALIGN_HELP", mode)
+        m = g.NdtMatcher2D([1.0, 0.5])
+        m.set_target(small_world["map_xy"])
+        out[mode] = m.align_batch_ranges(ranges, sc["angle_min"], sc["angle_inc"], init, range_scale=1.0)
+        m.close()
+    assert out["0"].tobytes() == out["1"].tobytes()
+    assert (out["1"]["status"] != g.NO_OVERLAP).any()
+
+
 def _between(a, b):
     c, s_ = math.cos(a[2]), math.sin(a[2])
     dx, dy = b[0] - a[0], b[1] - a[1]
