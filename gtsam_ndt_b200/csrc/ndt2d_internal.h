@@ -56,7 +56,7 @@ struct LaunchCfg {
     int sm_count;
     int max_smem_optin;
     cudaStream_t stream;
-    int block_align_max;     // calls with at most this many scans use the block-per-scan align kernel (-1: one resident wave of blocks)
+    int block_align_max;     // calls with at most this many scans use the block-per-scan align kernel (-1: 8 x SMs)
     int align_help;          // helper warps in k_align (K = 1, staged scans): 0 never, 1 always, -1 up to NDT2D_HELP_MAX_SCANS scans
 };
 

@@ -228,11 +228,16 @@ static constexpr int ALIGN_MIN_BLOCKS = NDT2D_ALIGN_MIN_BLOCKS;
 // ------------------------------------------------------------------------------------------------
 // With one warp per scan an evaluation is 17 dependent (gather, compute) steps, ~9 us; a lone align is latency, not
 // throughput. Here the eight warps of a block compute the SPEC 4 factors (e, c1..c9) of different 64-point steps at
-// the same time and park them in shared memory; warp 0 then applies them to the 64 partial sums in the order SPEC 4
-// prescribes (increasing point index, cell order within a point), so the sums - and everything after - are the bits
-// of the one-warp kernel. The LM logic is executed by every thread on the same shared-memory state (uniform).
+// the same time and park them in shared memory; they are then applied to the 64 partial sums in the order SPEC 4
+// prescribes (increasing point index, cell order within a point) - by five warps, each owning whole accumulators - so the
+// sums, and everything after, are the bits of the one-warp kernel. The LM logic is executed by every thread on the same
+// shared-memory state (uniform).
 
-static constexpr int BLOCK_ALIGN_THREADS = 256; // 8 warps (18 warps, one round for 1080 points, measured no faster: the serial part dominates)
+#ifndef NDT2D_BLOCK_ALIGN_THREADS
+#define NDT2D_BLOCK_ALIGN_THREADS 256
+#endif
+static constexpr int BLOCK_ALIGN_THREADS = NDT2D_BLOCK_ALIGN_THREADS; // at least 5 warps (the second half of eval_block)
+static_assert(BLOCK_ALIGN_THREADS >= 160 && BLOCK_ALIGN_THREADS % 32 == 0, "eval_block applies the factors with five warps");
 
 template <int OV>
 __device__ __forceinline__ void eval_block(const LevelDev *L, const float2 *pts, int n, WarpState *ws, u64 *fac)
@@ -258,18 +263,53 @@ __device__ __forceinline__ void eval_block(const LevelDev *L, const float2 *pts,
         }
     }
     __syncthreads();
-    if (warp == 0) {
-        Partials S;
-        S.s0 = S.s3 = S.s9 = 0ull;
-        S.s7[0] = S.s7[1] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) S.s12[k] = S.s45[k] = S.s68[k] = 0ull;
-        int cnt = 0;
-        for (int e = 0; e < nsteps * NC; ++e) apply_parked(fac + ((size_t)e * FACTOR_WORDS) * 32 + lane, S, cnt);
-        Eval E;
-        finish_partials<true, true>(S, cnt, lane, E);
-        ws->t[E.slot] = E.v[0];
-        if (lane == 0) ws->tcount = E.count;
+    // Second half: the parked factors are applied in SPEC order - but SPEC 4 orders the updates of ONE accumulator; the ten
+    // accumulators of a partial are independent chains. Five warps each take the accumulators that end in the same sums
+    // (warp 0: T0 T3 T9 and the count; warps 1-3: the per-point pairs (T1,T2) (T4,T5) (T6,T8); warp 4: T7), widen to f64
+    // and run SPEC 4's butterfly for their sums: the serial tail of an evaluation is a fifth of what one warp would need.
+    if (warp < 5) {
+        const int ne = nsteps * NC;
+        const u64 *o = fac + lane;
+        if (warp == 0) {
+            u64 s0 = 0ull, s3 = 0ull, s9 = 0ull;
+            int cnt = 0;
+            for (int e = 0; e < ne; ++e, o += FACTOR_WORDS * 32) {
+                const u64 ee = o[0 * 32];
+                // a contributing pair has e = exp(-h) with h < 30, never zero; a skipped pair has e = 0 exactly
+                cnt += (lo32(ee) != 0.0f ? 1 : 0) + (hi32(ee) != 0.0f ? 1 : 0);
+                add2_acc(s0, ee);
+                fma2_acc(s3, ee, o[7 * 32]);
+                fma2_acc(s9, ee, o[8 * 32]);
+            }
+            const double t0 = warp_sum((double)lo32(s0) + (double)hi32(s0));
+            const double t3 = warp_sum((double)lo32(s3) + (double)hi32(s3));
+            const double t9 = warp_sum((double)lo32(s9) + (double)hi32(s9));
+            cnt = __reduce_add_sync(FULL_MASK, cnt);
+            if (lane == 0) { ws->t[0] = t0; ws->t[3] = t3; ws->t[9] = t9; ws->tcount = cnt; }
+        } else if (warp < 4) {
+            const int w0 = 2 * warp - 1;                      // words (1,2) (3,4) (5,6): the pair of point A, of point B
+            u64 a = 0ull, b = 0ull;
+            for (int e = 0; e < ne; ++e, o += FACTOR_WORDS * 32) {
+                const u64 ee = o[0 * 32];
+                fma2_acc(a, o[w0 * 32], bc(lo32(ee)));
+                fma2_acc(b, o[(w0 + 1) * 32], bc(hi32(ee)));
+            }
+            const double tl = warp_sum((double)lo32(a) + (double)lo32(b));
+            const double th = warp_sum((double)hi32(a) + (double)hi32(b));
+            const int il = warp == 1 ? 1 : warp == 2 ? 4 : 6, ih = warp == 1 ? 2 : warp == 2 ? 5 : 8;
+            if (lane == 0) { ws->t[il] = tl; ws->t[ih] = th; }
+        } else {
+            float a = 0.0f, b = 0.0f;
+            for (int e = 0; e < ne; ++e, o += FACTOR_WORDS * 32) {
+                const u64 ee = o[0 * 32];
+                float cA, cB;
+                upk(o[9 * 32], cA, cB);
+                a = __fmaf_rn(lo32(ee), cA, a);
+                b = __fmaf_rn(hi32(ee), cB, b);
+            }
+            const double t7 = warp_sum((double)a + (double)b);
+            if (lane == 0) ws->t[7] = t7;
+        }
     }
     __syncthreads();
 }
@@ -655,8 +695,8 @@ cudaError_t launch_align(const LaunchCfg &c, const AlignArgs &a, int64_t *launch
     const bool ranges = (a.xy == nullptr);
     const bool staged = a.cap_points > 0;
     // few scans: latency matters, not throughput - one block per scan (k_align_block) if its factor buffer fits
-    // (midsize_probe: the block form wins up to ~1000 scans on a 148-SM part, four resident blocks per SM)
-    if (!ranges && staged && !a.pairs && a.nscans <= (c.block_align_max >= 0 ? c.block_align_max : 6 * c.sm_count)) {
+    // (tools/midsize_probe.py: the block form wins up to ~1250 scans on a 148-SM part, four resident blocks per SM)
+    if (!ranges && staged && !a.pairs && a.nscans <= (c.block_align_max >= 0 ? c.block_align_max : 8 * c.sm_count)) {
         const int NC = a.prm.overlap ? 4 : 1;
         const size_t smem = sizeof(WarpState) + (size_t)a.cap_points * sizeof(float2) +
                             (size_t)(a.cap_points / 64) * NC * FACTOR_WORDS * 32 * sizeof(u64);
