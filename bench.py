@@ -214,6 +214,24 @@ def ncu_pipes(kernel_key):
         return None
 
 
+def instruction_mix(kernel_key, kernel_ms, clocks, sm_count, evals, npts):
+    """How close the point loop is to the speed of light of its own instruction mix. tools/mix_probe.py issues the loop's
+    instruction counts from independent register chains (no memory, no dependencies): its cycles per body per scheduler are
+    the floor any schedule of the mix has (`mix_floor_cycles`: classes grouped / interleaved). The loop's actual cycles per
+    64-point step per scheduler = live kernel time x clock x schedulers x the loop's share of the kernel's PC samples / steps."""
+    try:
+        e = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel_key]
+        floor, share = e["mix_floor_cycles"], e["loop_sample_share"]
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        steps = evals * ((npts + 63) // 64)
+        cyc = kernel_ms * 1e-3 * mhz * 1e6 * sm_count * 4 * share / steps
+        return {"loop_cycles_per_step_per_scheduler": cyc, "mix_floor_cycles": floor, "frac_of_grouped_floor": floor[0] / cyc,
+                "frac_of_interleaved_floor": floor[1] / cyc, "loop_sample_share": share,
+                "note": "floor: profiles/r3m_mix_probe.txt (tools/mix_probe.py); share: profiles/r3k_k_align_loop_stalls.txt"}
+    except Exception:
+        return None
+
+
 def ncu_traffic_sweep(args, hyps):
     try:
         tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -601,7 +619,8 @@ def run_native(args):
                                        "see DESIGN.md section 5). The ncu counters are per-configuration constants from profiles/traffic.json "
                                        "(its `commit` field names the build they were captured on); the times are measured live",
                          "evals_per_launch": float(iters.sum()), "bytes_per_eval": eval_bytes(npts, K),
-                         "evals_per_s": total_evals_per_step * args.steps / (ms / 1e3), "gather_pipe": gp, "pipes": ncu_pipes(key)},
+                         "evals_per_s": total_evals_per_step * args.steps / (ms / 1e3), "gather_pipe": gp, "pipes": ncu_pipes(key),
+                         "instruction_mix": instruction_mix(key, kernel_ms, clocks, sm_count, float(iters.sum()), npts)},
             "mean_iterations": float(iters.mean()), "status_counts": np.bincount(res["status"], minlength=4).tolist(),
             "map_build_ms": build_ms, "clocks": clocks,
         }

@@ -43,6 +43,9 @@ def main():
         e = {k: v[m] for k, m in FIELDS.items() if m in v}
         e["dram_bytes"] = e.get("dram_read", 0.0) + e.get("dram_write", 0.0)
         e.update(source=f"profiles/{tag}_{suffix}", commit=commit, spec="v4", note=note)
+        for keep in ("mix_floor_cycles", "loop_sample_share", "mix_note"):   # from tools/mix_probe.py / tools/srcstall.py, not from a summary
+            if keep in tab.get(key, {}):
+                e[keep] = tab[key][keep]
         tab[key] = e
         print(key, {k: e[k] for k in ("dram_bytes", "l1tex_sectors", "kernel_ms_under_ncu") if k in e})
     json.dump(tab, open(path, "w"), indent=1)
