@@ -24,6 +24,9 @@
 #ifndef NDT2D_ESEL
 #define NDT2D_ESEL 1 // SPEC 4's pair tests, select and count written in PTX (see select_count)
 #endif
+#ifndef NDT2D_EXP_LEA
+#define NDT2D_EXP_LEA 1 // expneg2: the 2^-n factor from a shift-add on the integer pipe instead of an IMAD (see expneg2)
+#endif
 #ifndef NDT2D_LDMODE
 #define NDT2D_LDMODE 4 // cell gather instruction variant; 4 = ld.global.nc.L1::no_allocate, one 256-bit load (measured best:
                        // a gathered record is rarely reused before L1 evicts it, and not allocating spares the fill bandwidth)
@@ -216,6 +219,28 @@ __device__ __forceinline__ float expneg(float h)
 __device__ __forceinline__ u64 expneg2(u64 nh)
 {
     const u64 MAGIC = bc(12582912.0f);
+#if NDT2D_EXP_LEA
+    // The magic sum taken with the sign of n flipped: t = M - n (fma(-h, L, M); exact mirror of M + n, M's mantissa is even), so
+    // that the bits of t are 0x4B400000 - n and 2^-n's bit pattern 0x3F800000 - (n << 23) is 0x3F800000 + (bits(t) << 23)
+    // (0x4B400000 << 23 vanishes mod 2^32): one shift-add on the integer pipe per value, where n * -0x800000 + 0x3F800000 was
+    // an IMAD - two cycles of the FMA pipe, the loop's busiest unit (tools/mix_probe.py) - plus a constant move per step.
+    u64 t = fma2(nh, bc(1.44269502f), MAGIC);
+    u64 nf = sub2(t, MAGIC);                       // -n, exactly
+    float t0, t1;
+    upk(t, t0, t1);
+    unsigned s0, s1;
+    asm("{\n\t.reg .b32 x;\n\tshl.b32 x, %1, 23;\n\tadd.s32 %0, x, 0x3F800000;\n\t}" : "=r"(s0) : "r"(__float_as_int(t0)));
+    asm("{\n\t.reg .b32 x;\n\tshl.b32 x, %1, 23;\n\tadd.s32 %0, x, 0x3F800000;\n\t}" : "=r"(s1) : "r"(__float_as_int(t1)));
+    u64 y = fma2(nf, bc(-0.693145752f), nh);       // -h + n ln2: fma(-n, -C, y) == fma(n, C, y)
+    y = fma2(nf, bc(-1.42860677e-6f), y);
+    u64 p = fma2(bc(1.38888889e-3f), y, bc(8.33333333e-3f));
+    p = fma2(p, y, bc(4.16666667e-2f));
+    p = fma2(p, y, bc(1.66666667e-1f));
+    p = fma2(p, y, bc(0.5f));
+    p = fma2(p, y, bc(1.0f));
+    p = fma2(p, y, bc(1.0f));
+    return mul2(p, pk(__int_as_float((int)s0), __int_as_float((int)s1)));
+#else
     u64 t = fma2(nh, bc(-1.44269502f), MAGIC);
     u64 nf = sub2(t, MAGIC);
     float t0, t1;
@@ -230,6 +255,7 @@ __device__ __forceinline__ u64 expneg2(u64 nh)
     p = fma2(p, y, bc(1.0f));
     p = fma2(p, y, bc(1.0f));
     return mul2(p, pk(__int_as_float(0x3F800000 - n0 * 0x800000), __int_as_float(0x3F800000 - n1 * 0x800000)));
+#endif
 }
 
 // ---- SPEC 4: pose and point -----------------------------------------------------------------------------
