@@ -227,7 +227,7 @@ def instruction_mix(kernel_key, kernel_ms, clocks, sm_count, evals, npts):
         cyc = kernel_ms * 1e-3 * mhz * 1e6 * sm_count * 4 * share / steps
         return {"loop_cycles_per_step_per_scheduler": cyc, "mix_floor_cycles": floor, "frac_of_grouped_floor": floor[0] / cyc,
                 "frac_of_interleaved_floor": floor[1] / cyc, "loop_sample_share": share,
-                "note": "floor: profiles/r3m_mix_probe.txt (tools/mix_probe.py); share: profiles/r3k_k_align_loop_stalls.txt"}
+                "note": "floor: profiles/r3n_mix_probe.txt (tools/mix_probe.py); share: profiles/r3k_k_align_loop_stalls.txt"}
     except Exception:
         return None
 
