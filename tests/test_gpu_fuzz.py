@@ -27,8 +27,10 @@ def test_random_configuration_is_bit_identical(small_world, seed, monkeypatch):
     from gtsam_ndt_b200 import synth
     rng = np.random.default_rng(1000 + seed)
     res, prm, grid = _config(rng, seed)
-    # small batches normally run the block-per-scan kernel; half of the seeds force the one-warp-per-scan kernel instead
+    # small batches normally run the block-per-scan kernel; half of the seeds force the one-warp-per-scan kernel instead,
+    # with (K = 1 only) and without its helper warps
     monkeypatch.setenv("NDT2D_BLOCK_ALIGN_MAX", "0" if (seed + seed // 2) % 2 else "100000")
+    monkeypatch.setenv("NDT2D_ALIGN_HELP", "1" if seed % 4 < 2 else "0")
     m, o = g.NdtMatcher2D(res, **prm), oracle.Oracle(res, **prm)
     if grid:
         m.set_grid(*grid); o.set_grid(*grid)
