@@ -75,6 +75,9 @@ def parse_args():
                                                   "sweep,pyramid,prior2,odometry,dense,config0,precision")
     ap.add_argument("--world", default="room", choices=["room", "dense"],
                     help="synthetic world of the scan2map workload: the SURVEY 8(d) room (14 k valid map cells) or the cluttered dense world (> 300 k)")
+    ap.add_argument("--relay", default="auto", choices=["auto", "off"],
+                    help="e2e on several GPUs: auto = ranks whose host-to-device rate is lower than a peer's relay a share of their input "
+                         "through that peer's GPU (ndt2d_set_upload_relay); off = every rank uses its own PCIe link only")
     ap.add_argument("--pinned", default="default", choices=["default", "wc"],
                     help="e2e input buffer: ordinary pinned memory, or write-combined pinned memory (ndt2d_host_alloc_flags)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the NUMA node of its GPU")
@@ -493,6 +496,44 @@ def h2d_bandwidth(ctx, h_tensor, reps=3):
     return ctx.gather_floats(gbs)
 
 
+def plan_upload_relay(ctx, m, gbs, min_ratio=1.15):
+    """Upload relay between the ranks of the job (ndt2d_set_upload_relay): with every rank copying its step input at the same
+    time, the box's host side does not feed all PCIe links alike (gbs = measured GB/s per rank). The slowest rank is paired
+    with the fastest, the second slowest with the second fastest, ...; a pair whose rates differ by more than min_ratio moves
+    the share x = (fast - slow) / (fast + slow) of the slow rank's chunks onto the fast rank's link (both links then finish
+    together) and from that GPU over NVLink. Single node: a rank's device index is its rank. Returns the plan (same on
+    every rank) or None."""
+    if ctx.world < 2 or not gbs or len(gbs) != ctx.world:
+        return None
+    order = sorted(range(ctx.world), key=lambda r: gbs[r])
+    pairs = {}
+    for i in range(ctx.world // 2):
+        slow, fast = order[i], order[-1 - i]
+        if gbs[fast] > min_ratio * gbs[slow]:
+            pairs[slow] = (fast, (gbs[fast] - gbs[slow]) / (gbs[fast] + gbs[slow]))
+    if not pairs:
+        return None
+    if ctx.rank in pairs:
+        fast, x = pairs[ctx.rank]
+        m.set_upload_relay(fast, min(max(x, 0.05), 0.6))
+    return {"pairs": {str(k): {"via_rank": v[0], "fraction": round(v[1], 3)} for k, v in pairs.items()},
+            "note": "share of a slow rank's input chunks copied host -> the paired rank's GPU (its PCIe link) -> NVLink peer copy"}
+
+
+def refine_upload_relay(ctx, m, plan, t_ms):
+    """One calibration step: t_ms = every rank's e2e step time with the planned relay. A slow rank's time scales with the
+    share 1 - x it still copies itself, its partner's with 1 + x; move x to where the two meet."""
+    for slow, v in plan["pairs"].items():
+        fast, x = v["via_rank"], v["fraction"]
+        ts, tf = t_ms[int(slow)], t_ms[fast]
+        x2 = min(max(x + (ts - tf) / (ts / (1.0 - x) + tf / (1.0 + x)), 0.05), 0.6)
+        v["first_fraction"], v["fraction"] = x, round(x2, 3)
+        if ctx.rank == int(slow):
+            m.set_upload_relay(fast, x2)
+    plan["note"] += "; fractions refined once from the per-rank step times of a calibration run"
+    return plan
+
+
 def run_native(args):
     import gtsam_ndt_b200 as g
     from gtsam_ndt_b200 import synth
@@ -561,7 +602,7 @@ def run_native(args):
             h_in = pin(ranges)
             nbytes = h_in.numel() * 4 + h_init.numel() * 8
             fn = lambda: m.align_batch_ranges(h_in.numpy(), sc["angle_min"], sc["angle_inc"], h_init.numpy(), range_scale=1.0, out=res_view)
-        if mode == args.input:
+        if mode == args.input and h2d_gbs is None:
             h2d_gbs = h2d_bandwidth(ctx, h_in)
         for _ in range(args.warmup):
             fn()
@@ -575,13 +616,23 @@ def run_native(args):
         return dt_ms, int(nbytes), same
 
     e2e_all = {}
+    relay_plan, e2e_direct = None, None
     for mode in dict.fromkeys([args.input, "xy", "ranges_f32", "ranges_u16"]):
         e2e_all[mode] = e2e_run(mode)
+        if mode == args.input and args.relay == "auto":
+            # the primary format once more with the upload relay between unequal ranks, if the box has any
+            relay_plan = plan_upload_relay(ctx, m, h2d_gbs, float(os.environ.get("NDT2D_BENCH_RELAY_MIN_RATIO", "1.15")))
+            if relay_plan:
+                e2e_direct = e2e_all[mode]
+                calib = e2e_run(mode)
+                relay_plan = refine_upload_relay(ctx, m, relay_plan, ctx.gather_floats(calib[0]))
+                e2e_all[mode] = e2e_run(mode)
     ctx.sync_all()
     e2e_ms, in_bytes, e2e_iters_equal = e2e_all[args.input]
     clocks = sampler.stop() if rank == 0 else None
     e2e_rank_ms = ctx.gather_floats(e2e_ms)
     ms, e2e_ms = ctx.max_over_ranks(ms, e2e_ms)
+    e2e_direct_ms = ctx.max_over_ranks(e2e_direct[0], 0.0)[0] if relay_plan else None
     total_evals_per_step, total_scans = ctx.sum_over_ranks(float(iters.sum()), float(B))
 
     line = None
@@ -606,7 +657,9 @@ def run_native(args):
                     "per_rank": {"h2d_gbs_plain_copy": h2d_gbs, "e2e_ms_per_step": [t / args.steps for t in e2e_rank_ms],
                                  "effective_h2d_gbs": [in_bytes / (t / args.steps / 1e3) / 1e9 for t in e2e_rank_ms],
                                  "note": "plain copy: the step's pinned input copied by every rank at the same time, no kernel; effective: input bytes / e2e step time"},
-                    "numa": ctx.numa, "pinned": args.pinned},
+                    "numa": ctx.numa, "pinned": args.pinned, "relay": relay_plan,
+                    "without_relay": ({"value": total_scans * args.steps / (e2e_direct_ms / 1e3), "ms_per_step": e2e_direct_ms / args.steps}
+                                      if relay_plan else None)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                          "dram_frac": (traffic / (kernel_ms / 1e3) / 1e9 / hbm) if traffic else None,

@@ -76,6 +76,7 @@ SIGNATURES = {
     "ndt2d_host_alloc": (C.c_int, [C.POINTER(_V), C.c_size_t]),
     "ndt2d_host_alloc_flags": (C.c_int, [C.POINTER(_V), C.c_size_t, C.c_int]),
     "ndt2d_host_free": (C.c_int, [_V]),
+    "ndt2d_set_upload_relay": (C.c_int, [_V, C.c_int, C.c_double]),
 }
 
 _lib = None

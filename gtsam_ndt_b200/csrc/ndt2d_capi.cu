@@ -175,20 +175,73 @@ ChunkPlan plan_chunks(const ndt2d_matcher *m, int nscans, size_t total_bytes)
     return p;
 }
 
-template <typename CopyFn, typename LaunchFn>
-int run_pipeline(ndt2d_matcher *m, int nscans, size_t total_bytes, ndt2d_result *res, CopyFn copy_chunk, LaunchFn launch_chunk)
+// chunk_desc(s0, s1, &dst, &src, &bytes): where the input of scans [s0, s1) goes on the device, where it comes from on the
+// host, and how long it is. With an upload relay (ndt2d_set_upload_relay) about relay_frac of the chunks take the detour
+// host -> relay GPU -> this GPU: their ev_chunk is recorded after the peer copy instead of after the direct one.
+static void release_relay(ndt2d_matcher *m)
+{
+    if (m->relay_dev < 0) return;
+    {
+        DeviceGuard g(m->relay_dev);
+        if (m->relay_stream) { cudaStreamSynchronize(m->relay_stream); cudaStreamDestroy(m->relay_stream); }
+        for (cudaEvent_t &e : m->ev_relay) { if (e) cudaEventDestroy(e); e = nullptr; }
+        if (m->relay_buf) cudaFree(m->relay_buf);
+    }
+    if (m->relay_peer_stream) {
+        DeviceGuard g(m->device);
+        cudaStreamSynchronize(m->relay_peer_stream);
+        cudaStreamDestroy(m->relay_peer_stream);
+    }
+    m->relay_stream = m->relay_peer_stream = nullptr;
+    m->relay_buf = nullptr;
+    m->relay_cap = 0;
+    m->relay_dev = -1;
+    m->relay_frac = 0.0;
+}
+
+template <typename DescFn, typename LaunchFn>
+int run_pipeline(ndt2d_matcher *m, int nscans, size_t total_bytes, ndt2d_result *res, DescFn chunk_desc, LaunchFn launch_chunk)
 {
     const ChunkPlan pl = plan_chunks(m, nscans, total_bytes);
+    const bool relay = m->relay_dev >= 0 && pl.nchunks > 1;
+    if (relay && m->relay_cap < total_bytes) {          // the relay GPU mirrors the call's input buffer
+        DeviceGuard g(m->relay_dev);
+        if (m->relay_buf) { cudaStreamSynchronize(m->relay_stream); cudaFree(m->relay_buf); m->relay_buf = nullptr; m->relay_cap = 0; }
+        CK(m, cudaMalloc(&m->relay_buf, total_bytes + total_bytes / 8));
+        m->relay_cap = total_bytes + total_bytes / 8;
+    }
     CK(m, cudaEventRecord(m->ev_begin, m->cfg.stream)); // earlier work on the handle's stream comes first
     CK(m, cudaStreamWaitEvent(m->copy_stream, m->ev_begin, 0));
     for (int i = 0; i < 2; ++i) CK(m, cudaStreamWaitEvent(m->work_stream[i], m->ev_begin, 0));
+    if (relay) {
+        CK(m, cudaStreamWaitEvent(m->relay_stream, m->ev_begin, 0));
+        CK(m, cudaStreamWaitEvent(m->relay_peer_stream, m->ev_begin, 0));
+    }
+    unsigned char *base_dst = nullptr;
     for (int c = 0; c < pl.nchunks; ++c) {
         int s0 = c * pl.per, s1 = s0 + pl.per < nscans ? s0 + pl.per : nscans;
-        if (s1 > s0) {
-            int rc = copy_chunk(s0, s1, m->copy_stream);
-            if (rc) return rc;
+        void *dst = nullptr;
+        const void *src = nullptr;
+        size_t bytes = 0;
+        if (s1 > s0) chunk_desc(s0, s1, &dst, &src, &bytes);
+        if (c == 0) base_dst = static_cast<unsigned char *>(dst);
+        // chunk c is relayed when the running share of relayed chunks falls behind relay_frac; the half-step phase keeps the
+        // first chunk (it gates the start) and the last ones (a relayed chunk arrives after two hops) on the direct link
+        const bool via = relay && bytes > 0 && c > 0 && (int)((c + 1) * m->relay_frac + 0.5) > (int)(c * m->relay_frac + 0.5);
+        if (via) {
+            unsigned char *mid = static_cast<unsigned char *>(m->relay_buf) + (static_cast<unsigned char *>(dst) - base_dst);
+            {
+                DeviceGuard g(m->relay_dev);
+                CK(m, cudaMemcpyAsync(mid, src, bytes, cudaMemcpyHostToDevice, m->relay_stream));
+                CK(m, cudaEventRecord(m->ev_relay[c], m->relay_stream));
+            }
+            CK(m, cudaStreamWaitEvent(m->relay_peer_stream, m->ev_relay[c], 0));
+            CK(m, cudaMemcpyPeerAsync(dst, m->device, mid, m->relay_dev, bytes, m->relay_peer_stream));
+            CK(m, cudaEventRecord(m->ev_chunk[c], m->relay_peer_stream));
+        } else {
+            if (bytes > 0) CK(m, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+            CK(m, cudaEventRecord(m->ev_chunk[c], m->copy_stream));
         }
-        CK(m, cudaEventRecord(m->ev_chunk[c], m->copy_stream));
     }
     const cudaStream_t main_stream = m->cfg.stream;
     int rc = NDT2D_OK;
@@ -310,6 +363,7 @@ void ndt2d_destroy(ndt2d_matcher *m)
                       &m->b_hyp, &m->b_scores, &m->b_tki, &m->b_tkv, &m->b_scratch, &m->b_counter, &m->b_beams, &m->b_ranges,
                       &m->b_box, &m->b_ptab, &m->b_pcnt, &m->b_psums, &m->b_pgeo, &m->b_ptargets, &m->b_ppairs, &m->b_perr, &m->b_reloc};
     for (DevBuf *b : bufs) b->release();
+    release_relay(m);
     if (m->copy_stream) {
         cudaStreamSynchronize(m->copy_stream);
         cudaStreamDestroy(m->copy_stream);
@@ -824,11 +878,11 @@ int ndt2d_align_batch(ndt2d_matcher *m, const float *xy, const int64_t *offsets,
     if ((rc = upload(m, m->b_init, init, (size_t)nscans * 24))) return rc;
     return run_pipeline(
         m, nscans, (size_t)total * 8, res,
-        [&](int s0, int s1, cudaStream_t cs) -> int {
+        [&](int s0, int s1, void **dst, const void **src, size_t *bytes) {
             int64_t p0 = offsets[s0], p1 = offsets[s1];
-            if (p1 > p0)
-                CK(m, cudaMemcpyAsync(m->b_xy.as<float>() + 2 * p0, xy + 2 * p0, (size_t)(p1 - p0) * 8, cudaMemcpyHostToDevice, cs));
-            return NDT2D_OK;
+            *dst = m->b_xy.as<float>() + 2 * p0;
+            *src = xy + 2 * p0;
+            *bytes = (size_t)(p1 - p0) * 8;
         },
         [&](int s0, int s1, unsigned int *counter) -> int {
             return align_batch_device_impl(m, m->b_xy.as<float>(), m->b_off.as<int64_t>() + s0, s1 - s0, (int)maxn,
@@ -906,11 +960,10 @@ int ndt2d_align_batch_ranges(ndt2d_matcher *m, const void *ranges, int ranges_ar
     if ((rc = ensure_beams(m, nbeams, angle_min, angle_inc))) return rc; // on the main stream, before the work streams fork
     return run_pipeline(
         m, nscans, (size_t)nscans * nbeams * esz, res,
-        [&](int s0, int s1, cudaStream_t cs) -> int {
-            CK(m, cudaMemcpyAsync(m->b_ranges.as<unsigned char>() + (size_t)s0 * nbeams * esz,
-                                  reinterpret_cast<const unsigned char *>(ranges) + (size_t)s0 * nbeams * esz,
-                                  (size_t)(s1 - s0) * nbeams * esz, cudaMemcpyHostToDevice, cs));
-            return NDT2D_OK;
+        [&](int s0, int s1, void **dst, const void **src, size_t *bytes) {
+            *dst = m->b_ranges.as<unsigned char>() + (size_t)s0 * nbeams * esz;
+            *src = reinterpret_cast<const unsigned char *>(ranges) + (size_t)s0 * nbeams * esz;
+            *bytes = (size_t)(s1 - s0) * nbeams * esz;
         },
         [&](int s0, int s1, unsigned int *counter) -> int {
             return align_ranges_device_impl(m, m->b_ranges.as<unsigned char>() + (size_t)s0 * nbeams * esz, ranges_are_u16,
@@ -1022,6 +1075,42 @@ int ndt2d_relocalize(ndt2d_matcher *m, int level, const float *xy, int n, const 
             memset(res + j, 0, sizeof(ndt2d_result));
             res[j].status = NDT2D_NO_OVERLAP;
         }
+    return NDT2D_OK;
+}
+
+int ndt2d_set_upload_relay(ndt2d_matcher *m, int relay_device, double fraction)
+{
+    if (!m) return NDT2D_EINVAL;
+    int rs = ndt2d_synchronize(m);
+    if (rs) return rs;
+    release_relay(m);
+    if (relay_device < 0) return NDT2D_OK;
+    int ndev = 0;
+    CK(m, cudaGetDeviceCount(&ndev));
+    if (relay_device >= ndev || relay_device == m->device || !(fraction > 0.0) || !(fraction < 1.0))
+        return fail(m, NDT2D_EINVAL, "upload relay: device %d (this handle: %d, %d devices), fraction %g (0 < f < 1)", relay_device, m->device,
+                    ndev, fraction);
+    int can = 0;
+    CK(m, cudaDeviceCanAccessPeer(&can, m->device, relay_device));
+    if (!can) return fail(m, NDT2D_EINVAL, "upload relay: device %d cannot access device %d as a peer", m->device, relay_device);
+    {
+        DeviceGuard g(m->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(relay_device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(m, e);
+        cudaGetLastError();
+        CK(m, cudaStreamCreateWithFlags(&m->relay_peer_stream, cudaStreamNonBlocking));
+    }
+    m->relay_dev = relay_device;        // from here on release_relay() undoes a partial set-up
+    {
+        DeviceGuard g(relay_device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(m->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { release_relay(m); CK(m, e); }
+        cudaGetLastError();
+        e = cudaStreamCreateWithFlags(&m->relay_stream, cudaStreamNonBlocking);
+        for (int i = 0; i < ndt2d_matcher::MAX_CHUNKS && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_relay[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) { release_relay(m); CK(m, e); }
+    }
+    m->relay_frac = fraction;
     return NDT2D_OK;
 }
 

@@ -118,6 +118,15 @@ struct ndt2d_matcher {
     ndt2d::PeerTable ex, rx;
     int rx_k = 0;                   // candidates per rank and query in `rx`
     int chunk_scans = 0; // NDT2D_CHUNK_SCANS override; 0 = choose by bytes (plan_chunks)
+    // upload relay (ndt2d_set_upload_relay): a share of the chunks of a host-buffer call travels host -> relay GPU over that
+    // GPU's PCIe link, then relay GPU -> this GPU over NVLink
+    int relay_dev = -1;
+    double relay_frac = 0.0;
+    cudaStream_t relay_stream = nullptr;       // on relay_dev: host -> relay buffer
+    cudaStream_t relay_peer_stream = nullptr;  // on this device: relay buffer -> input buffer
+    cudaEvent_t ev_relay[MAX_CHUNKS] = {};     // on relay_dev
+    void *relay_buf = nullptr;                 // on relay_dev, relay_cap bytes
+    size_t relay_cap = 0;
     // low-latency path of small host-buffer calls (a single align is 3 CUDA calls): pinned staging for one packed upload,
     // results written by the kernel straight into mapped pinned memory, work-queue counters from a pre-zeroed ring
     static constexpr size_t FAST_BYTES = 256 << 10;

@@ -87,6 +87,11 @@ class NdtMatcher2D:
     def synchronize(self):
         self._ck(self._L.ndt2d_synchronize(self._h))
 
+    def set_upload_relay(self, relay_device, fraction=0.5):
+        """About `fraction` of the input chunks of the host-buffer batch calls go host -> relay_device -> this GPU (that GPU's
+        PCIe link, then NVLink) instead of over this GPU's own link; relay_device < 0 switches it off (ndt2d_set_upload_relay)."""
+        self._ck(self._L.ndt2d_set_upload_relay(self._h, int(relay_device), float(fraction)))
+
     @property
     def stream(self):
         return self._L.ndt2d_stream(self._h) or 0

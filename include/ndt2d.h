@@ -260,6 +260,15 @@ int ndt2d_host_alloc(void **p, size_t bytes);
 int ndt2d_host_alloc_flags(void **p, size_t bytes, int flags);
 int ndt2d_host_free(void *p);
 
+/* Upload relay for the host-buffer batch calls (ndt2d_align_batch, ndt2d_align_batch_ranges). On a multi-GPU box the host
+ * side often cannot feed every GPU's PCIe link at once (measured on an 8 x B200 node: four GPUs get 23 GB/s each, the
+ * other four 35 GB/s, one GPU alone 50-55 GB/s). With a relay, about `fraction` of a call's input chunks are copied
+ * host -> relay_device (that GPU's link) and from there to this handle's device by a peer copy over NVLink, while the rest
+ * takes the handle's own link; results are unchanged. relay_device must differ from the handle's device and be
+ * peer-accessible; it needs no handle of its own and may serve a handle of another process at the same time. fraction
+ * in (0, 1); relay_device < 0 switches the relay off. No reference counterpart (none citable). */
+int ndt2d_set_upload_relay(ndt2d_matcher *m, int relay_device, double fraction);
+
 #ifdef __cplusplus
 }
 #endif

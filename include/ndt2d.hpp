@@ -238,6 +238,8 @@ class Matcher {
 
     ndt2d_matcher *handle() const { return h_; }
     void synchronize() { ck(ndt2d_synchronize(h_)); }
+    // a share of the input of the host-buffer batch calls travels over another GPU's PCIe link and NVLink (ndt2d_set_upload_relay)
+    void setUploadRelay(int relayDevice, double fraction = 0.5) { ck(ndt2d_set_upload_relay(h_, relayDevice, fraction)); }
 
   private:
     void ck(int rc) const

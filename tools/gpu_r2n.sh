@@ -11,6 +11,7 @@ import json
 try:
     d = json.loads(open('gpurun_out/${TAG}_n${N}_bench.json').read().strip().splitlines()[-1])
     print('N=$N value', round(d['value']/1e6,2), 'e2e', round(d['e2e']['value']/1e6,2), d['e2e']['per_rank'], d['e2e']['numa'])
+    print('relay', d['e2e'].get('relay'), 'without', d['e2e'].get('without_relay'), 'by_input', {k: round(v['value']/1e6,2) for k, v in d['e2e']['by_input'].items()})
     for k in ('prior2','pyramid'):
         print(k, round(d[k]['value']/1e6,3), d[k].get('mean_iterations'))
     s = d['sweep']; print('sweep', round(s['value']/1e6,1), s['ms_per_query'], s['combine_equals_host_api_result'], s.get('nccl'), s['exchange_check'], s['relocalize'], s['ok'])
