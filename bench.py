@@ -513,9 +513,21 @@ def plan_upload_relay(ctx, m, gbs, min_ratio=1.15):
             pairs[slow] = (fast, (gbs[fast] - gbs[slow]) / (gbs[fast] + gbs[slow]))
     if not pairs:
         return None
+    ok = 1.0
     if ctx.rank in pairs:
         fast, x = pairs[ctx.rank]
-        m.set_upload_relay(fast, min(max(x, 0.05), 0.6))
+        try:
+            m.set_upload_relay(fast, min(max(x, 0.05), 0.6))
+        except Exception as e:                      # e.g. no peer access on this box: every rank then stays on its own link
+            print(f"[bench] rank {ctx.rank}: upload relay unavailable: {e}", file=sys.stderr)
+            ok = 0.0
+    if min(ctx.gather_floats(ok)) < 1.0:
+        if ctx.rank in pairs:
+            try:
+                m.set_upload_relay(-1)
+            except Exception:
+                pass
+        return None
     return {"pairs": {str(k): {"via_rank": v[0], "fraction": round(v[1], 3)} for k, v in pairs.items()},
             "note": "share of a slow rank's input chunks copied host -> the paired rank's GPU (its PCIe link) -> NVLink peer copy"}
 
@@ -529,7 +541,11 @@ def refine_upload_relay(ctx, m, plan, t_ms):
         x2 = min(max(x + (ts - tf) / (ts / (1.0 - x) + tf / (1.0 + x)), 0.05), 0.6)
         v["first_fraction"], v["fraction"] = x, round(x2, 3)
         if ctx.rank == int(slow):
-            m.set_upload_relay(fast, x2)
+            try:
+                m.set_upload_relay(fast, x2)
+            except Exception as e:
+                print(f"[bench] rank {ctx.rank}: upload relay refinement failed, keeping {x}: {e}", file=sys.stderr)
+                m.set_upload_relay(fast, x)
     plan["note"] += "; fractions refined once from the per-rank step times of a calibration run"
     return plan
 
