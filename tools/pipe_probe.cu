@@ -11,11 +11,11 @@ typedef unsigned long long u64;
 #define REP 8      // the body is repeated REP times per trip, so the three loop-control instructions are 3 in 64+
 #define ITERS 512
 
-enum Op { FFMA, FFMA2, FMUL2, DFMA, DADD, F2F_WIDE, F2F_NARROW, IMAD, LOP, MIX_FFMA2_FFMA, MIX_FFMA2_DFMA, MIX_FFMA2_F2F, MIX_FFMA2_LOP, MIX_DFMA_F2F, MIX_LOOP, NOPS };
-static const char *kNames[NOPS] = {"FFMA", "FFMA2 (packed f32x2)", "FMUL2", "DFMA", "DADD", "F2F.F64.F32", "F2F.F32.F64", "IMAD", "LOP3",
+enum Op { FFMA, FFMA2, FMUL2, DFMA, DADD, F2F_WIDE, F2F_NARROW, IMAD, LOP, IMADW, LEA2, MOVS, MIX_FFMA2_FFMA, MIX_FFMA2_DFMA, MIX_FFMA2_F2F, MIX_FFMA2_LOP, MIX_DFMA_F2F, MIX_LOOP, NOPS };
+static const char *kNames[NOPS] = {"FFMA", "FFMA2 (packed f32x2)", "FMUL2", "DFMA", "DADD", "F2F.F64.F32", "F2F.F32.F64", "IMAD", "LOP3", "IMAD.WIDE (address = index * 32 + base)", "shift-add pair for the same 64-bit address", "MOV (register copy)",
                                    "FFMA2 + FFMA alternating", "FFMA2 + DFMA alternating", "FFMA2 + F2F alternating", "FFMA2 + LOP3 alternating",
                                    "DFMA + F2F alternating", "loop mix: 8 FFMA2, 2 FFMA, 2 IMAD, 3 DFMA/DADD, 1 F2F, 1 LOP3 (17)"};
-static const int kInstrPerIter[NOPS] = {CHAINS, CHAINS, CHAINS, CHAINS, CHAINS, CHAINS, CHAINS, CHAINS, CHAINS, 2 * CHAINS, 2 * CHAINS, 2 * CHAINS,
+static const int kInstrPerIter[NOPS] = {CHAINS, CHAINS, CHAINS, CHAINS, CHAINS, CHAINS, CHAINS, CHAINS, CHAINS, CHAINS, 2 * CHAINS, CHAINS, 2 * CHAINS, 2 * CHAINS, 2 * CHAINS,
                                         2 * CHAINS, 2 * CHAINS, 17};
 
 template <int OP>
@@ -56,6 +56,9 @@ __global__ void __launch_bounds__(1024) k_probe(u64 *out_cycles, float *sink, fl
             if (OP == F2F_WIDE || OP == MIX_FFMA2_F2F || OP == MIX_DFMA_F2F) { asm volatile("" : "+f"(f[i])); asm volatile("cvt.f64.f32 %0, %1;" : "=d"(w[i]) : "f"(f[i])); }
             if (OP == F2F_NARROW) { asm volatile("" : "+d"(d[i])); asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f[i]) : "d"(d[i])); }
             if (OP == IMAD) asm volatile("mad.lo.s32 %0, %0, %1, %1;" : "+r"(n[i]) : "r"(k3));
+            if (OP == IMADW) asm volatile("mad.wide.u32 %0, %1, 32, %0;" : "+l"(p[i]) : "r"(n[i]));
+            if (OP == LEA2) asm volatile("{.reg .b64 t; cvt.u64.u32 t, %1; shl.b64 t, t, 5; add.s64 %0, %0, t;}" : "+l"(p[i]) : "r"(n[i]));
+            if (OP == MOVS) { asm volatile("mov.b32 %0, %1;" : "=r"(n[i]) : "r"(n[(i + 1) % CHAINS])); }
             if (OP == MIX_FFMA2_LOP || OP == LOP) asm volatile("lop3.b32 %0, %0, %1, %1, 0x96;" : "+r"(n[i]) : "r"(k3));
         }
         if (OP == MIX_LOOP) {
@@ -121,6 +124,9 @@ int main()
     run<F2F_NARROW>(d_cycles, d_sink);
     run<IMAD>(d_cycles, d_sink);
     run<LOP>(d_cycles, d_sink);
+    run<IMADW>(d_cycles, d_sink);
+    run<LEA2>(d_cycles, d_sink);
+    run<MOVS>(d_cycles, d_sink);
     run<MIX_FFMA2_FFMA>(d_cycles, d_sink);
     run<MIX_FFMA2_DFMA>(d_cycles, d_sink);
     run<MIX_FFMA2_F2F>(d_cycles, d_sink);
