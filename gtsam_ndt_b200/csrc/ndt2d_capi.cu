@@ -811,8 +811,8 @@ static int align_batch_device_impl(ndt2d_matcher *m, const float *d_xy, const in
 // Small host-buffer batches (a single align above all): offsets, initial poses and points are packed into one pinned
 // buffer and go up in ONE copy, the kernel writes its results into mapped pinned memory, the queue counter comes from a
 // pre-zeroed ring: copy, launch, synchronise - instead of the ~15 calls of the chunked pipeline.
-static int align_batch_fast(ndt2d_matcher *m, const float *xy, const int64_t *offsets, int nscans, int64_t total, int64_t maxn,
-                            const double *init, ndt2d_result *res)
+// the buffers of the small-call path (align_batch_fast, align_ranges_fast), and a zeroed work-queue counter from the ring
+static int fast_prepare(ndt2d_matcher *m)
 {
     if (!m->fast_ready) {   // set only after every allocation below has succeeded: a failed attempt is simply repeated
         if (!m->fast_host) CK(m, cudaHostAlloc(reinterpret_cast<void **>(&m->fast_host), ndt2d_matcher::FAST_BYTES, cudaHostAllocDefault));
@@ -828,6 +828,14 @@ static int align_batch_fast(ndt2d_matcher *m, const float *xy, const int64_t *of
         CK(m, cudaMemsetAsync(m->b_ring.p, 0, ndt2d_matcher::RING * 4, m->cfg.stream));
         m->ring_pos = 0;
     }
+    return NDT2D_OK;
+}
+
+static int align_batch_fast(ndt2d_matcher *m, const float *xy, const int64_t *offsets, int nscans, int64_t total, int64_t maxn,
+                            const double *init, ndt2d_result *res)
+{
+    int rcp = fast_prepare(m);
+    if (rcp) return rcp;
     const size_t off_bytes = (size_t)(nscans + 1) * 8, init_bytes = (size_t)nscans * 24, xy_bytes = (size_t)total * 8;
     unsigned char *h = m->fast_host;
     memcpy(h, offsets, off_bytes);
@@ -943,6 +951,43 @@ static int align_ranges_device_impl(ndt2d_matcher *m, const void *d_ranges, int 
     return NDT2D_OK;
 }
 
+// Small LaserScan calls (one scan above all), the ranges form of align_batch_fast: initial poses and ranges in one pinned
+// upload, results written by the kernel into mapped pinned memory - three CUDA calls instead of a pipeline.
+static int align_ranges_fast(ndt2d_matcher *m, const void *ranges, int ranges_are_u16, int nscans, int nbeams, double angle_min,
+                             double angle_inc, float range_scale, float range_min, float range_max, const double *init, ndt2d_result *res)
+{
+    int rc = fast_prepare(m);
+    if (rc) return rc;
+    int cap = align_cap_points(m, nbeams);
+    if (cap == 0) return fail(m, NDT2D_EINVAL, "nbeams %d exceeds the shared-memory staging limit", nbeams);
+    if ((rc = ensure_beams(m, nbeams, angle_min, angle_inc))) return rc;
+    const size_t init_bytes = (size_t)nscans * 24, r_bytes = (size_t)nscans * nbeams * (ranges_are_u16 ? 2 : 4);
+    unsigned char *h = m->fast_host;
+    memcpy(h, init, init_bytes);
+    memcpy(h + init_bytes, ranges, r_bytes);
+    unsigned char *d = m->b_fast.as<unsigned char>();
+    CK(m, cudaMemcpyAsync(d, h, init_bytes + r_bytes, cudaMemcpyHostToDevice, m->cfg.stream));
+    AlignArgs a;
+    fill_align_args(m, a);
+    a.xy = nullptr;
+    a.ranges = d + init_bytes;
+    a.beams = m->b_beams.as<float2>();
+    a.ranges_u16 = ranges_are_u16 ? 1 : 0;
+    a.nbeams = nbeams;
+    a.range_scale = range_scale; a.range_min = range_min; a.range_max = range_max;
+    a.init = reinterpret_cast<const double *>(d);
+    a.res = m->fast_res_dev;
+    a.nscans = nscans;
+    a.cap_points = cap;
+    a.counter = m->b_ring.as<unsigned int>() + m->ring_pos++;
+    a.counter_is_zero = 1;
+    CK(m, launch_align(m->cfg, a, &m->launches));
+    rc = ndt2d_synchronize(m);
+    if (rc) return rc;
+    memcpy(res, m->fast_res, (size_t)nscans * sizeof(ndt2d_result));
+    return NDT2D_OK;
+}
+
 int ndt2d_align_batch_ranges(ndt2d_matcher *m, const void *ranges, int ranges_are_u16, int nscans, int nbeams,
                              double angle_min, double angle_inc, float range_scale, float range_min, float range_max,
                              const double *init, ndt2d_result *res)
@@ -954,6 +999,9 @@ int ndt2d_align_batch_ranges(ndt2d_matcher *m, const void *ranges, int ranges_ar
     DeviceGuard g(m->device);
     int rc;
     const size_t esz = ranges_are_u16 ? 2 : 4;
+    // init at offset 0 (8-byte aligned) and the ranges behind it: nscans * 24 is a multiple of 4, enough for f32 and u16
+    if (nscans <= ndt2d_matcher::FAST_SCANS && (size_t)nscans * 24 + (size_t)nscans * nbeams * esz <= ndt2d_matcher::FAST_BYTES)
+        return align_ranges_fast(m, ranges, ranges_are_u16, nscans, nbeams, angle_min, angle_inc, range_scale, range_min, range_max, init, res);
     CK(m, m->b_ranges.ensure((size_t)nscans * nbeams * esz));
     CK(m, m->b_res.ensure((size_t)nscans * sizeof(ndt2d_result)));
     if ((rc = upload(m, m->b_init, init, (size_t)nscans * 24))) return rc;

@@ -322,21 +322,67 @@ __device__ __forceinline__ int align_level_block(const LevelDev *L, const ndt2d_
     return lm_level<BlockScope>(P, n, ws, evals_total, [&]() { eval_block<OV>(L, pts, n, ws, fac); });
 }
 
-template <int OV>
+// SPEC 8 for one warp: the beams of LaserScan `job` with range_min <= rho <= range_max, converted to points and written to
+// `slot` in beam order; returns how many were kept. (k_align's staging step in ranges mode, and k_align_block's, done by warp 0.)
+__device__ __forceinline__ int stage_ranges(const AlignArgs &a, unsigned job, float2 *slot, int lane)
+{
+    int kept = 0;
+    for (int b0 = 0; b0 < a.nbeams; b0 += 32) {
+        int b = b0 + lane;
+        float rho = 0.0f;
+        bool ok = false;
+        if (b < a.nbeams) {
+            if (a.ranges_u16) {
+                unsigned short u = __ldg(reinterpret_cast<const unsigned short *>(a.ranges) + (size_t)job * a.nbeams + b);
+                rho = __fmul_rn((float)u, a.range_scale);
+                ok = (u != 0);
+            } else {
+                rho = __ldg(reinterpret_cast<const float *>(a.ranges) + (size_t)job * a.nbeams + b);
+                ok = true;
+            }
+            ok = ok && (rho >= a.range_min) && (rho <= a.range_max);
+        }
+        unsigned m = __ballot_sync(FULL_MASK, ok);
+        if (ok) {
+            float2 bt = __ldg(a.beams + b);
+            int dst = kept + __popc(m & ((1u << lane) - 1u));
+            slot[dst] = sanitize(make_float2(__fmul_rn(rho, bt.x), __fmul_rn(rho, bt.y)));
+        }
+        kept += __popc(m);
+    }
+    return kept;
+}
+
+// RANGES: LaserScan input (a.xy == nullptr); warp 0 converts and compacts the beams, the other warps wait at the barrier
+template <int OV, bool RANGES = false>
 __global__ void __launch_bounds__(BLOCK_ALIGN_THREADS) k_align_block(const __grid_constant__ AlignArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_n;
     WarpState *ws = reinterpret_cast<WarpState *>(smem_raw);
     float2 *pts = reinterpret_cast<float2 *>(smem_raw + sizeof(WarpState));
     u64 *fac = reinterpret_cast<u64 *>(smem_raw + sizeof(WarpState) + (size_t)a.cap_points * sizeof(float2));
     const int job = blockIdx.x, tid = threadIdx.x;
-    const int scan = a.job_scan ? __ldg(a.job_scan + job) : job;
-    const int64_t o0 = scan >= 0 ? __ldg(a.offsets + scan) : 0, o1 = scan >= 0 ? __ldg(a.offsets + scan + 1) : 0;
-    const int n = (int)(o1 - o0), npad = (n + 63) & ~63;
-    const float2 *src = a.xy + o0;
-    for (int i = tid; i < npad; i += BLOCK_ALIGN_THREADS) pts[i] = i < n ? sanitize(__ldg(src + i)) : make_float2(1e18f, 1e18f);
-    if (tid < 3) ws->p[tid] = __ldg(a.init + 3 * (size_t)job + tid);
-    __syncthreads();
+    int n;
+    if (RANGES) {
+        if (tid < 32) {
+            const int kept = stage_ranges(a, (unsigned)job, pts, tid);
+            for (int i = kept + tid; i < ((kept + 63) & ~63); i += 32) pts[i] = make_float2(1e18f, 1e18f);
+            if (tid == 0) s_n = kept;
+        }
+        if (tid < 3) ws->p[tid] = __ldg(a.init + 3 * (size_t)job + tid);
+        __syncthreads();
+        n = s_n;
+    } else {
+        const int scan = a.job_scan ? __ldg(a.job_scan + job) : job;
+        const int64_t o0 = scan >= 0 ? __ldg(a.offsets + scan) : 0, o1 = scan >= 0 ? __ldg(a.offsets + scan + 1) : 0;
+        n = (int)(o1 - o0);
+        const int npad = (n + 63) & ~63;
+        const float2 *src = a.xy + o0;
+        for (int i = tid; i < npad; i += BLOCK_ALIGN_THREADS) pts[i] = i < n ? sanitize(__ldg(src + i)) : make_float2(1e18f, 1e18f);
+        if (tid < 3) ws->p[tid] = __ldg(a.init + 3 * (size_t)job + tid);
+        __syncthreads();
+    }
     int evals = 0, status = NDT2D_NO_OVERLAP;
     for (int l = 0; l < a.nlevels; ++l) status = align_level_block<OV>(&a.lv[l], a.prm, pts, n, ws, fac, evals);
     if (tid == 0) write_result(*ws, evals, status, a.res + job);
@@ -411,32 +457,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, (STAGED || RANGES) ? ALIGN_MIN_
         ScanView v;
         v.pts = slot; v.n = 0;
         if (RANGES) {
-            // SPEC 8: keep beams with range_min <= rho <= range_max, in beam order
-            int kept = 0;
-            for (int b0 = 0; b0 < a.nbeams; b0 += 32) {
-                int b = b0 + lane;
-                float rho = 0.0f;
-                bool ok = false;
-                if (b < a.nbeams) {
-                    if (a.ranges_u16) {
-                        unsigned short u = __ldg(reinterpret_cast<const unsigned short *>(a.ranges) + (size_t)job * a.nbeams + b);
-                        rho = __fmul_rn((float)u, a.range_scale);
-                        ok = (u != 0);
-                    } else {
-                        rho = __ldg(reinterpret_cast<const float *>(a.ranges) + (size_t)job * a.nbeams + b);
-                        ok = true;
-                    }
-                    ok = ok && (rho >= a.range_min) && (rho <= a.range_max);
-                }
-                unsigned m = __ballot_sync(FULL_MASK, ok);
-                if (ok) {
-                    float2 bt = __ldg(a.beams + b);
-                    int dst = kept + __popc(m & ((1u << lane) - 1u));
-                    slot[dst] = sanitize(make_float2(__fmul_rn(rho, bt.x), __fmul_rn(rho, bt.y)));
-                }
-                kept += __popc(m);
-            }
-            v.n = kept;
+            v.n = stage_ranges(a, job, slot, lane);   // SPEC 8: keep beams with range_min <= rho <= range_max, in beam order
         } else {
             const int src_scan = PAIRS ? __ldg(a.pairs + 2 * (size_t)job + 1) : a.job_scan ? __ldg(a.job_scan + job) : (int)job;
             int64_t o0 = src_scan >= 0 ? __ldg(a.offsets + src_scan) : 0, o1 = src_scan >= 0 ? __ldg(a.offsets + src_scan + 1) : 0;
@@ -696,21 +717,17 @@ cudaError_t launch_align(const LaunchCfg &c, const AlignArgs &a, int64_t *launch
     const bool staged = a.cap_points > 0;
     // few scans: latency matters, not throughput - one block per scan (k_align_block) if its factor buffer fits
     // (tools/midsize_probe.py: the block form wins up to ~1250 scans on a 148-SM part, four resident blocks per SM)
-    if (!ranges && staged && !a.pairs && a.nscans <= (c.block_align_max >= 0 ? c.block_align_max : 8 * c.sm_count)) {
+    if (staged && !a.pairs && a.nscans <= (c.block_align_max >= 0 ? c.block_align_max : 8 * c.sm_count)) {
         const int NC = a.prm.overlap ? 4 : 1;
         const size_t smem = sizeof(WarpState) + (size_t)a.cap_points * sizeof(float2) +
                             (size_t)(a.cap_points / 64) * NC * FACTOR_WORDS * 32 * sizeof(u64);
         if (smem <= (size_t)c.max_smem_optin) {
             cudaError_t e2 = cudaSuccess;
-            if (a.prm.overlap) {
-                if (smem > 48 * 1024) e2 = cudaFuncSetAttribute(k_align_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e2 != cudaSuccess) return e2;
-                k_align_block<1><<<a.nscans, BLOCK_ALIGN_THREADS, smem, c.stream>>>(a);
-            } else {
-                if (smem > 48 * 1024) e2 = cudaFuncSetAttribute(k_align_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e2 != cudaSuccess) return e2;
-                k_align_block<0><<<a.nscans, BLOCK_ALIGN_THREADS, smem, c.stream>>>(a);
-            }
+            auto kern = a.prm.overlap ? (ranges ? k_align_block<1, true> : k_align_block<1, false>)
+                                      : (ranges ? k_align_block<0, true> : k_align_block<0, false>);
+            if (smem > 48 * 1024) e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e2 != cudaSuccess) return e2;
+            kern<<<a.nscans, BLOCK_ALIGN_THREADS, smem, c.stream>>>(a);
             return cudaGetLastError();
         }
     }
