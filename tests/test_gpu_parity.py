@@ -379,21 +379,28 @@ def test_helper_warps_leave_every_bit_unchanged(mods, small_world, cfg, monkeypa
 
 
 def test_helper_warps_ranges_input(mods, small_world, monkeypatch):
-    """The LaserScan form of the same check (the helpers read the owner's converted points)."""
+    """The LaserScan form of the same check (the helpers read the owner's converted points), and the block-per-scan kernel's
+    LaserScan form (warp 0 converts the beams) against both."""
     from gtsam_ndt_b200 import synth
     g, _ = mods
     sc = synth.SCAN_1080
     ranges, poses = synth.scans(37, traj_len=600, first=3, step=13, **sc)
     init = poses + synth.uniform3(37) * np.array([0.05, 0.05, np.radians(0.5)])
     out = {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("NDT2D_ALIGN_HELP", mode)
+    u16 = np.round(ranges / 0.004).clip(0, 65535).astype(np.uint16)
+    u16[3, 100:140] = 0                                   # no return: those beams are dropped (SPEC 8)
+    for mode, env in (("warp", ("0", "0")), ("help", ("0", "1")), ("block", ("100000", "0"))):
+        monkeypatch.setenv("NDT2D_BLOCK_ALIGN_MAX", env[0])
+        monkeypatch.setenv("NDT2D_ALIGN_HELP", env[1])
         m = g.NdtMatcher2D([1.0, 0.5])
         m.set_target(small_world["map_xy"])
-        out[mode] = m.align_batch_ranges(ranges, sc["angle_min"], sc["angle_inc"], init, range_scale=1.0)
+        out[mode] = (m.align_batch_ranges(ranges, sc["angle_min"], sc["angle_inc"], init, range_scale=1.0).tobytes(),
+                     m.align_batch_ranges(u16, sc["angle_min"], sc["angle_inc"], init, range_scale=0.004, range_min=0.5, range_max=25.0).tobytes(),
+                     m.align_batch_ranges(ranges[:1], sc["angle_min"], sc["angle_inc"], init[:1], range_scale=1.0).tobytes())
         m.close()
-    assert out["0"].tobytes() == out["1"].tobytes()
-    assert (out["1"]["status"] != g.NO_OVERLAP).any()
+    assert out["warp"] == out["help"] == out["block"]      # the three kernel forms, f32 and u16 ranges, one scan (small-call path)
+    first = np.frombuffer(out["block"][0], dtype=g.RESULT_DTYPE)
+    assert (first["status"] != g.NO_OVERLAP).any() and out["block"][2] == first[:1].tobytes()
 
 
 def _between(a, b):
