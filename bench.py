@@ -26,6 +26,7 @@ The default run (`--workload scan2map`, what the driver launches at N = 1, 2, 4,
   odometry  batched scan-to-scan (ndt2d_align_pairs): 16 384 consecutive scans per GPU, pair k = (scan k-1 -> scan k), 0.5 m cells
   dense     configs[1] in a cluttered world whose map has > 300 k valid cells (the default room has 14 k)
   config0   configs[0]: one 360-beam scan-to-scan align at 0.5 m cells, CPU oracle on one thread vs ndt2d_align latency
+  config4   configs[4], the front end: examples/slam_frontend.cpp (GPU odometry + loop closure -> g2o pose graph), its own figures
   precision distance of the GPU results from an independent f64 NDT (oracle/f64ref.py) at north_star's tolerances
 """
 import argparse
@@ -72,7 +73,7 @@ def parse_args():
     ap.add_argument("--ref-scans", type=int, default=0, help="scans per step of the reference arm (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--legs", default="all", help="scan2map only: extra legs in the same JSON line: all | none | comma list of "
-                                                  "sweep,pyramid,prior2,odometry,dense,config0,precision")
+                                                  "sweep,pyramid,prior2,odometry,dense,config0,config4,precision")
     ap.add_argument("--world", default="room", choices=["room", "dense"],
                     help="synthetic world of the scan2map workload: the SURVEY 8(d) room (14 k valid map cells) or the cluttered dense world (> 300 k)")
     ap.add_argument("--relay", default="auto", choices=["auto", "off"],
@@ -90,7 +91,7 @@ def parse_args():
         a.steps = 50 if a.workload == "sweep" else 10
     a.res = a.res or dflt[1]
     a.perturb = a.perturb or dflt[2]
-    legs = ["sweep", "pyramid", "prior2", "odometry", "dense", "config0", "precision"]
+    legs = ["sweep", "pyramid", "prior2", "odometry", "dense", "config0", "config4", "precision"]
     a.legs = legs if a.legs == "all" else [] if a.legs == "none" else [x for x in a.legs.split(",") if x]
     if a.workload != "scan2map" or a.overlap or a.world != "room" or a.res != [0.25]:
         a.legs = []          # the legs belong to the default configuration
@@ -727,6 +728,8 @@ def run_native(args):
         os.sched_setaffinity(0, ctx.affinity0)      # the CPU legs below use every core the process was given
         if "dense" in args.legs:
             line["dense"] = leg_dense(ctx, args)
+        if "config4" in args.legs:
+            line["config4"] = config4_slam_frontend()
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, xy, offsets, init, map_xy, res, m if "precision" in args.legs else None,
                                                 want_config0="config0" in args.legs)
@@ -1448,6 +1451,39 @@ def precision_vs_f64(m, map_xy, xy, offsets, init, n=64):
                                 "drot_median": float(np.median(drot)), "drot_max": float(drot.max())},
             "tolerance": {"score_hessian_rel": 1e-6, "pose_m": 1e-5, "pose_rad": 1e-6},
             "note": "scans outside the pose tolerance took a different accept/reject path through the LM loop (DESIGN.md section 3b); SPEC v3 measured 1.3e-4 / 7e-3 on score / Hessian"}
+
+
+def config4_slam_frontend():
+    """BASELINE configs[4], the part that exists without GTSAM: examples/slam_frontend.cpp (C++ host code over ndt2d.hpp) drives a
+    closed loop through a synthetic room - sequential GPU NDT odometry, the loop-closure search (sweep + refinement), the same
+    odometry batched through alignPairs - checks its own factors against the truth and writes the g2o pose graph that
+    gtsam::readG2o + ISAM2 consume. Built with the system g++ on the spot; the figures are the program's own."""
+    import re
+    import tempfile
+    exe = os.path.join(ROOT, "examples", "slam_frontend")
+    src = exe + ".cpp"
+    libdir = os.path.join(ROOT, "gtsam_ndt_b200")
+    try:
+        if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(libdir, "libndt2d.so"))):
+            subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), src, "-L", libdir, "-lndt2d",
+                            "-Wl,-rpath," + libdir, "-o", exe], check=True, capture_output=True, timeout=120)
+        with tempfile.TemporaryDirectory() as td:
+            r = subprocess.run([exe, os.path.join(td, "graph.g2o")], capture_output=True, text=True, timeout=120)
+        out = r.stdout
+        num = lambda rx: [float(x) for x in re.search(rx, out).groups()]
+        edges, bad, worst, drift = num(r"odometry: (\d+) edges, (\d+) not converged, worst relative error ([\d.]+) m, dead-reckoning drift ([\d.]+) m")
+        odo_ms, loop_ms, nhyp = num(r"timing: ([\d.]+) ms per odometry step .*?, ([\d.]+) ms for the loop-closure search \((\d+) hypotheses")
+        npairs, batch_ms, differ = num(r"batched odometry: (\d+) pairs in ([\d.]+) ms through alignPairs .*?, (\d+) results differ")
+        loop_err = num(r"loop closure .*?error vs truth ([\d.]+) m")[0]
+        return {"workload": "configs[4] front end: examples/slam_frontend (C++ over ndt2d.hpp), closed loop in a 24 x 16 m room, GPU odometry + "
+                            "loop closure -> g2o pose graph for GTSAM (no solver here: GTSAM is absent)",
+                "ok": r.returncode == 0, "odometry_edges": int(edges), "not_converged": int(bad), "worst_relative_error_m": worst,
+                "dead_reckoning_drift_m": drift, "loop_closure_error_m": loop_err, "ms_per_odometry_step_sequential": odo_ms,
+                "odometry_steps_per_s_sequential": 1e3 / odo_ms, "loop_closure_search_ms": loop_ms, "loop_closure_hypotheses": int(nhyp),
+                "batched_odometry_ms": batch_ms, "batched_odometry_pairs_per_s": npairs / (batch_ms / 1e3),
+                "batched_results_differing_from_sequential": int(differ)}
+    except Exception as e:
+        return {"workload": "configs[4] front end: examples/slam_frontend", "ok": False, "error": repr(e)[:300]}
 
 
 def config0_pair(device=0):

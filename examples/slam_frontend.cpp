@@ -118,6 +118,8 @@ int main(int argc, char **argv)
         ndt2d::Pose2d prior{};
         double worst_rel = 0;
         int bad = 0;
+        ndt.setTarget(scans[0]);                         // warm-up: the handle's buffers are allocated on first use
+        (void)ndt.align(scans[1], prior);
         const auto t_odo = std::chrono::steady_clock::now();
         for (int k = 1; k <= N; ++k) {
             ndt.setTarget(scans[k - 1]);
