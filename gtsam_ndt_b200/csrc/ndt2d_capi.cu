@@ -60,10 +60,10 @@ static int install_level(ndt2d_matcher *m, int l)
     LevelMem &M = m->mem[l];
     const int64_t pad = LevelMem::zero_pad(L.njx);
     CK(m, M.ensure(nc, pad));
-    // all-zero records after the table: the gather targets of points outside the lattice (never written again)
-    CK(m, cudaMemsetAsync(M.cells, 0, (size_t)(nc + pad) * 32, m->cfg.stream));
-    CK(m, cudaMemsetAsync(M.cnt, 0, (size_t)nc * 4, m->cfg.stream));
-    CK(m, cudaMemsetAsync(M.sums, 0, (size_t)nc * 40, m->cfg.stream));
+    // records, sums and counts share one allocation and are cleared by one memset (three launches fewer per level: a
+    // target scan's tables are small, the launches were most of the clearing); the all-zero records after the table are
+    // the gather targets of points outside the lattice and are never written again
+    CK(m, cudaMemsetAsync(M.base, 0, M.bytes, m->cfg.stream));
     L.cells = M.cells;
     L.cnt = M.cnt;
     L.sums = M.sums;
@@ -444,14 +444,18 @@ int ndt2d_set_grid(ndt2d_matcher *m, float ox, float oy, float ex, float ey)
     return NDT2D_OK;
 }
 
-int ndt2d_set_target_device(ndt2d_matcher *m, const float *d_xy, int64_t n)
+// host_bbox: the caller already knows the bounding box of the finite points (ndt2d_set_target computes it on the host for
+// small targets while the points are still in its hands: no bbox kernel, no read-back, no synchronisation)
+static int set_target_impl(ndt2d_matcher *m, const float *d_xy, int64_t n, const float *host_bbox)
 {
     if (!m || n < 0 || (n > 0 && !d_xy)) return m ? fail(m, NDT2D_EINVAL, "bad target arguments") : NDT2D_EINVAL;
     DeviceGuard g(m->device);
     CK(m, cudaStreamSynchronize(m->cfg.stream));
     drop_target(m, /*keep_memory=*/true);
     float bbox[4] = {0, 0, 0, 0};
-    if (!m->explicit_grid) {
+    if (host_bbox) {
+        for (int i = 0; i < 4; ++i) bbox[i] = host_bbox[i];
+    } else if (!m->explicit_grid) {
         int box[4];
         CK(m, launch_bbox(m->cfg, reinterpret_cast<const float2 *>(d_xy), n, m->b_box.as<int>(), &m->launches));
         CK(m, cudaMemcpyAsync(box, m->b_box.p, sizeof(box), cudaMemcpyDeviceToHost, m->cfg.stream));
@@ -471,6 +475,8 @@ int ndt2d_set_target_device(ndt2d_matcher *m, const float *d_xy, int64_t n)
     m->sums_valid = true;
     return NDT2D_OK;
 }
+
+int ndt2d_set_target_device(ndt2d_matcher *m, const float *d_xy, int64_t n) { return set_target_impl(m, d_xy, n, nullptr); }
 
 int ndt2d_add_target_device(ndt2d_matcher *m, const float *d_xy, int64_t n)
 {
@@ -503,7 +509,19 @@ int ndt2d_set_target(ndt2d_matcher *m, const float *xy, int64_t n)
     DeviceGuard g(m->device);
     int rc = upload(m, m->b_xy, xy, (size_t)n * 8);
     if (rc) return rc;
-    rc = ndt2d_set_target_device(m, m->b_xy.as<float>(), n);
+    // a target scan: the auto-fit bounding box (SPEC 2: min and max over the finite points - exact, order independent) is
+    // cheaper to take here than with a kernel, a copy back and a synchronisation; a map cloud goes to the GPU
+    float bbox[4] = {INFINITY, INFINITY, -INFINITY, -INFINITY};
+    const bool on_host = !m->explicit_grid && n <= 16384;
+    if (on_host) {
+        for (int64_t i = 0; i < n; ++i) {
+            const float x = xy[2 * i], y = xy[2 * i + 1];
+            if (!std::isfinite(x) || !std::isfinite(y)) continue;
+            bbox[0] = fminf(bbox[0], x); bbox[2] = fmaxf(bbox[2], x);
+            bbox[1] = fminf(bbox[1], y); bbox[3] = fmaxf(bbox[3], y);
+        }
+    }
+    rc = set_target_impl(m, m->b_xy.as<float>(), n, on_host ? bbox : nullptr);
     if (rc) return rc;
     return ndt2d_synchronize(m);
 }

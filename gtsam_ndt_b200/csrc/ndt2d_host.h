@@ -61,14 +61,14 @@ struct LevelMem {
     int64_t cap = 0; // cells the allocations can hold (plus the zero records behind the table, see ZERO_PAD)
     // all-zero records behind a dense table: a point outside the lattice gathers records sentinel + {0, 1, njx, njx + 1}
     static int64_t zero_pad(int64_t njx) { return njx + 2; }
+    unsigned char *base = nullptr; // ONE allocation: cells | sums | cnt, each sized for `cap` cells - a new target clears it with one memset
+    size_t bytes = 0;
     void release()
     {
-        if (cells) cudaFree(cells);
-        if (cnt) cudaFree(cnt);
-        if (sums) cudaFree(sums);
+        if (base) cudaFree(base);
         if (dirty) cudaFree(dirty);
-        cells = nullptr; cnt = nullptr; sums = nullptr; dirty = nullptr;
-        cap = 0;
+        base = nullptr; cells = nullptr; cnt = nullptr; sums = nullptr; dirty = nullptr;
+        cap = 0; bytes = 0;
     }
     // Grow-only: scan-to-scan odometry sets a new target of about the same size for every scan, and a
     // cudaFree/cudaMalloc pair per level and call costs more than building the grid.
@@ -77,11 +77,13 @@ struct LevelMem {
         if (nc + pad <= cap) return cudaSuccess;
         release();
         const int64_t want = nc + pad + nc / 4 + 1024;
-        cudaError_t e = cudaMalloc(&cells, (size_t)want * 32);
-        if (e == cudaSuccess) e = cudaMalloc(&cnt, (size_t)want * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&sums, (size_t)want * 40);
+        cudaError_t e = cudaMalloc(&base, (size_t)want * 76);
         if (e != cudaSuccess) { release(); return e; }
+        cells = reinterpret_cast<float4 *>(base);                                            // want * 32 bytes
+        sums = reinterpret_cast<unsigned long long *>(base + (size_t)want * 32);              // want * 40
+        cnt = reinterpret_cast<uint32_t *>(base + (size_t)want * 72);                         // want * 4
         cap = want;
+        bytes = (size_t)want * 76;
         return cudaSuccess;
     }
 };

@@ -661,4 +661,4 @@ def test_errors_are_reported(mods):
         m.set_params(min_points=1)
     n0 = m.kernel_launches
     m.set_target(np.random.default_rng(0).normal(size=(100, 2)).astype(np.float32))
-    assert m.kernel_launches >= n0 + 3
+    assert m.kernel_launches >= n0 + 2          # accumulate + finalise (the bounding box of a small host target is taken on the host)
