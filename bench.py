@@ -504,14 +504,10 @@ def plan_upload_relay(ctx, m, gbs, min_ratio=1.15):
     the share x = (fast - slow) / (fast + slow) of the slow rank's chunks onto the fast rank's link (both links then finish
     together) and from that GPU over NVLink. Single node: a rank's device index is its rank. Returns the plan (same on
     every rank) or None."""
+    from gtsam_ndt_b200 import distributed as D
     if ctx.world < 2 or not gbs or len(gbs) != ctx.world:
         return None
-    order = sorted(range(ctx.world), key=lambda r: gbs[r])
-    pairs = {}
-    for i in range(ctx.world // 2):
-        slow, fast = order[i], order[-1 - i]
-        if gbs[fast] > min_ratio * gbs[slow]:
-            pairs[slow] = (fast, (gbs[fast] - gbs[slow]) / (gbs[fast] + gbs[slow]))
+    pairs = D.upload_relay_pairs(gbs, min_ratio)
     if not pairs:
         return None
     ok = 1.0
@@ -536,10 +532,11 @@ def plan_upload_relay(ctx, m, gbs, min_ratio=1.15):
 def refine_upload_relay(ctx, m, plan, t_ms):
     """One calibration step: t_ms = every rank's e2e step time with the planned relay. A slow rank's time scales with the
     share 1 - x it still copies itself, its partner's with 1 + x; move x to where the two meet."""
+    from gtsam_ndt_b200 import distributed as D
     for slow, v in plan["pairs"].items():
         fast, x = v["via_rank"], v["fraction"]
         ts, tf = t_ms[int(slow)], t_ms[fast]
-        x2 = min(max(x + (ts - tf) / (ts / (1.0 - x) + tf / (1.0 + x)), 0.05), 0.6)
+        x2 = D.refine_relay_fraction(x, ts, tf)
         v["first_fraction"], v["fraction"] = x, round(x2, 3)
         if ctx.rank == int(slow):
             try:

@@ -184,3 +184,27 @@ def align_sharded_counts(nscans):
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     return shard_range(nscans, rank, world)
+
+
+# ---- upload relay between the ranks of a job (ndt2d_set_upload_relay) ---------------------------------------------------------
+
+def upload_relay_pairs(gbs, min_ratio=1.15):
+    """Pair ranks whose host-to-device copy rates differ. gbs[r] = GB/s rank r gets for its step input when every rank copies
+    at the same time (measure it: one plain pinned copy per rank, all at once). The slowest rank is paired with the fastest,
+    the second slowest with the second fastest, ...; a pair whose rates differ by more than min_ratio moves the share
+    x = (fast - slow) / (fast + slow) of the slow rank's input chunks onto the fast rank's PCIe link - with that share both links
+    finish together - and from that GPU over NVLink. Returns {slow_rank: (fast_rank, x)}; pure host logic, the same on every rank."""
+    world = len(gbs)
+    order = sorted(range(world), key=lambda r: gbs[r])
+    pairs = {}
+    for i in range(world // 2):
+        slow, fast = order[i], order[-1 - i]
+        if gbs[fast] > min_ratio * gbs[slow]:
+            pairs[slow] = (fast, (gbs[fast] - gbs[slow]) / (gbs[fast] + gbs[slow]))
+    return pairs
+
+
+def refine_relay_fraction(x, t_slow, t_fast):
+    """One calibration step for a pair: t_slow / t_fast = the two ranks' step times with share x relayed. The slow rank's time
+    scales with the share 1 - x it still copies itself, its partner's with 1 + x; returns the x where the two meet."""
+    return min(max(x + (t_slow - t_fast) / (t_slow / (1.0 - x) + t_fast / (1.0 + x)), 0.05), 0.6)

@@ -102,3 +102,18 @@ def test_sweep_sharded_world2_gloo_matches_unsharded():
     assert all(o[1] for o in out), out
     assert out[0][3] == out[1][3]                      # every rank holds the same global answer
     assert out[0][2] == (0, 51) and out[1][2] == (51, 101)
+
+
+def test_upload_relay_pairs_and_refinement():
+    """Host logic of the upload relay plan (gtsam_ndt_b200.distributed): rates as measured on the 8-GPU box."""
+    from gtsam_ndt_b200 import distributed as D
+    pairs = D.upload_relay_pairs([23.4, 23.5, 23.4, 23.5, 34.9, 35.3, 35.2, 35.3])
+    assert sorted(pairs) == [0, 1, 2, 3] and sorted(f for f, _ in pairs.values()) == [4, 5, 6, 7]
+    assert all(0.19 < x < 0.21 for _, x in pairs.values())
+    assert D.upload_relay_pairs([55.3, 55.4]) == {} and D.upload_relay_pairs([50.0]) == {}
+    assert D.upload_relay_pairs([20.0, 30.0, 40.0]) == {0: (2, (40.0 - 20.0) / 60.0)}       # odd world: the middle rank stays alone
+    x2 = D.refine_relay_fraction(0.2, 11.6, 10.0)
+    assert 0.26 < x2 < 0.28
+    # at the refined share the modelled step times meet
+    assert abs(11.6 / 0.8 * (1 - x2) - 10.0 / 1.2 * (1 + x2)) < 1e-9
+    assert D.refine_relay_fraction(0.5, 30.0, 1.0) == 0.6 and D.refine_relay_fraction(0.1, 1.0, 30.0) == 0.05
