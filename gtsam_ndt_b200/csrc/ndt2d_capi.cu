@@ -95,6 +95,14 @@ int setup_level(ndt2d_matcher *m, int l, const float bbox[4])
 
 int accumulate_and_finalize(ndt2d_matcher *m, const float2 *d_xy, int64_t n)
 {
+    if (m->nlevels > 1) {       // a pyramid: all its levels in one accumulate and one finalise launch
+        LevelSet S;
+        memset(&S, 0, sizeof(S));
+        S.nlevels = m->nlevels;
+        for (int l = 0; l < m->nlevels; ++l) { S.lv[l] = m->lv[l]; S.cells[l] = m->mem[l].cells; }
+        CK(m, launch_build_levels(m->cfg, S, m->prm, d_xy, n, &m->launches));
+        return NDT2D_OK;
+    }
     for (int l = 0; l < m->nlevels; ++l) {
         CK(m, launch_accumulate(m->cfg, m->lv[l], d_xy, n, &m->launches));
         CK(m, launch_finalize(m->cfg, m->lv[l], m->mem[l].cells, m->prm, &m->launches));

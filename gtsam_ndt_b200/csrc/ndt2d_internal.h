@@ -25,6 +25,13 @@ struct LevelDev {
 
 static constexpr unsigned kEmptyKey = 0xffffffffu;
 
+// every level of a target's pyramid, for the kernels that build them in one launch (launch_build_levels)
+struct LevelSet {
+    LevelDev lv[NDT2D_MAX_LEVELS];
+    float4 *cells[NDT2D_MAX_LEVELS];   // the writable record tables (LevelDev::cells is the read-only view)
+    int nlevels;
+};
+
 struct AlignArgs {
     LevelDev lv[NDT2D_MAX_LEVELS];
     int nlevels;
@@ -63,6 +70,8 @@ struct LaunchCfg {
 // all launchers return the cudaError_t of the launch; *launches is incremented per kernel launched
 cudaError_t launch_accumulate(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int64_t n, int64_t *launches);
 cudaError_t launch_finalize(const LaunchCfg &c, const LevelDev &L, float4 *cells_out, const ndt2d_params &p, int64_t *launches);
+// accumulate + finalise every level of S from the same points: two launches whatever the number of levels
+cudaError_t launch_build_levels(const LaunchCfg &c, const LevelSet &S, const ndt2d_params &p, const float2 *d_xy, int64_t n, int64_t *launches);
 cudaError_t launch_add_points(const LaunchCfg &c, const LevelDev &L, float4 *cells_out, const ndt2d_params &p, const float2 *d_xy,
                               int64_t n, unsigned *dirty, unsigned *list, unsigned *nlist, int64_t *launches);
 cudaError_t launch_cell_index(const LaunchCfg &c, const LevelDev &L, const float2 *d_xy, int n, const double *d_pose,

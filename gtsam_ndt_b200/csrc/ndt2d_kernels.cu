@@ -63,6 +63,46 @@ __global__ void __launch_bounds__(256) k_finalize(const LevelDev L, float4 *__re
     }
 }
 
+// The same two kernels for every level of a pyramid in one launch each (blockIdx.y = level): a target SCAN's grids are so
+// small that the launches, not the work, were the cost of building them (sequential scan-to-scan odometry builds three
+// levels per step).
+template <int OV>
+__global__ void __launch_bounds__(256) k_accumulate_levels(const __grid_constant__ LevelSet S, const float2 *__restrict__ xy, int64_t n)
+{
+    const LevelDev &L = S.lv[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (int64_t base = warp_id * 32; base < n; base += warps_total * 32) {
+        const int64_t i = base + lane;
+        float2 p = make_float2(0.0f, 0.0f);
+        if (i < n) p = __ldg(xy + i);
+        accumulate_window<OV>(L, i < n, p.x, p.y, lane, [&](int key, unsigned c, long long sx, long long sy, long long sxx, long long sxy, long long syy) {
+            atomicAdd(L.cnt + key, c);
+            unsigned long long *s = L.sums + 5 * (size_t)key;
+            atomicAdd(s + 0, (unsigned long long)sx);
+            atomicAdd(s + 1, (unsigned long long)sy);
+            atomicAdd(s + 2, (unsigned long long)sxx);
+            atomicAdd(s + 3, (unsigned long long)sxy);
+            atomicAdd(s + 4, (unsigned long long)syy);
+        });
+    }
+}
+
+__global__ void __launch_bounds__(256) k_finalize_levels(const __grid_constant__ LevelSet S, int min_points, double eig_ratio)
+{
+    const LevelDev &L = S.lv[blockIdx.y];
+    float4 *__restrict__ cells = S.cells[blockIdx.y];
+    const int64_t nc = (int64_t)L.njx * L.njy;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+        const long long *s = reinterpret_cast<const long long *>(L.sums) + 5 * c;
+        float4 ra, rb;
+        finalize_record(L.cnt[c], s[0], s[1], s[2], s[3], s[4], L.qu, min_points, eig_ratio, ra, rb);
+        cells[2 * c] = ra;
+        cells[2 * c + 1] = rb;
+    }
+}
+
 // Finalisation of the touched cells only (incremental update): the list is consumed and the dirty words are cleared.
 __global__ void __launch_bounds__(256) k_finalize_list(const LevelDev L, float4 *__restrict__ cells, int min_points, double eig_ratio,
                                                        unsigned *__restrict__ dirty, const unsigned *__restrict__ list,
@@ -600,6 +640,22 @@ cudaError_t launch_add_points(const LaunchCfg &c, const LevelDev &L, float4 *cel
     else k_accumulate<0, true><<<grid, 256, 0, c.stream>>>(L, d_xy, n, dirty, list, nlist);
     k_finalize_list<<<grid_for(n * (L.ov ? 4 : 1), 256, c.sm_count, 8), 256, 0, c.stream>>>(L, cells_out, p.min_points, p.eig_ratio, dirty, list, nlist);
     *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_levels(const LaunchCfg &c, const LevelSet &S, const ndt2d_params &p, const float2 *d_xy, int64_t n, int64_t *launches)
+{
+    int64_t max_nc = 1;
+    for (int l = 0; l < S.nlevels; ++l) max_nc = std::max<int64_t>(max_nc, (int64_t)S.lv[l].njx * S.lv[l].njy);
+    if (n > 0) {
+        dim3 ga(grid_for(n, 256, c.sm_count, 8), S.nlevels);
+        if (S.lv[0].ov) k_accumulate_levels<1><<<ga, 256, 0, c.stream>>>(S, d_xy, n);
+        else k_accumulate_levels<0><<<ga, 256, 0, c.stream>>>(S, d_xy, n);
+        ++*launches;
+    }
+    dim3 gf(grid_for(max_nc, 256, c.sm_count, 8), S.nlevels);
+    k_finalize_levels<<<gf, 256, 0, c.stream>>>(S, p.min_points, p.eig_ratio);
+    ++*launches;
     return cudaGetLastError();
 }
 
