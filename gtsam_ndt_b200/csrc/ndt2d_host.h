@@ -134,7 +134,9 @@ struct ndt2d_matcher {
     static constexpr size_t FAST_BYTES = 256 << 10;
     static constexpr int FAST_SCANS = 256, RING = 4096;
     bool fast_ready = false;                 // every allocation of the fast path exists and the ring is zeroed
-    unsigned char *fast_host = nullptr;      // pinned, FAST_BYTES
+    unsigned char *fast_host = nullptr;      // pinned + mapped, FAST_BYTES
+    unsigned char *fast_host_dev = nullptr;  // its device address: small xy calls are staged by the kernel from there (NDT2D_FAST_ZEROCOPY=0: copied first)
+    bool fast_zerocopy = true;
     ndt2d_result *fast_res = nullptr;        // pinned + mapped, FAST_SCANS records
     ndt2d_result *fast_res_dev = nullptr;    // its device address
     ndt2d::DevBuf b_fast, b_ring;
